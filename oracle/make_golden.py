@@ -1,0 +1,165 @@
+"""TEST INFRASTRUCTURE ONLY -- generate tests/golden/*.npz from the reference itself.
+
+Run in the build container (needs /root/reference):
+
+    python oracle/make_golden.py
+
+Every fixture is the output of the reference's *own* code (AST-extracted, unmodified --
+see oracle/ref_extract.py) on seeded inputs that are stored next to it, so the tests can
+run anywhere without the reference tree.  Large outputs are stored decimated together
+with whole-array checksums (sum, sum of squares) so fixtures stay small.
+"""
+from __future__ import annotations
+
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "nis-sar-amtigmti-video_b200"))
+
+from oracle import ref_extract  # noqa: E402
+from nis_sar import scenes, params  # noqa: E402
+
+OUT = os.path.join(ROOT, "tests", "golden")
+
+
+def _as_targets(pos, rcs):
+    return [{"position": np.array(p), "rcs": float(r)} for p, r in zip(pos, rcs)]
+
+
+def _digest(a, step):
+    a = np.asarray(a)
+    flat = a.ravel()
+    return {"dec": flat[::step].copy(), "sum": np.sum(flat), "sumsq": np.sum(np.abs(flat) ** 2),
+            "shape": np.array(a.shape)}
+
+
+def golden_vehicle_targets():
+    gens = ref_extract.vehicle_target_generators()
+    out = {}
+    center = (12.5, -40.0, 3.0)
+    for name, fn in gens.items():
+        t = fn(center_pos=center)
+        out[f"{name}_pos"] = np.array([x["position"] for x in t], dtype=np.float64)
+        out[f"{name}_rcs"] = np.array([x["rcs"] for x in t], dtype=np.float64)
+    out["center"] = np.array(center)
+    np.savez_compressed(os.path.join(OUT, "vehicle_targets.npz"), **out)
+
+
+def golden_echo():
+    # (1) bistatic engine at reduced sample rate: full arrays.
+    prm = params.spaceborne_preset(fs=60e6, bw=50e6)
+    sc = scenes.ati_scene(seed=11, num_pulses=8, num_clutter=20, prm=prm)
+    bist, _ = ref_extract.ati_csa_functions(prm.as_globals())
+    raw_ship, t0 = bist(_as_targets(sc["ship_pos"], sc["ship_rcs"]), sc["t_vec"], sc["pos_tx"], sc["vel_tx"],
+                        sc["rx_offsets"][0], sc["ship_vel"])
+    raw_clut, _ = bist(_as_targets(sc["clutter_pos"], sc["clutter_rcs"]), sc["t_vec"], sc["pos_tx"], sc["vel_tx"],
+                       sc["rx_offsets"][1], sc["clutter_vel"])
+    np.savez_compressed(os.path.join(OUT, "echo_bistatic_fs60.npz"),
+                        fs=60e6, bw=50e6, seed=11, num_pulses=8, num_clutter=20,
+                        raw_ship_rx1=raw_ship, raw_clutter_rx2=raw_clut, t_start_fast=t0)
+
+    # (2) bistatic engine at the true 600 MHz parameters: decimated + checksums + support.
+    prm = params.spaceborne_preset()
+    sc = scenes.ati_scene(seed=12, num_pulses=3, num_clutter=30, prm=prm)
+    bist, _ = ref_extract.ati_csa_functions(prm.as_globals())
+    pos = np.concatenate([sc["ship_pos"], sc["clutter_pos"]])
+    rcs = np.concatenate([sc["ship_rcs"], sc["clutter_rcs"]])
+    raw, t0 = bist(_as_targets(pos, rcs), sc["t_vec"], sc["pos_tx"], sc["vel_tx"], sc["rx_offsets"][0], sc["ship_vel"])
+    d = _digest(raw, 7)
+    nz = raw != 0
+    np.savez_compressed(os.path.join(OUT, "echo_bistatic_fs600.npz"), seed=12, num_pulses=3, num_clutter=30,
+                        dec=d["dec"], step=7, sum=d["sum"], sumsq=d["sumsq"], shape=d["shape"], t_start_fast=t0,
+                        first_nz=np.argmax(nz, axis=1), last_nz=raw.shape[1] - 1 - np.argmax(nz[:, ::-1], axis=1))
+
+    # (3) monostatic engines (S is hard-wired to 13200 / 2048 inside them).
+    g = prm.as_globals()
+    sat = scenes.stripmap_scene(num_pulses=2, num_samples=13200, n_side=3, half_extent=400.0)
+    eng = ref_extract.satellite_engine(g)
+    raw, t0, fs = eng(_as_targets(sat["pos"], sat["rcs"]), sat["pos_sat"], sat["t_vec"])
+    d = _digest(raw, 5)
+    np.savez_compressed(os.path.join(OUT, "echo_satellite.npz"), dec=d["dec"], step=5, sum=d["sum"],
+                        sumsq=d["sumsq"], shape=d["shape"], t_start_fast=t0, fs=fs)
+
+    mov = ref_extract.moving_engine(g)
+    vel = [4.0, -9.0, 0.0]
+    raw, t0, fs = mov(_as_targets(sc["ship_pos"], sc["ship_rcs"]), sat["t_vec"], sat["pos_sat"], vel)
+    d = _digest(raw, 5)
+    np.savez_compressed(os.path.join(OUT, "echo_moving.npz"), dec=d["dec"], step=5, sum=d["sum"],
+                        sumsq=d["sumsq"], shape=d["shape"], t_start_fast=t0, fs=fs, vel=np.array(vel))
+
+    vp = params.airborne_vehicle_preset()
+    veh = scenes.vehicle_scene(seed=5, num_pulses=4, num_scatterers=60)
+    # spread the 4 pulses over the real aperture so the range history actually changes
+    t_vec = np.linspace(-8.0, 8.0, 4)
+    pos_plat, _ = scenes.straight_trajectory(vp, t_vec)
+    ve = ref_extract.vehicle_engine(vp.as_globals())
+    raw = ve(_as_targets(veh["pos"], veh["rcs"]), t_vec, pos_plat, 500e-6, vp.T_p, vp.FC, vp.BW)
+    np.savez_compressed(os.path.join(OUT, "echo_vehicle.npz"), raw=raw, t_vec=t_vec, seed=5, num_scatterers=60)
+
+
+def golden_csa():
+    prm = params.spaceborne_preset()
+    _, csa = ref_extract.ati_csa_functions(prm.as_globals())
+    rng = np.random.default_rng(2024)
+    out = {}
+    for tag, (n_az, n_rg) in {"p2": (64, 128), "odd": (45, 88), "prime": (31, 101)}.items():
+        x = (rng.standard_normal((n_az, n_rg)) + 1j * rng.standard_normal((n_az, n_rg))).astype(np.complex64)
+        img, rax, cax = csa(x.astype(np.complex128), prm.Lambda, prm.T_p, prm.k_rate, prm.FS, prm.PRF,
+                            prm.V_eff, prm.R0, prm.t_start_fast)
+        assert img.shape == (n_rg, n_az) and img.flags.f_contiguous
+        out[f"{tag}_in"] = x
+        out[f"{tag}_img"] = np.ascontiguousarray(img)
+        out[f"{tag}_rax"] = rax
+        out[f"{tag}_cax"] = cax
+    np.savez_compressed(os.path.join(OUT, "csa_random.npz"), **out)
+
+
+def golden_chain():
+    """Reduced default scene end to end through the reference: 2-channel echo, pulse shift,
+    CSA x2, inline ATI/DPCA products.  Stored as digests."""
+    prm = params.spaceborne_preset()
+    P = 64
+    sc = scenes.ati_scene(seed=7, num_pulses=P, num_clutter=40, prm=prm)
+    bist, csa = ref_extract.ati_csa_functions(prm.as_globals())
+    ship = _as_targets(sc["ship_pos"], sc["ship_rcs"])
+    clut = _as_targets(sc["clutter_pos"], sc["clutter_rcs"])
+    raws = []
+    for off in sc["rx_offsets"]:
+        a, t0 = bist(ship, sc["t_vec"], sc["pos_tx"], sc["vel_tx"], off, sc["ship_vel"])
+        b, _ = bist(clut, sc["t_vec"], sc["pos_tx"], sc["vel_tx"], off, sc["clutter_vel"])
+        raws.append(a + b)
+    rx1, rx2 = raws[0][1:, :], raws[1][:-1, :]           # sar_ati_dcpa_sim_csa.py:402-403
+    slc1, rax, cax = csa(rx1, prm.Lambda, prm.T_p, prm.k_rate, prm.FS, prm.PRF, prm.V_eff, prm.R0, t0)
+    slc2, _, _ = csa(rx2, prm.Lambda, prm.T_p, prm.k_rate, prm.FS, prm.PRF, prm.V_eff, prm.R0, t0)
+    prod = ref_extract.ati_inline_products(slc1, slc2)
+    step = 97
+    mag = prod["slc1_mag"]
+    thr = mag.max() * 0.05
+    np.savez_compressed(
+        os.path.join(OUT, "chain_ati_p64.npz"), seed=7, num_pulses=P, num_clutter=40, step=step,
+        slc1_dec=np.ascontiguousarray(slc1).ravel()[::step], slc2_dec=np.ascontiguousarray(slc2).ravel()[::step],
+        slc1_sumsq=np.sum(np.abs(slc1) ** 2), slc2_sumsq=np.sum(np.abs(slc2) ** 2),
+        interf_dec=np.ascontiguousarray(prod["ati_interf"]).ravel()[::step],
+        phase_dec=np.ascontiguousarray(prod["ati_phase"]).ravel()[::step],
+        dpca_mag_dec=np.ascontiguousarray(prod["dpca_mag"]).ravel()[::step],
+        det_idx=np.flatnonzero(prod["mag_mask"]), peak_idx=int(np.argmax(mag)),
+        phase_at_det=prod["ati_phase_masked"][prod["mag_mask"]],
+        margin=float(np.min(np.abs(mag - thr)) / thr), shape=np.array(slc1.shape),
+        rax=rax, cax=cax, t_start_fast=t0,
+        f_contiguous=bool(slc1.flags.f_contiguous))
+
+
+if __name__ == "__main__":
+    if not ref_extract.reference_available():
+        sys.exit("reference tree not found: fixtures can only be regenerated in the build container")
+    os.makedirs(OUT, exist_ok=True)
+    golden_vehicle_targets()
+    golden_echo()
+    golden_csa()
+    golden_chain()
+    for f in sorted(os.listdir(OUT)):
+        print(f, os.path.getsize(os.path.join(OUT, f)))

@@ -1,0 +1,200 @@
+"""TEST INFRASTRUCTURE ONLY -- numpy (fp64) restatement of the reference hot path.
+
+Each function names the reference lines whose arithmetic it follows.  It is a
+restatement (written from the maths, broadcasting instead of meshgrid copies),
+not a copy; ``tests/test_oracle_golden.py`` pins it to vectors produced by the
+reference's own functions (``oracle/make_golden.py``).
+
+Radar constants arrive as a plain dict ``g`` with the names of the reference's
+module globals: ``C, R0, FC, BW, T_p, FS`` (sar_ati_dcpa_sim_csa.py:18-38).
+"""
+from __future__ import annotations
+
+import numpy as np
+
+C_LIGHT = 299792458.0
+
+
+# --------------------------------------------------------------------------- echo
+def fast_time_axis(t_start: float, n_samples: int, fs: float) -> np.ndarray:
+    """Receive-window sample times.  The grid is ``linspace(0, S/fs, S)`` -- S points
+    *including* the end point, so the step is S/((S-1) fs), not 1/fs
+    (sar_ati_dcpa_sim_csa.py:113-114; sar_satellite_sim.py:254-255;
+    sar_vehicle_sim.py:88,100)."""
+    return t_start + np.linspace(0.0, n_samples / fs, n_samples)
+
+
+def window_start_satellite(g: dict) -> float:
+    """Window opens 1 us + T_p/2 before the scene-centre echo
+    (sar_ati_dcpa_sim_csa.py:112; sar_satellite_sim.py:252)."""
+    return (2 * g["R0"] / g["C"]) - (g["T_p"] / 2) - 1e-6
+
+
+def _accumulate_pulse(t_fast, tau, phase0, amp, t_p, k_rate, block=256):
+    """One pulse row: sum_b amp_b exp(j(phase0_b + pi k (t - tau_b - T_p/2)^2)) gated to the
+    closed interval |t - tau_b - T_p/2| <= T_p/2 (sar_ati_dcpa_sim_csa.py:163-176)."""
+    row = np.zeros(t_fast.shape[0], dtype=np.complex128)
+    half = t_p / 2
+    for b0 in range(0, tau.shape[0], block):
+        sl = slice(b0, b0 + block)
+        u = (t_fast[None, :] - tau[sl, None]) - half
+        gate = np.abs(u) <= half
+        arg = phase0[sl, None] + np.pi * k_rate * (u ** 2)
+        row += np.sum(amp[sl, None] * np.exp(1j * arg) * gate, axis=0)
+    return row
+
+
+def echo_bistatic(pos0, rcs, t_slow, pos_tx, vel_tx, rx_offset, vel_target, g, n_samples=None):
+    """Two-phase-centre chirp echo of ``run_bistatic_physics_gpu``
+    (sar_ati_dcpa_sim_csa.py:106-181).  Receiver sits ``rx_offset`` metres along the
+    unit velocity from the transmitter (:145-148); every scatterer of the call moves
+    with the one ``vel_target`` (:151); delay is (|p-p_tx| + |p-p_rx|)/C (:154-159);
+    carrier phase -2 pi FC tau (:160); amplitude sqrt(rcs) (:171).
+    Returns (raw[P, S] complex128, t_start_fast)."""
+    pos0 = np.asarray(pos0, dtype=np.float64).reshape(-1, 3)
+    rcs = np.asarray(rcs, dtype=np.float64).reshape(-1)
+    vel_target = np.asarray(vel_target, dtype=np.float64).reshape(3)
+    S = int(22e-6 * g["FS"]) if n_samples is None else int(n_samples)
+    t0 = window_start_satellite(g)
+    t_fast = fast_time_axis(t0, S, g["FS"])
+    k_rate = g["BW"] / g["T_p"]
+    amp = np.sqrt(rcs)
+    raw = np.zeros((len(t_slow), S), dtype=np.complex128)
+    for i in range(len(t_slow)):
+        p_tx = np.asarray(pos_tx[i], dtype=np.float64)
+        v = np.asarray(vel_tx[i], dtype=np.float64)
+        p_rx = p_tx + (v / np.sqrt(np.sum(v * v))) * rx_offset
+        p = pos0 + vel_target[None, :] * t_slow[i]
+        d_tx = np.sqrt(np.sum((p - p_tx) ** 2, axis=1))
+        d_rx = np.sqrt(np.sum((p - p_rx) ** 2, axis=1))
+        tau = (d_tx + d_rx) / g["C"]
+        raw[i] = _accumulate_pulse(t_fast, tau, -2.0 * np.pi * g["FC"] * tau, amp, g["T_p"], k_rate)
+    return raw, t0
+
+
+def echo_monostatic(pos0, rcs, t_slow, pos_sat, g, vel_target=None, n_samples=None,
+                    fs=None, t_start=None, t_p=None, fc=None, bw=None):
+    """Monostatic engines: ``run_physics_engine`` (sar_satellite_sim.py:211-305, static
+    scatterers), ``run_moving_physics`` (sar_satellite_moving_sim.py:111-159, p = p0 + v t
+    at :138) and ``run_custom_physics`` (sar_vehicle_sim.py:83-126, fs=360 MHz, S=2048,
+    window centred on 2 R0/C at :89).  tau = 2 d / C, carrier phase -4 pi FC d / C
+    (sar_satellite_sim.py:273-274)."""
+    pos0 = np.asarray(pos0, dtype=np.float64).reshape(-1, 3)
+    rcs = np.asarray(rcs, dtype=np.float64).reshape(-1)
+    fs = 600e6 if fs is None else fs
+    t_p = g["T_p"] if t_p is None else t_p
+    fc = g["FC"] if fc is None else fc
+    bw = g["BW"] if bw is None else bw
+    S = int(22e-6 * fs) if n_samples is None else int(n_samples)
+    t0 = window_start_satellite(g) if t_start is None else t_start
+    t_fast = fast_time_axis(t0, S, fs)
+    k_rate = bw / t_p
+    amp = np.sqrt(rcs)
+    vt = None if vel_target is None else np.asarray(vel_target, dtype=np.float64).reshape(3)
+    raw = np.zeros((len(t_slow), S), dtype=np.complex128)
+    for i in range(len(t_slow)):
+        p = pos0 if vt is None else pos0 + vt * t_slow[i]
+        d = np.sqrt(np.sum((p - np.asarray(pos_sat[i], dtype=np.float64)) ** 2, axis=1))
+        tau = 2 * d / g["C"]
+        raw[i] = _accumulate_pulse(t_fast, tau, -4.0 * np.pi * fc * d / g["C"], amp, t_p, k_rate)
+    return raw, t0, fs
+
+
+def vehicle_window_start(g: dict, n_samples: int = 2048, fs: float = 360e6) -> float:
+    """sar_vehicle_sim.py:89 -- window centred on the scene-centre delay."""
+    return (2 * g["R0"] / g["C"]) - (n_samples / fs) / 2
+
+
+# ---------------------------------------------------------------------------- CSA
+def csa_axes(n_az, n_rg, lam, fs, prf, vr, r_ref, t_start):
+    """Axes and per-Doppler scalars of ``sar_focus_csa`` (sar_ati_dcpa_sim_csa.py:217-262):
+    tau_n = t_start + n/fs (:219), shifted frequency axes (:222-235, :281), migration factor
+    D(fa) = sqrt(1 - (lam fa / 2 Vr)^2) with negative arguments clamped to 1e-9 (:244-247),
+    Cs = 1/D - 1 (:249), tau_ref = 2 R_ref / (c D) (:262)."""
+    dt = 1.0 / fs
+    tau = t_start + np.arange(n_rg) * dt
+    fr = np.fft.fftshift(np.fft.fftfreq(n_rg, dt))
+    fa = np.fft.fftshift(np.fft.fftfreq(n_az, 1.0 / prf))
+    arg = 1.0 - (lam * fa / (2.0 * vr)) ** 2
+    arg[arg < 0] = 1e-9
+    d = np.sqrt(arg)
+    cs = (1.0 / d) - 1.0
+    tau_ref = 2.0 * r_ref / (C_LIGHT * d)
+    return tau, fr, fa, d, cs, tau_ref
+
+
+def focus_csa(phist, lam, kr, fs, prf, vr, r_ref, t_start):
+    """Chirp Scaling focusing, ``sar_focus_csa`` (sar_ati_dcpa_sim_csa.py:202-396).
+
+    azimuth FFT + shift (:233-234) -> x Phi1 = exp(-j pi Kr Cs (tau - tau_ref)^2) (:272-274)
+    -> range FFT + shift (:278-280) -> x Phi2 = exp(j(pi fr^2/(Kr(1+Cs)) + 4 pi R_ref Cs fr/c))
+    (:318-326) -> unshift + range IFFT (:331) -> x Phi3 = exp(j(4 pi R D/lam
+    - pi Kr Cs(1+Cs)(tau - 2 R_ref/c)^2)), R = c tau/2 (:346-382) -> unshift + azimuth IFFT (:385).
+    Returns (img.T  -- an [N_rg, N_az] view --, range_axis, cross_range_axis) (:392-396)."""
+    phist = np.asarray(phist)
+    n_az, n_rg = phist.shape
+    tau, fr, fa, d, cs, tau_ref = csa_axes(n_az, n_rg, lam, fs, prf, vr, r_ref, t_start)
+    c = C_LIGHT
+    csc = cs[:, None]
+
+    s = np.fft.fftshift(np.fft.fft(phist, axis=0), axes=0)
+    s = s * np.exp(-1j * np.pi * kr * csc * (tau[None, :] - tau_ref[:, None]) ** 2)
+
+    s = np.fft.fftshift(np.fft.fft(s, axis=1), axes=1)
+    frr = fr[None, :]
+    s = s * np.exp(1j * (np.pi * (frr ** 2) / (kr * (1.0 + csc)) + 4.0 * np.pi * r_ref * csc * frr / c))
+
+    s = np.fft.ifft(np.fft.ifftshift(s, axes=1), axis=1)
+    rng = c * tau / 2.0
+    resid = -np.pi * kr * csc * (1.0 + csc) * ((tau[None, :] - (2.0 * r_ref / c)) ** 2)
+    s = s * np.exp(1j * (4.0 * np.pi * rng[None, :] * d[:, None] / lam + resid))
+
+    img = np.fft.ifft(np.fft.ifftshift(s, axes=0), axis=0)
+    t_slow = np.arange(n_az) / prf
+    t_slow -= np.mean(t_slow)
+    return img.T, rng, t_slow * vr
+
+
+# --------------------------------------------------------------------------- GMTI
+def dpca_coregister(raw_rx1, raw_rx2):
+    """One-pulse shift that aligns the two phase centres (sar_ati_dcpa_sim_csa.py:402-403)."""
+    return raw_rx1[1:, :], raw_rx2[:-1, :]
+
+
+def gmti_products(slc1, slc2, thresh_frac=0.05, cal_phase=0.0):
+    """ATI / DPCA products (sar_ati_dcpa_sim_csa.py:414-419, :447-449) with the viewer's
+    optional channel balance s2 * exp(j cal) (sar_ati_dcpa_viewer_csa.py:43).
+    Detected pixels = flatnonzero(|slc1| > thresh_frac * max|slc1|) in row-major order of
+    the [N_rg, N_az] array; peak = first argmax |slc1|."""
+    slc1 = np.asarray(slc1)
+    s2 = np.asarray(slc2)
+    if cal_phase != 0.0:
+        s2 = s2 * np.exp(1j * cal_phase)
+    interf = slc1 * np.conj(s2)
+    phase = np.angle(interf)
+    mag1 = np.abs(slc1)
+    diff = slc1 - s2
+    dmag = np.abs(diff)
+    mask = mag1 > (np.max(mag1) * thresh_frac)
+    phase_masked = np.copy(phase)
+    phase_masked[~mask] = 0
+    return {
+        "ati_interf": interf, "ati_phase": phase, "slc1_mag": mag1,
+        "dpca_diff": diff, "dpca_mag": dmag, "mag_mask": mask,
+        "ati_phase_masked": phase_masked,
+        "det_idx": np.flatnonzero(mask),
+        "peak_idx": int(np.argmax(mag1)),
+    }
+
+
+def balance_phase(slc1, slc2):
+    """Viewer auto-balance: angle(mean(slc1 conj(slc2))) (sar_ati_dcpa_viewer_csa.py:249-250)."""
+    return float(np.angle(np.mean(np.asarray(slc1) * np.conj(np.asarray(slc2)))))
+
+
+def threshold_margin(slc1, thresh_frac=0.05):
+    """Smallest relative distance of any pixel magnitude to the detection threshold --
+    reported next to every bit-exact index comparison so a flip is attributable."""
+    mag = np.abs(np.asarray(slc1)).ravel()
+    thr = mag.max() * thresh_frac
+    return float(np.min(np.abs(mag - thr)) / thr)

@@ -1,0 +1,156 @@
+"""The numpy oracle held to vectors produced by the reference's own code
+(oracle/make_golden.py ran the AST-extracted reference functions in the build container)."""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import sar_oracle as orc
+from nis_sar import params, scenes, targets
+
+from conftest import GOLDEN
+
+
+def _load(name):
+    return np.load(os.path.join(GOLDEN, name))
+
+
+def _rel(a, b):
+    return float(np.linalg.norm(np.ravel(a) - np.ravel(b)) / np.linalg.norm(np.ravel(b)))
+
+
+def test_vehicle_generators_match_reference():
+    g = _load("vehicle_targets.npz")
+    center = tuple(g["center"])
+    for name in ("generate_car", "generate_tank", "generate_fighter_jet", "generate_f35", "generate_destroyer"):
+        pos, rcs = targets.targets_to_arrays(getattr(targets, name)(center_pos=center))
+        assert np.array_equal(pos, g[f"{name}_pos"]), name
+        assert np.array_equal(rcs, g[f"{name}_rcs"]), name
+
+
+def test_destroyer_inventory():
+    t = targets.generate_destroyer()
+    assert len(t) == 35 and sum(x["rcs"] for x in t) == 43000.0
+    assert set(t[0]) == {"position", "rcs", "name"}
+
+
+def test_echo_bistatic_reduced_rate():
+    g = _load("echo_bistatic_fs60.npz")
+    prm = params.spaceborne_preset(fs=float(g["fs"]), bw=float(g["bw"]))
+    sc = scenes.ati_scene(seed=int(g["seed"]), num_pulses=int(g["num_pulses"]),
+                          num_clutter=int(g["num_clutter"]), prm=prm)
+    raw, t0 = orc.echo_bistatic(sc["ship_pos"], sc["ship_rcs"], sc["t_vec"], sc["pos_tx"], sc["vel_tx"],
+                                sc["rx_offsets"][0], sc["ship_vel"], prm.as_globals())
+    assert t0 == float(g["t_start_fast"])
+    assert raw.shape == g["raw_ship_rx1"].shape == (8, 1320)
+    # carrier phase is ~2e8 rad: fp64 evaluation-order noise is ~1e-8
+    assert _rel(raw, g["raw_ship_rx1"]) < 2e-7
+    assert np.array_equal(raw != 0, g["raw_ship_rx1"] != 0)
+    raw2, _ = orc.echo_bistatic(sc["clutter_pos"], sc["clutter_rcs"], sc["t_vec"], sc["pos_tx"], sc["vel_tx"],
+                                sc["rx_offsets"][1], sc["clutter_vel"], prm.as_globals())
+    assert _rel(raw2, g["raw_clutter_rx2"]) < 2e-7
+
+
+def test_echo_bistatic_full_rate_digest():
+    g = _load("echo_bistatic_fs600.npz")
+    prm = params.spaceborne_preset()
+    sc = scenes.ati_scene(seed=int(g["seed"]), num_pulses=int(g["num_pulses"]),
+                          num_clutter=int(g["num_clutter"]), prm=prm)
+    pos = np.concatenate([sc["ship_pos"], sc["clutter_pos"]])
+    rcs = np.concatenate([sc["ship_rcs"], sc["clutter_rcs"]])
+    raw, t0 = orc.echo_bistatic(pos, rcs, sc["t_vec"], sc["pos_tx"], sc["vel_tx"], sc["rx_offsets"][0],
+                                sc["ship_vel"], prm.as_globals())
+    assert tuple(g["shape"]) == raw.shape == (3, 13200)
+    assert _rel(raw.ravel()[::int(g["step"])], g["dec"]) < 2e-7
+    assert abs(np.sum(np.abs(raw) ** 2) - float(g["sumsq"])) / float(g["sumsq"]) < 1e-9
+    nz = raw != 0
+    assert np.array_equal(np.argmax(nz, axis=1), g["first_nz"])
+    assert np.array_equal(raw.shape[1] - 1 - np.argmax(nz[:, ::-1], axis=1), g["last_nz"])
+
+
+def test_echo_monostatic_engines():
+    prm = params.spaceborne_preset()
+    g = _load("echo_satellite.npz")
+    sat = scenes.stripmap_scene(num_pulses=2, num_samples=13200, n_side=3, half_extent=400.0)
+    raw, t0, fs = orc.echo_monostatic(sat["pos"], sat["rcs"], sat["t_vec"], sat["pos_sat"], prm.as_globals())
+    assert fs == float(g["fs"]) and t0 == float(g["t_start_fast"])
+    assert _rel(raw.ravel()[::int(g["step"])], g["dec"]) < 2e-7
+
+    g = _load("echo_moving.npz")
+    ship_pos, ship_rcs = targets.targets_to_arrays(targets.generate_destroyer())
+    raw, _, _ = orc.echo_monostatic(ship_pos, ship_rcs, sat["t_vec"], sat["pos_sat"], prm.as_globals(),
+                                    vel_target=g["vel"])
+    assert _rel(raw.ravel()[::int(g["step"])], g["dec"]) < 2e-7
+    assert abs(np.sum(np.abs(raw) ** 2) - float(g["sumsq"])) / float(g["sumsq"]) < 1e-9
+
+
+def test_echo_vehicle_engine():
+    g = _load("echo_vehicle.npz")
+    vp = params.airborne_vehicle_preset()
+    veh = scenes.vehicle_scene(seed=int(g["seed"]), num_pulses=4, num_scatterers=int(g["num_scatterers"]))
+    t_vec = g["t_vec"]
+    pos_plat, _ = scenes.straight_trajectory(vp, t_vec)
+    gl = vp.as_globals()
+    raw, _, _ = orc.echo_monostatic(veh["pos"], veh["rcs"], t_vec, pos_plat, gl, n_samples=2048, fs=360e6,
+                                    t_start=orc.vehicle_window_start(gl), t_p=vp.T_p, fc=vp.FC, bw=vp.BW)
+    assert raw.shape == g["raw"].shape == (4, 2048)
+    assert _rel(raw, g["raw"]) < 2e-7
+    assert np.array_equal(raw != 0, g["raw"] != 0)
+
+
+@pytest.mark.parametrize("tag", ["p2", "odd", "prime"])
+def test_csa_matches_reference(tag):
+    g = _load("csa_random.npz")
+    prm = params.spaceborne_preset()
+    x = g[f"{tag}_in"].astype(np.complex128)
+    img, rax, cax = orc.focus_csa(x, prm.Lambda, prm.k_rate, prm.FS, prm.PRF, prm.V_eff, prm.R0, prm.t_start_fast)
+    assert img.shape == g[f"{tag}_img"].shape == (x.shape[1], x.shape[0])
+    assert img.flags.f_contiguous            # img.T is a view (sar_ati_dcpa_sim_csa.py:396)
+    assert _rel(img, g[f"{tag}_img"]) < 1e-9
+    assert np.allclose(rax, g[f"{tag}_rax"], rtol=0, atol=0)
+    assert np.allclose(cax, g[f"{tag}_cax"], rtol=1e-15, atol=1e-12)
+
+
+def test_chain_digest():
+    """Reduced default scene: echo x2 channels -> pulse shift -> CSA x2 -> ATI/DPCA products."""
+    g = _load("chain_ati_p64.npz")
+    prm = params.spaceborne_preset()
+    sc = scenes.ati_scene(seed=int(g["seed"]), num_pulses=int(g["num_pulses"]),
+                          num_clutter=int(g["num_clutter"]), prm=prm)
+    gl = prm.as_globals()
+    raws = []
+    for off in sc["rx_offsets"]:
+        a, t0 = orc.echo_bistatic(sc["ship_pos"], sc["ship_rcs"], sc["t_vec"], sc["pos_tx"], sc["vel_tx"], off,
+                                  sc["ship_vel"], gl)
+        b, _ = orc.echo_bistatic(sc["clutter_pos"], sc["clutter_rcs"], sc["t_vec"], sc["pos_tx"], sc["vel_tx"], off,
+                                 sc["clutter_vel"], gl)
+        raws.append(a + b)
+    rx1, rx2 = orc.dpca_coregister(raws[0], raws[1])
+    slc1, rax, cax = orc.focus_csa(rx1, prm.Lambda, prm.k_rate, prm.FS, prm.PRF, prm.V_eff, prm.R0, t0)
+    slc2, _, _ = orc.focus_csa(rx2, prm.Lambda, prm.k_rate, prm.FS, prm.PRF, prm.V_eff, prm.R0, t0)
+    prod = orc.gmti_products(slc1, slc2)
+    step = int(g["step"])
+    assert tuple(g["shape"]) == slc1.shape == (13200, 63)
+    assert _rel(np.ascontiguousarray(slc1).ravel()[::step], g["slc1_dec"]) < 1e-6
+    assert _rel(np.ascontiguousarray(slc2).ravel()[::step], g["slc2_dec"]) < 1e-6
+    assert _rel(np.ascontiguousarray(prod["ati_interf"]).ravel()[::step], g["interf_dec"]) < 1e-6
+    assert _rel(np.ascontiguousarray(prod["dpca_mag"]).ravel()[::step], g["dpca_mag_dec"]) < 1e-5
+    # detections and peak are bit-exact against the reference (threshold margin is stored)
+    assert float(g["margin"]) > 1e-7
+    assert np.array_equal(prod["det_idx"], g["det_idx"])
+    assert prod["peak_idx"] == int(g["peak_idx"])
+    assert np.max(np.abs(np.angle(np.exp(1j * (prod["ati_phase_masked"][prod["mag_mask"]] - g["phase_at_det"]))))) < 1e-5
+
+
+def test_gmti_definitions_small():
+    rng = np.random.default_rng(3)
+    s1 = rng.standard_normal((7, 5)) + 1j * rng.standard_normal((7, 5))
+    s2 = rng.standard_normal((7, 5)) + 1j * rng.standard_normal((7, 5))
+    p = orc.gmti_products(s1, s2, thresh_frac=0.5)
+    assert p["mag_mask"].dtype == np.bool_
+    assert np.all(p["ati_phase_masked"][~p["mag_mask"]] == 0)
+    assert np.array_equal(p["det_idx"], np.flatnonzero(np.abs(s1) > 0.5 * np.abs(s1).max()))
+    # strict '>' : the peak pixel itself is detected, a pixel exactly at the threshold is not
+    s1b = np.array([[2.0 + 0j, 1.0 + 0j, 0.5 + 0j]])
+    pb = orc.gmti_products(s1b, s1b, thresh_frac=0.5)
+    assert list(pb["det_idx"]) == [0]
