@@ -1,0 +1,165 @@
+/*
+ * nis_sar.h -- C ABI of libnis_sar.so: the B200 (sm_100a) SAR hot path.
+ *
+ * The reference (noiseinspacechannel/NIS-SAR-AMTIGMTI-Video) has no FFI: its boundary is a set of
+ * Python functions and inline numpy expressions.  Each entry point below names the reference code
+ * it replaces (file:line, relative to the reference root).  INTEGRATION.md shows the ctypes stub a
+ * maintainer of the reference would add.
+ *
+ * Conventions
+ *   - every function returns 0 (NIS_OK) or a negative error class; the message is read with
+ *     nis_last_error() (thread-local).  Nothing throws across this boundary.
+ *   - pointers marked "dev" are CUDA device pointers owned by the CALLER (a torch tensor's
+ *     data_ptr() is fine); the library owns only ctx / plan handles and their private workspace.
+ *   - all work is enqueued on the given cudaStream_t (passed as void*) and is asynchronous;
+ *     the only hidden synchronisations are the explicitly named *_readback helpers.
+ *   - there is NO CPU fallback: without a CUDA device nis_ctx_create() fails.
+ *   - complex samples are interleaved (re, im) float32 pairs ("c32") on the device.
+ */
+#ifndef NIS_SAR_H
+#define NIS_SAR_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NIS_SAR_ABI_VERSION 1
+
+#if defined(__GNUC__)
+#define NIS_API __attribute__((visibility("default")))
+#else
+#define NIS_API
+#endif
+
+enum {
+    NIS_OK = 0,
+    NIS_ERR_INVALID = -1,      /* bad argument */
+    NIS_ERR_CUDA = -2,         /* CUDA runtime error (message has the cudaError string) */
+    NIS_ERR_UNSUPPORTED = -3,  /* size / mode not supported by this build */
+    NIS_ERR_NOMEM = -4
+};
+
+typedef struct nis_ctx nis_ctx;
+typedef struct nis_csa_plan nis_csa_plan;
+typedef struct { float re, im; } nis_c32;
+typedef void* nis_stream; /* cudaStream_t */
+
+/* ------------------------------------------------------------------ library / context */
+NIS_API int nis_version(void);
+/* copies the calling thread's last error message (NUL terminated) and returns its length */
+NIS_API size_t nis_last_error(char* buf, size_t cap);
+/* one context per device; owns scratch used by nis_gmti_fused */
+NIS_API int nis_ctx_create(int device, nis_ctx** out);
+NIS_API int nis_ctx_destroy(nis_ctx* ctx);
+/* number of kernels this library has launched on ctx since creation (bench.py "gpu_launches") */
+NIS_API uint64_t nis_ctx_launch_count(const nis_ctx* ctx);
+
+/* ------------------------------------------------------------------ K1: raw-echo synthesis
+ * Replaces the per-pulse loops of
+ *   run_bistatic_physics_gpu   sar_ati_dcpa_sim_csa.py:106-181   (bistatic = 1)
+ *   run_physics_engine         sar_satellite_sim.py:211-305      (bistatic = 0, tgt_vel = 0)
+ *   run_moving_physics         sar_satellite_moving_sim.py:111-159
+ *   run_custom_physics         sar_vehicle_sim.py:83-126
+ * raw[i][n] (+)= sum_b amp_b * exp(j 2 pi (-fc tau_bi + (k_rate/2) (t_n - tau_bi - t_p/2)^2))
+ *               over scatterers with |t_n - tau_bi - t_p/2| <= t_p/2 (closed interval),
+ * tau_bi = (|p_b(t_i) - pos_tx_i| + |p_b(t_i) - pos_rx_i|) / c, p_b(t) = pos0_b + vel_b t.
+ * For a monostatic engine pass pos_rx = NULL (tau = 2 |p - pos_tx| / c).
+ * The receiver positions are host-side geometry (p_tx + v/|v| * offset, :145-148) and arrive
+ * precomputed.  Geometry is evaluated in fp64 per (scatterer, pulse); samples accumulate in fp32.
+ */
+typedef struct {
+    double c;        /* propagation speed (m/s) */
+    double fc;       /* carrier (Hz) */
+    double k_rate;   /* chirp rate BW / T_p (Hz/s) */
+    double t_p;      /* pulse width (s) */
+    double t_start;  /* t_fast[0] (s) */
+    double dt_fast;  /* nominal fast-time step: t_fast[n] ~= t_start + n * dt_fast */
+    int32_t per_target_velocity; /* 0: tgt_vel is one xyz triple; 1: tgt_vel is [T*3] */
+    int32_t reserved;
+} nis_echo_params;
+
+NIS_API int nis_echo_accumulate(nis_ctx* ctx, const nis_echo_params* prm,
+                        const double* tgt_pos0 /* dev [T*3] */,
+                        const double* tgt_vel  /* dev [3] or [T*3] */,
+                        const double* tgt_amp  /* dev [T]  sqrt(rcs) */,
+                        const double* pos_tx   /* dev [P*3] */,
+                        const double* pos_rx   /* dev [P*3] or NULL */,
+                        const double* t_slow   /* dev [P] */,
+                        const double* t_fast   /* dev [S] exact sample times (linspace grid) */,
+                        int32_t T, int32_t P0, int32_t P1, int32_t S,
+                        nis_c32* raw /* dev [P][S], rows P0..P1-1 are written */,
+                        int32_t accumulate /* 0: overwrite rows, 1: add to them */,
+                        nis_stream stream);
+
+/* ------------------------------------------------------------------ K2: Chirp Scaling focusing
+ * Replaces sar_focus_csa (sar_ati_dcpa_sim_csa.py:202-396): azimuth FFT, x Phi1, range FFT, x Phi2,
+ * range IFFT, x Phi3, azimuth IFFT, all fftshift/ifftshift folded into index arithmetic.
+ * A plan owns the twiddle tables, the fp64-derived per-Doppler phase coefficients and a workspace
+ * of n_az*n_rg complex samples.  The focused image is written CORNER-TURNED, i.e. as the
+ * [n_rg][n_az] array that the reference returns as `img.T` (:396).
+ */
+typedef struct {
+    double c;        /* 299792458.0 in the reference (:211) */
+    double lambda;   /* center_wavelength_m */
+    double kr;       /* chirp_rate_hzpsec */
+    double fs;       /* sample_rate_hz */
+    double prf;      /* prf_hz */
+    double vr;       /* platform_speed_mps */
+    double r_ref;    /* range_ref_m */
+    double t_start;  /* t_start_fast */
+} nis_csa_params;
+
+NIS_API int nis_csa_plan_create(nis_ctx* ctx, int32_t n_az, int32_t n_rg, const nis_csa_params* prm,
+                        nis_csa_plan** out);
+NIS_API int nis_csa_plan_destroy(nis_csa_plan* plan);
+/* 1 if (n_az, n_rg) is handled by the fused power-of-two path, 2 for the general-size path, 0 = unsupported */
+NIS_API int nis_csa_size_class(int32_t n_az, int32_t n_rg);
+/* range_axis[n_rg] = c tau / 2 (:346,:388), cross_range[n_az] = (n/prf - mean) vr (:392-394); host buffers */
+NIS_API int nis_csa_axes(const nis_csa_plan* plan, double* range_axis, double* cross_range);
+/* phist: dev [n_az][pitch] complex64, pitch in elements (>= n_rg).  The DPCA co-registration of
+ * :402-403 (rx1[1:], rx2[:-1]) is a pointer offset of one row by the caller.
+ * slc: dev [n_rg][n_az].  max_sq (optional, dev, 1 float): max |slc|^2, accumulated with max. */
+NIS_API int nis_csa_focus(nis_csa_plan* plan, const nis_c32* phist, int64_t pitch, nis_c32* slc,
+                  float* max_sq, nis_stream stream);
+
+/* ------------------------------------------------------------------ K3: DPCA + ATI + detection
+ * Replaces the inline numpy passes sar_ati_dcpa_sim_csa.py:414-419, :447-449 and
+ * SARData.compute_all (sar_ati_dcpa_viewer_csa.py:42-52):
+ *   s2c = slc2 * exp(j cal_phase); interf = slc1 conj(s2c); phase = atan2; diff = slc1 - s2c;
+ *   mask = |slc1| > thresh_frac * max|slc1| (strict, evaluated in fp64 on the fp32 samples);
+ *   phase_masked = mask ? phase : 0; det_idx = ascending flat indices with mask set;
+ *   peak = first index attaining max|slc1|.
+ * Any output pointer may be NULL (that product is not materialised).
+ */
+typedef struct {
+    uint32_t det_count;   /* number of detected pixels (may exceed det_cap: list is truncated) */
+    uint32_t peak_idx;    /* flat index of the first maximum of |slc1| */
+    double   max_mag_sq;  /* max |slc1|^2 (fp64 on the fp32 samples) */
+} nis_gmti_result;
+
+NIS_API int nis_gmti_fused(nis_ctx* ctx, const nis_c32* slc1, const nis_c32* slc2, uint64_t n_pix,
+                   double thresh_frac, double cal_phase,
+                   nis_c32* ati_interf, float* ati_phase, nis_c32* dpca_diff, float* dpca_mag,
+                   float* slc1_mag, uint8_t* mag_mask, float* ati_phase_masked,
+                   uint32_t* det_idx, uint32_t det_cap,
+                   nis_gmti_result* result /* dev */, nis_stream stream);
+/* viewer auto-balance (sar_ati_dcpa_viewer_csa.py:249-250): sum slc1 conj(slc2) in fp64;
+ * out: dev [2] doubles (re, im) of the SUM (angle of the mean == angle of the sum) */
+NIS_API int nis_gmti_balance_sum(nis_ctx* ctx, const nis_c32* slc1, const nis_c32* slc2, uint64_t n_pix,
+                         double* out_sum, nis_stream stream);
+
+/* ------------------------------------------------------------------ buffer format helpers
+ * The reference's arrays are complex128; these convert on the device so that host<->device copies
+ * are the only host-side cost. */
+NIS_API int nis_narrow_c128_to_c32(nis_ctx* ctx, const double* src /* dev [n*2] */, nis_c32* dst, uint64_t n, nis_stream stream);
+NIS_API int nis_widen_c32_to_c128(nis_ctx* ctx, const nis_c32* src, double* dst /* dev [n*2] */, uint64_t n, nis_stream stream);
+/* out[c][r] = in[r][c] for a rows x cols complex64 matrix (tiled, coalesced both sides) */
+NIS_API int nis_transpose_c32(nis_ctx* ctx, const nis_c32* in, nis_c32* out, int32_t rows, int32_t cols, nis_stream stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NIS_SAR_H */

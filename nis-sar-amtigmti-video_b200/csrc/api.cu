@@ -1,0 +1,148 @@
+// api.cu -- context, error reporting and buffer-format helpers of libnis_sar.
+#include <stdarg.h>
+#include <string.h>
+
+#include "common.cuh"
+
+namespace nis {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+}  // namespace nis
+
+using namespace nis;
+
+int nis_ctx::ensure_scratch(size_t bytes) {
+    if (bytes <= scratch_bytes) return NIS_OK;
+    if (scratch) cudaFree(scratch);
+    scratch = nullptr;
+    scratch_bytes = 0;
+    size_t want = bytes + (bytes >> 2);
+    if (cudaMalloc(&scratch, want) != cudaSuccess) {
+        set_error("scratch allocation of %zu bytes failed: %s", want, cudaGetErrorString(cudaGetLastError()));
+        return NIS_ERR_NOMEM;
+    }
+    scratch_bytes = want;
+    return NIS_OK;
+}
+
+extern "C" int nis_version(void) { return NIS_SAR_ABI_VERSION; }
+
+extern "C" size_t nis_last_error(char* buf, size_t cap) {
+    const size_t len = strlen(g_err);
+    if (buf && cap > 0) {
+        const size_t n = len < cap - 1 ? len : cap - 1;
+        memcpy(buf, g_err, n);
+        buf[n] = 0;
+    }
+    return len;
+}
+
+extern "C" int nis_ctx_create(int device, nis_ctx** out) {
+    NIS_REQUIRE(out != nullptr, "nis_ctx_create: null out pointer");
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0) {
+        set_error("nis_ctx_create: no CUDA device (%s); this library has no CPU fallback",
+                  e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
+        return NIS_ERR_CUDA;
+    }
+    NIS_REQUIRE(device >= 0 && device < count, "nis_ctx_create: device %d out of range (0..%d)", device, count - 1);
+    NIS_CUDA_TRY(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    NIS_CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10) {
+        set_error("nis_ctx_create: device %d is sm_%d%d; this build carries sm_100a code only", device, prop.major,
+                  prop.minor);
+        return NIS_ERR_UNSUPPORTED;
+    }
+    nis_ctx* ctx = new nis_ctx();
+    ctx->device = device;
+    ctx->num_sms = prop.multiProcessorCount;
+    *out = ctx;
+    return NIS_OK;
+}
+
+extern "C" int nis_ctx_destroy(nis_ctx* ctx) {
+    if (!ctx) return NIS_OK;
+    if (ctx->scratch) cudaFree(ctx->scratch);
+    delete ctx;
+    return NIS_OK;
+}
+
+extern "C" uint64_t nis_ctx_launch_count(const nis_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+// --------------------------------------------------------------------------- format helpers
+namespace {
+
+__global__ void __launch_bounds__(256) k_narrow(const double2* __restrict__ src, float2* __restrict__ dst, uint64_t n) {
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+        const double2 v = src[i];
+        dst[i] = make_float2((float)v.x, (float)v.y);
+    }
+}
+__global__ void __launch_bounds__(256) k_widen(const float2* __restrict__ src, double2* __restrict__ dst, uint64_t n) {
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+        const float2 v = src[i];
+        dst[i] = make_double2((double)v.x, (double)v.y);
+    }
+}
+// 32 x 32 tiles, 256 threads, padded shared tile: both sides move 256 B row pieces
+__global__ void __launch_bounds__(256) k_transpose(const float2* __restrict__ in, float2* __restrict__ out, int rows, int cols) {
+    __shared__ float2 tile[32][33];
+    const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int r = r0 + ty + 8 * i, c = c0 + tx;
+        if (r < rows && c < cols) tile[ty + 8 * i][tx] = in[(int64_t)r * cols + c];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int c = c0 + ty + 8 * i, r = r0 + tx;
+        if (r < rows && c < cols) out[(int64_t)c * rows + r] = tile[tx][ty + 8 * i];
+    }
+}
+
+int grid_for(const nis_ctx* ctx, uint64_t n) {
+    const uint64_t want = (n + 255) / 256, cap = (uint64_t)ctx->num_sms * 16;
+    return (int)(want < cap ? (want ? want : 1) : cap);
+}
+
+}  // namespace
+
+extern "C" int nis_narrow_c128_to_c32(nis_ctx* ctx, const double* src, nis_c32* dst, uint64_t n, nis_stream stream) {
+    NIS_REQUIRE(ctx && src && dst, "nis_narrow_c128_to_c32: null argument");
+    if (n == 0) return NIS_OK;
+    k_narrow<<<grid_for(ctx, n), 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const double2*>(src),
+                                                                reinterpret_cast<float2*>(dst), n);
+    NIS_LAUNCH_CHECK(ctx);
+    return NIS_OK;
+}
+
+extern "C" int nis_widen_c32_to_c128(nis_ctx* ctx, const nis_c32* src, double* dst, uint64_t n, nis_stream stream) {
+    NIS_REQUIRE(ctx && src && dst, "nis_widen_c32_to_c128: null argument");
+    if (n == 0) return NIS_OK;
+    k_widen<<<grid_for(ctx, n), 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const float2*>(src),
+                                                               reinterpret_cast<double2*>(dst), n);
+    NIS_LAUNCH_CHECK(ctx);
+    return NIS_OK;
+}
+
+extern "C" int nis_transpose_c32(nis_ctx* ctx, const nis_c32* in, nis_c32* out, int32_t rows, int32_t cols,
+                                 nis_stream stream) {
+    NIS_REQUIRE(ctx && in && out && rows > 0 && cols > 0, "nis_transpose_c32: bad argument");
+    dim3 grid((cols + 31) / 32, (rows + 31) / 32);
+    k_transpose<<<grid, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const float2*>(in),
+                                                        reinterpret_cast<float2*>(out), rows, cols);
+    NIS_LAUNCH_CHECK(ctx);
+    return NIS_OK;
+}

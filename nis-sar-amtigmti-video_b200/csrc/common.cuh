@@ -1,0 +1,99 @@
+// common.cuh -- shared host/device helpers for libnis_sar (sm_100a only).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+
+#include "../../include/nis_sar.h"
+
+namespace nis {
+
+constexpr int kNumSMsB200 = 148;
+
+void set_error(const char* fmt, ...);
+
+#define NIS_CUDA_TRY(expr)                                                              \
+    do {                                                                                \
+        cudaError_t _e = (expr);                                                        \
+        if (_e != cudaSuccess) {                                                        \
+            ::nis::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e),   \
+                             __FILE__, __LINE__);                                      \
+            return NIS_ERR_CUDA;                                                        \
+        }                                                                               \
+    } while (0)
+
+#define NIS_REQUIRE(cond, ...)                 \
+    do {                                       \
+        if (!(cond)) {                         \
+            ::nis::set_error(__VA_ARGS__);     \
+            return NIS_ERR_INVALID;            \
+        }                                      \
+    } while (0)
+
+// after a kernel launch
+#define NIS_LAUNCH_CHECK(ctx)                  \
+    do {                                       \
+        (ctx)->launches++;                     \
+        NIS_CUDA_TRY(cudaGetLastError());      \
+    } while (0)
+
+}  // namespace nis
+
+struct nis_ctx {
+    int device = 0;
+    int num_sms = nis::kNumSMsB200;
+    uint64_t launches = 0;
+    // scratch for the GMTI detection pipeline (grown on demand)
+    void* scratch = nullptr;
+    size_t scratch_bytes = 0;
+    int ensure_scratch(size_t bytes);
+};
+
+namespace nis {
+
+// ---------------------------------------------------------------- device helpers
+#ifdef __CUDA_ARCH__
+#define NIS_LDG(p) __ldg(p)
+#else
+#define NIS_LDG(p) (*(p))
+#endif
+
+__host__ __device__ __forceinline__ float2 cmul(float2 a, float2 b) {
+    return make_float2(fmaf(a.x, b.x, -a.y * b.y), fmaf(a.x, b.y, a.y * b.x));
+}
+__host__ __device__ __forceinline__ float2 cmul_conj(float2 a, float2 b) {  // a * conj(b)
+    return make_float2(fmaf(a.x, b.x, a.y * b.y), fmaf(a.y, b.x, -a.x * b.y));
+}
+__host__ __device__ __forceinline__ float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
+__host__ __device__ __forceinline__ float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
+
+// Phase arithmetic in "turns" held as unsigned fixed point: value = u / 2^64 (or / 2^32).
+// Integer wrap-around IS the mod-1 reduction, so quadratic phases of 1e4..1e8 rad keep full
+// precision without fp64 in the inner loops.
+__host__ __device__ __forceinline__ uint64_t turns_to_u64(double t) {
+    t -= floor(t);                       // [0,1)
+    double s = t * 18446744073709551616.0;  // 2^64
+    if (s >= 18446744073709551615.0) return 0xFFFFFFFFFFFFFFFFull;
+    return (uint64_t)s;
+}
+
+// exp(j 2 pi u/2^32): top 32 bits of the phase -> signed turns in [-0.5,0.5) -> MUFU sin/cos.
+// Absolute error ~5e-7 (MUFU.SIN/COS on a reduced argument).
+__device__ __forceinline__ float2 cis_u32(uint32_t u) {
+    float t = (float)(int32_t)u * 2.3283064365386963e-10f;  // * 2^-32 -> turns in [-0.5, 0.5)
+    float a = t * 6.283185307179586f;
+    float s, c;
+    __sincosf(a, &s, &c);
+    return make_float2(c, s);
+}
+__device__ __forceinline__ float2 cis_u64(uint64_t u) { return cis_u32((uint32_t)(u >> 32)); }
+
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+
+}  // namespace nis

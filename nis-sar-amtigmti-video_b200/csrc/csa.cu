@@ -1,0 +1,458 @@
+// csa.cu -- K2: Chirp Scaling Algorithm focusing (replaces sar_focus_csa,
+// sar_ati_dcpa_sim_csa.py:202-396) for power-of-two scenes.
+//
+// Data flow (complex64, one workspace W[n_az][n_rg]):
+//   k_az_outer_fwd   raw  -> W   radix-A1 butterflies down the columns (registers only) x w_N^(a2 k1)
+//   k_az_inner<fwd>  W   -> W   A2-point column FFTs on [A2 rows x 32 cols] tiles in shared memory
+//   k_range          W   -> W   per Doppler row: x Phi1, range FFT, x Phi2, range IFFT, x Phi3
+//   k_az_inner<inv>  W   -> W   A2-point inverse column FFTs x w_N^-(k1 a2)
+//   k_az_outer_inv   W   -> slc radix-A1 inverse butterflies, 1/(n_az n_rg), corner turn to [n_rg][n_az]
+// Azimuth length n_az = A1*A2 (four-step split).  Between the two azimuth transforms rows live in
+// the permuted order rho = k1*A2 + k2 <-> Doppler bin kk = k1 + A1*k2; every per-row quantity is
+// tabulated in that order, and the reference's fftshift / ifftshift pairs (:234, :280, :331, :385)
+// reduce to index relabelling (bin kk has frequency fftfreq[kk]).
+//
+// Phase functions are quadratic in the sample (or frequency) index with per-row coefficients:
+//   Phi1: -(Kr Cs/2) (tau_n - tau_ref)^2                      tau_n = t0 + n/fs        (:272)
+//   Phi2:  fr^2 / (2 Kr (1+Cs)) + 2 R_ref Cs fr / c            fr = k' fs/n_rg          (:318-324)
+//   Phi3:  c tau_n D / lam - (Kr Cs (1+Cs)/2) (tau_n - 2R_ref/c)^2                      (:359-380)
+// (in turns).  The coefficients are derived on the host in extended precision from the reference's
+// own fp64 D, Cs, tau_ref and converted to 64-bit fixed-point turns, so that 1e4..1e8 rad phases are
+// reduced mod 1 exactly by integer wrap-around on the device.
+#include <math.h>
+#include <string.h>
+
+#include <vector>
+
+#include "common.cuh"
+#include "fft.cuh"
+
+using namespace nis;
+using namespace nis::fft;
+
+namespace {
+
+struct RowCoef {          // one per azimuth row (permuted order)
+    uint64_t a1, b1, c1;  // Phi1: a1 n^2 + b1 n + c1
+    uint64_t a2, b2, bn2; // Phi2: a2 k'^2 + b2 k', bn2 = b2 * n_rg (subtracted for negative bins)
+    uint64_t a3, b3, c3;  // Phi3
+    uint64_t pad;
+};
+static_assert(sizeof(RowCoef) == 80, "RowCoef layout");
+
+__device__ __forceinline__ uint64_t quad_phase(uint64_t a, uint64_t b, uint64_t c, uint32_t n) {
+    return a * (uint64_t)(n * n) + b * (uint64_t)n + c;  // n < 65536: n*n fits 32 bits
+}
+
+// ------------------------------------------------------------------------------ azimuth, outer
+// Forward: Y[k1*A2 + a2][n] = w_N^(a2 k1) * sum_a1 x[a1*A2 + a2][n] w_A1^(a1 k1)
+template <int A1>
+__global__ void __launch_bounds__(256) k_az_outer_fwd(const float2* __restrict__ in, int64_t in_pitch,
+                                                      float2* __restrict__ out, int64_t out_pitch, int n_rg,
+                                                      int A2, int n_az, const float2* __restrict__ twN) {
+    const int n = blockIdx.x * 32 + (threadIdx.x & 31);
+    const int a2 = blockIdx.y * 8 + (threadIdx.x >> 5);
+    if (n >= n_rg || a2 >= A2) return;
+    float2 v[A1];
+#pragma unroll
+    for (int a1 = 0; a1 < A1; ++a1) v[a1] = in[(int64_t)(a1 * A2 + a2) * in_pitch + n];
+    fft_dif<A1, false, 1>(v);
+    constexpr int L = ilog2(A1);
+#pragma unroll
+    for (int k1 = 0; k1 < A1; ++k1) {
+        float2 x = v[brev(k1, L)];
+        if (k1 > 0) x = cmul(x, __ldg(twN + ((a2 * k1) & (n_az - 1))));
+        out[(int64_t)(k1 * A2 + a2) * out_pitch + n] = x;
+    }
+}
+
+// Inverse + corner turn: slc[n][a1*A2 + a2] = scale * sum_k1 Z[k1*A2 + a2][n] w_A1^-(k1 a1)
+// Tile: TN = 16 range columns x TA azimuth offsets; transposed through shared memory so that both
+// the reads (128 B row pieces) and the writes (TA*8 B pieces of an slc row) are coalesced.
+template <int A1, int TA>
+__global__ void __launch_bounds__(256) k_az_outer_inv(const float2* __restrict__ in, int64_t pitch,
+                                                      float2* __restrict__ slc, int n_rg, int A2, int n_az,
+                                                      float scale, float* __restrict__ max_sq) {
+    constexpr int TN = 16;
+    extern __shared__ float2 tile[];  // [A1][TN][TA+1]
+    const int n0 = blockIdx.x * TN, a20 = blockIdx.y * TA;
+    const int n_off = threadIdx.x & 15, a_off = threadIdx.x >> 4;  // 16 x 16
+    constexpr int L = ilog2(A1);
+#pragma unroll
+    for (int it = 0; it < TA / 16; ++it) {
+        const int a2 = a20 + a_off + 16 * it;
+        float2 v[A1];
+#pragma unroll
+        for (int k1 = 0; k1 < A1; ++k1) v[k1] = in[(int64_t)(k1 * A2 + a2) * pitch + n0 + n_off];
+        fft_dif<A1, true, 1>(v);
+#pragma unroll
+        for (int a1 = 0; a1 < A1; ++a1) {
+            float2 x = v[brev(a1, L)];
+            tile[(a1 * TN + n_off) * (TA + 1) + a_off + 16 * it] = make_float2(x.x * scale, x.y * scale);
+        }
+    }
+    __syncthreads();
+    float m = 0.f;
+    constexpr int LPR = TA;                 // lanes per (a1, n) row piece
+    constexpr int RPI = 256 / LPR;          // row pieces per iteration
+    const int l = threadIdx.x % LPR, g = threadIdx.x / LPR;
+    for (int p = g; p < A1 * TN; p += RPI) {
+        const int a1 = p / TN, nn = p % TN;
+        float2 x = tile[(a1 * TN + nn) * (TA + 1) + l];
+        slc[(int64_t)(n0 + nn) * n_az + a1 * A2 + a20 + l] = x;
+        m = fmaxf(m, fmaf(x.x, x.x, x.y * x.y));
+    }
+    if (max_sq != nullptr) {
+        m = warp_max(m);
+        if ((threadIdx.x & 31) == 0) atomicMax(reinterpret_cast<unsigned int*>(max_sq), __float_as_uint(m));
+    }
+}
+
+// ------------------------------------------------------------------------------ azimuth, inner
+// A2-point transforms down W adjacent columns of the row block [k1*A2, (k1+1)*A2); lanes <-> columns.
+template <class P, bool INV, int W>
+__global__ void __launch_bounds__(P::NT* W) k_az_inner(float2* __restrict__ data, int64_t pitch, int n_az,
+                                                       const float2* __restrict__ tw, const float2* __restrict__ twN) {
+    extern __shared__ float2 smem[];
+    constexpr int E = P::E, NT = P::NT, A2 = P::N;
+    const int c = threadIdx.x % W, t = threadIdx.x / W;
+    const int k1 = blockIdx.y;
+    float2* base = data + (int64_t)k1 * A2 * pitch + blockIdx.x * W + c;
+    float2 v[E];
+#pragma unroll
+    for (int s = 0; s < E; ++s) v[s] = base[(int64_t)(t + NT * s) * pitch];
+    transform<P, INV, W, 0>(v, t, smem + c, tw);
+#pragma unroll
+    for (int s = 0; s < E; ++s) {
+        float2 x = v[s];
+        if (INV) x = cmul_conj(x, __ldg(twN + ((k1 * (t + NT * s)) & (n_az - 1))));
+        base[(int64_t)(t + NT * s) * pitch] = x;
+    }
+}
+
+// ------------------------------------------------------------------------------ range
+// One Doppler row per thread group: x Phi1 -> FFT -> x Phi2 -> IFFT -> x Phi3, one HBM round trip.
+template <class P, int PAD, int RPB>
+__global__ void __launch_bounds__(P::NT* RPB, (P::NT * RPB <= 256 && P::E <= 16) ? 2 : 1) k_range(float2* __restrict__ data, int64_t pitch, int n_rows,
+                                                      const RowCoef* __restrict__ coef,
+                                                      const float2* __restrict__ tw) {
+    extern __shared__ float2 smem[];
+    constexpr int E = P::E, NT = P::NT, N = P::N;
+    constexpr int SMROW = N + (PAD ? (N >> PAD) : 0);
+    const int t = threadIdx.x;
+    float2* sm = smem + threadIdx.y * SMROW;
+    for (int rb = blockIdx.x * RPB; rb < n_rows; rb += gridDim.x * RPB) {
+        const int row = min(rb + (int)threadIdx.y, n_rows - 1);
+        const bool live = rb + (int)threadIdx.y < n_rows;
+        const RowCoef rc = coef[row];
+        float2* p = data + (int64_t)row * pitch;
+        float2 v[E];
+#pragma unroll
+        for (int s = 0; s < E; ++s) v[s] = p[t + NT * s];
+#pragma unroll
+        for (int s = 0; s < E; ++s)
+            v[s] = cmul(v[s], cis_u64(quad_phase(rc.a1, rc.b1, rc.c1, (uint32_t)(t + NT * s))));
+        transform<P, false, 1, PAD>(v, t, sm, tw);
+#pragma unroll
+        for (int s = 0; s < E; ++s) {
+            const uint32_t k = t + NT * s;
+            const bool neg = k >= N / 2;
+            const uint32_t ka = neg ? N - k : k;
+            uint64_t ph = rc.a2 * (uint64_t)(ka * ka) + rc.b2 * (uint64_t)k - (neg ? rc.bn2 : 0ull);
+            v[s] = cmul(v[s], cis_u64(ph));
+        }
+        __syncthreads();
+        transform<P, true, 1, PAD>(v, t, sm, tw);
+        if (live) {
+#pragma unroll
+            for (int s = 0; s < E; ++s)
+                p[t + NT * s] = cmul(v[s], cis_u64(quad_phase(rc.a3, rc.b3, rc.c3, (uint32_t)(t + NT * s))));
+        }
+        __syncthreads();
+    }
+}
+
+// ------------------------------------------------------------------------------ host: plan
+typedef int (*az_outer_fwd_fn)(nis_csa_plan*, const float2*, int64_t, cudaStream_t);
+typedef int (*az_outer_inv_fn)(nis_csa_plan*, float2*, float*, cudaStream_t);
+typedef int (*az_inner_fn)(nis_csa_plan*, bool, cudaStream_t);
+typedef int (*range_fn)(nis_csa_plan*, cudaStream_t);
+
+}  // namespace
+
+struct nis_csa_plan {
+    nis_ctx* ctx = nullptr;
+    int n_az = 0, n_rg = 0, A1 = 0, A2 = 0;
+    nis_csa_params prm{};
+    float2* work = nullptr;
+    float2* tw_inner = nullptr;
+    float2* tw_full = nullptr;
+    float2* tw_rg = nullptr;
+    RowCoef* coef = nullptr;
+    std::vector<double> range_axis, cross_range;
+    az_outer_fwd_fn outer_fwd = nullptr;
+    az_outer_inv_fn outer_inv = nullptr;
+    az_inner_fn inner = nullptr;
+    range_fn range = nullptr;
+};
+
+namespace {
+
+template <int A1>
+int launch_outer_fwd(nis_csa_plan* pl, const float2* in, int64_t in_pitch, cudaStream_t st) {
+    dim3 grid((pl->n_rg + 31) / 32, (pl->A2 + 7) / 8);
+    k_az_outer_fwd<A1><<<grid, 256, 0, st>>>(in, in_pitch, pl->work, pl->n_rg, pl->n_rg, pl->A2, pl->n_az,
+                                              pl->tw_full);
+    NIS_LAUNCH_CHECK(pl->ctx);
+    return NIS_OK;
+}
+
+template <int A1, int TA>
+int launch_outer_inv(nis_csa_plan* pl, float2* slc, float* max_sq, cudaStream_t st) {
+    const size_t smem = (size_t)A1 * 16 * (TA + 1) * sizeof(float2);
+    static bool attr_done = false;
+    if (!attr_done) {
+        NIS_CUDA_TRY(cudaFuncSetAttribute(k_az_outer_inv<A1, TA>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          (int)smem));
+        attr_done = true;
+    }
+    dim3 grid(pl->n_rg / 16, pl->A2 / TA);
+    const float scale = (float)(1.0 / ((double)pl->n_az * (double)pl->n_rg));
+    k_az_outer_inv<A1, TA><<<grid, 256, smem, st>>>(pl->work, pl->n_rg, slc, pl->n_rg, pl->A2, pl->n_az, scale,
+                                                    max_sq);
+    NIS_LAUNCH_CHECK(pl->ctx);
+    return NIS_OK;
+}
+
+template <class P, int W>
+int launch_inner(nis_csa_plan* pl, bool inv, cudaStream_t st) {
+    const size_t smem = (size_t)P::N * W * sizeof(float2);
+    static bool attr_done = false;
+    if (!attr_done) {
+        NIS_CUDA_TRY(cudaFuncSetAttribute(k_az_inner<P, false, W>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          (int)smem));
+        NIS_CUDA_TRY(cudaFuncSetAttribute(k_az_inner<P, true, W>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          (int)smem));
+        attr_done = true;
+    }
+    dim3 grid(pl->n_rg / W, pl->A1);
+    if (inv)
+        k_az_inner<P, true, W><<<grid, P::NT * W, smem, st>>>(pl->work, pl->n_rg, pl->n_az, pl->tw_inner, pl->tw_full);
+    else
+        k_az_inner<P, false, W><<<grid, P::NT * W, smem, st>>>(pl->work, pl->n_rg, pl->n_az, pl->tw_inner, pl->tw_full);
+    NIS_LAUNCH_CHECK(pl->ctx);
+    return NIS_OK;
+}
+
+template <class P, int PAD, int RPB>
+int launch_range(nis_csa_plan* pl, cudaStream_t st) {
+    constexpr int SMROW = P::N + (PAD ? (P::N >> PAD) : 0);
+    const size_t smem = (size_t)SMROW * RPB * sizeof(float2);
+    static bool attr_done = false;
+    if (!attr_done) {
+        NIS_CUDA_TRY(cudaFuncSetAttribute(k_range<P, PAD, RPB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_done = true;
+    }
+    int per_sm = 1;
+    NIS_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_range<P, PAD, RPB>, P::NT * RPB, smem));
+    if (per_sm < 1) per_sm = 1;
+    const int blocks_needed = (pl->n_az + RPB - 1) / RPB;
+    int grid = pl->ctx->num_sms * per_sm;
+    if (grid > blocks_needed) grid = blocks_needed;
+    k_range<P, PAD, RPB><<<grid, dim3(P::NT, RPB), smem, st>>>(pl->work, pl->n_rg, pl->n_az, pl->coef, pl->tw_rg);
+    NIS_LAUNCH_CHECK(pl->ctx);
+    return NIS_OK;
+}
+
+// plans: <N, E, R0, R1, R2>
+using P16 = Plan<16, 16, 16, 1, 1>;
+using P64 = Plan<64, 8, 8, 8, 1>;
+using P128 = Plan<128, 16, 16, 8, 1>;
+using P256 = Plan<256, 16, 16, 16, 1>;
+using P512 = Plan<512, 16, 8, 8, 8>;
+using P1024 = Plan<1024, 16, 16, 8, 8>;
+using P2048 = Plan<2048, 16, 16, 16, 8>;
+using P4096 = Plan<4096, 16, 16, 16, 16>;
+using P8192 = Plan<8192, 32, 32, 16, 16>;
+using P16384 = Plan<16384, 32, 32, 32, 16>;
+
+template <class P>
+int upload_twiddles(float2** dev) {
+    std::vector<float2> h(P::tw_len + 1);
+    build_twiddles<P>(h.data());
+    NIS_CUDA_TRY(cudaMalloc(dev, h.size() * sizeof(float2)));
+    NIS_CUDA_TRY(cudaMemcpy(*dev, h.data(), h.size() * sizeof(float2), cudaMemcpyHostToDevice));
+    return NIS_OK;
+}
+
+struct AzSplit { int n, a1, a2; };
+const AzSplit kAzSplits[] = {{64, 4, 16},     {128, 8, 16},    {256, 16, 16},   {512, 8, 64},    {1024, 16, 64},
+                             {2048, 8, 256},  {4096, 16, 256}, {8192, 16, 512}, {16384, 16, 1024}};
+
+bool range_supported(int n) { return n >= 64 && n <= 16384 && (n & (n - 1)) == 0; }
+bool az_supported(int n) {
+    for (const auto& s : kAzSplits)
+        if (s.n == n) return true;
+    return false;
+}
+
+uint64_t to_fix(long double turns) {
+    long double f = turns - floorl(turns);
+    long double s = f * 18446744073709551616.0L;
+    if (s >= 18446744073709551615.0L) return 0xFFFFFFFFFFFFFFFFull;
+    return (uint64_t)s;
+}
+
+}  // namespace
+
+extern "C" int nis_csa_size_class(int32_t n_az, int32_t n_rg) {
+    return (az_supported(n_az) && range_supported(n_rg)) ? 1 : 0;
+}
+
+extern "C" int nis_csa_plan_destroy(nis_csa_plan* pl) {
+    if (!pl) return NIS_OK;
+    cudaFree(pl->work);
+    cudaFree(pl->tw_inner);
+    cudaFree(pl->tw_full);
+    cudaFree(pl->tw_rg);
+    cudaFree(pl->coef);
+    delete pl;
+    return NIS_OK;
+}
+
+extern "C" int nis_csa_plan_create(nis_ctx* ctx, int32_t n_az, int32_t n_rg, const nis_csa_params* prm,
+                                   nis_csa_plan** out) {
+    NIS_REQUIRE(ctx && prm && out, "nis_csa_plan_create: null argument");
+    if (!nis_csa_size_class(n_az, n_rg)) {
+        set_error("nis_csa_plan_create: size %d x %d not supported (power-of-two 64..16384 per axis)", n_az, n_rg);
+        return NIS_ERR_UNSUPPORTED;
+    }
+    NIS_REQUIRE(prm->fs > 0 && prm->prf > 0 && prm->vr > 0 && prm->kr != 0 && prm->lambda > 0 && prm->c > 0,
+                "nis_csa_plan_create: non-physical parameters");
+    NIS_CUDA_TRY(cudaSetDevice(ctx->device));
+    nis_csa_plan* pl = new nis_csa_plan();
+    pl->ctx = ctx;
+    pl->n_az = n_az;
+    pl->n_rg = n_rg;
+    pl->prm = *prm;
+    for (const auto& s : kAzSplits)
+        if (s.n == n_az) { pl->A1 = s.a1; pl->A2 = s.a2; }
+    int rc = NIS_OK;
+#define FAIL_IF(x) do { rc = (x); if (rc != NIS_OK) { nis_csa_plan_destroy(pl); return rc; } } while (0)
+
+    // ---- kernel selection
+    switch (pl->A1) {
+        case 4: pl->outer_fwd = launch_outer_fwd<4>; pl->outer_inv = launch_outer_inv<4, 16>; break;
+        case 8: pl->outer_fwd = launch_outer_fwd<8>;
+                pl->outer_inv = (pl->A2 >= 32) ? launch_outer_inv<8, 32> : launch_outer_inv<8, 16>; break;
+        default: pl->outer_fwd = launch_outer_fwd<16>;
+                 pl->outer_inv = (pl->A2 >= 32) ? launch_outer_inv<16, 32> : launch_outer_inv<16, 16>; break;
+    }
+    switch (pl->A2) {
+        case 16: pl->inner = launch_inner<P16, 32>; FAIL_IF(upload_twiddles<P16>(&pl->tw_inner)); break;
+        case 64: pl->inner = launch_inner<P64, 32>; FAIL_IF(upload_twiddles<P64>(&pl->tw_inner)); break;
+        case 256: pl->inner = launch_inner<P256, 32>; FAIL_IF(upload_twiddles<P256>(&pl->tw_inner)); break;
+        case 512: pl->inner = launch_inner<P512, 16>; FAIL_IF(upload_twiddles<P512>(&pl->tw_inner)); break;
+        default: pl->inner = launch_inner<P1024, 16>; FAIL_IF(upload_twiddles<P1024>(&pl->tw_inner)); break;
+    }
+    switch (n_rg) {
+        case 64: pl->range = launch_range<P64, 3, 8>; FAIL_IF(upload_twiddles<P64>(&pl->tw_rg)); break;
+        case 128: pl->range = launch_range<P128, 4, 8>; FAIL_IF(upload_twiddles<P128>(&pl->tw_rg)); break;
+        case 256: pl->range = launch_range<P256, 4, 8>; FAIL_IF(upload_twiddles<P256>(&pl->tw_rg)); break;
+        case 512: pl->range = launch_range<P512, 3, 4>; FAIL_IF(upload_twiddles<P512>(&pl->tw_rg)); break;
+        case 1024: pl->range = launch_range<P1024, 4, 4>; FAIL_IF(upload_twiddles<P1024>(&pl->tw_rg)); break;
+        case 2048: pl->range = launch_range<P2048, 4, 2>; FAIL_IF(upload_twiddles<P2048>(&pl->tw_rg)); break;
+        case 4096: pl->range = launch_range<P4096, 4, 1>; FAIL_IF(upload_twiddles<P4096>(&pl->tw_rg)); break;
+        case 8192: pl->range = launch_range<P8192, 5, 1>; FAIL_IF(upload_twiddles<P8192>(&pl->tw_rg)); break;
+        default: pl->range = launch_range<P16384, 5, 1>; FAIL_IF(upload_twiddles<P16384>(&pl->tw_rg)); break;
+    }
+
+    // ---- full-length azimuth twiddles w_N^m
+    {
+        std::vector<float2> h(n_az);
+        const double two_pi = 6.283185307179586476925286766559;
+        for (int m = 0; m < n_az; ++m) {
+            double a = -two_pi * (double)m / (double)n_az;
+            h[m] = make_float2((float)cos(a), (float)sin(a));
+        }
+        FAIL_IF(cudaMalloc(&pl->tw_full, n_az * sizeof(float2)) == cudaSuccess ? NIS_OK : NIS_ERR_NOMEM);
+        NIS_CUDA_TRY(cudaMemcpy(pl->tw_full, h.data(), n_az * sizeof(float2), cudaMemcpyHostToDevice));
+    }
+
+    // ---- axes and per-row phase coefficients (reference arithmetic in fp64, polynomial in long double)
+    {
+        const double c = prm->c, lam = prm->lambda, Kr = prm->kr, Vr = prm->vr, R_ref = prm->r_ref;
+        const double dt = 1.0 / prm->fs;
+        pl->range_axis.resize(n_rg);
+        for (int n = 0; n < n_rg; ++n) pl->range_axis[n] = c * (prm->t_start + n * dt) / 2.0;  // :219, :346
+        pl->cross_range.resize(n_az);
+        {
+            // t_slow = arange(N)/prf; t_slow -= mean(t_slow)  (:392-394); numpy's pairwise mean is
+            // reproduced to the last few ulps by an extended-precision sum
+            long double acc = 0;
+            for (int i = 0; i < n_az; ++i) acc += (long double)((double)i / prm->prf);
+            const double mean = (double)(acc / n_az);
+            for (int i = 0; i < n_az; ++i) pl->cross_range[i] = ((double)i / prm->prf - mean) * Vr;
+        }
+        std::vector<RowCoef> h(n_az);
+        const long double dtl = dt, t0 = prm->t_start;
+        const long double df = (long double)prm->fs / n_rg;
+        for (int rho = 0; rho < n_az; ++rho) {
+            const int k1 = rho / pl->A2, k2 = rho % pl->A2;
+            const int kk = k1 + pl->A1 * k2;                       // Doppler bin held by this row
+            const int ks = (kk < (n_az + 1) / 2) ? kk : kk - n_az;  // fftfreq sign convention
+            const double fa = (double)ks / ((double)n_az * (1.0 / prm->prf));  // np.fft.fftfreq(n, d): k/(n d)
+            double arg = 1.0 - (lam * fa / (2.0 * Vr)) * (lam * fa / (2.0 * Vr));
+            if (arg < 0) arg = 1e-9;                                // :246
+            const double D = sqrt(arg);
+            const double Cs = (1.0 / D) - 1.0;
+            const double tau_ref = 2.0 * R_ref / (c * D);
+            const long double cs = Cs, d1 = t0 - (long double)tau_ref;
+            RowCoef r{};
+            r.a1 = to_fix(-(Kr * cs / 2) * dtl * dtl);
+            r.b1 = to_fix(-(Kr * cs) * dtl * d1);
+            r.c1 = to_fix(-(Kr * cs / 2) * d1 * d1);
+            r.a2 = to_fix(df * df / (2.0L * Kr * (1.0L + cs)));
+            const long double b2 = 2.0L * R_ref * cs * df / c;
+            r.b2 = to_fix(b2);
+            r.bn2 = r.b2 * (uint64_t)n_rg;
+            const long double e3 = t0 - 2.0L * R_ref / c;
+            const long double q3 = (long double)Kr * cs * (1.0L + cs);
+            r.a3 = to_fix(-(q3 / 2) * dtl * dtl);
+            r.b3 = to_fix((long double)c * D * dtl / lam - q3 * dtl * e3);
+            r.c3 = to_fix((long double)c * D * t0 / lam - (q3 / 2) * e3 * e3);
+            h[rho] = r;
+        }
+        FAIL_IF(cudaMalloc(&pl->coef, n_az * sizeof(RowCoef)) == cudaSuccess ? NIS_OK : NIS_ERR_NOMEM);
+        NIS_CUDA_TRY(cudaMemcpy(pl->coef, h.data(), n_az * sizeof(RowCoef), cudaMemcpyHostToDevice));
+    }
+    if (cudaMalloc(&pl->work, (size_t)n_az * n_rg * sizeof(float2)) != cudaSuccess) {
+        set_error("nis_csa_plan_create: cannot allocate %zu-byte workspace", (size_t)n_az * n_rg * sizeof(float2));
+        nis_csa_plan_destroy(pl);
+        return NIS_ERR_NOMEM;
+    }
+#undef FAIL_IF
+    *out = pl;
+    return NIS_OK;
+}
+
+extern "C" int nis_csa_axes(const nis_csa_plan* pl, double* range_axis, double* cross_range) {
+    NIS_REQUIRE(pl, "nis_csa_axes: null plan");
+    if (range_axis) memcpy(range_axis, pl->range_axis.data(), pl->range_axis.size() * sizeof(double));
+    if (cross_range) memcpy(cross_range, pl->cross_range.data(), pl->cross_range.size() * sizeof(double));
+    return NIS_OK;
+}
+
+extern "C" int nis_csa_focus(nis_csa_plan* pl, const nis_c32* phist, int64_t pitch, nis_c32* slc, float* max_sq,
+                             nis_stream stream) {
+    NIS_REQUIRE(pl && phist && slc, "nis_csa_focus: null argument");
+    NIS_REQUIRE(pitch >= pl->n_rg, "nis_csa_focus: pitch %lld < n_rg %d", (long long)pitch, pl->n_rg);
+    cudaStream_t st = (cudaStream_t)stream;
+    int rc;
+    if ((rc = pl->outer_fwd(pl, reinterpret_cast<const float2*>(phist), pitch, st)) != NIS_OK) return rc;
+    if ((rc = pl->inner(pl, false, st)) != NIS_OK) return rc;
+    if ((rc = pl->range(pl, st)) != NIS_OK) return rc;
+    if ((rc = pl->inner(pl, true, st)) != NIS_OK) return rc;
+    if ((rc = pl->outer_inv(pl, reinterpret_cast<float2*>(slc), max_sq, st)) != NIS_OK) return rc;
+    return NIS_OK;
+}

@@ -1,0 +1,236 @@
+// echo.cu -- K1: scatterer x pulse x range-bin raw-echo accumulator.
+//
+// Replaces the per-pulse loops of run_bistatic_physics_gpu (sar_ati_dcpa_sim_csa.py:137-178),
+// run_physics_engine (sar_satellite_sim.py:264-302), run_moving_physics
+// (sar_satellite_moving_sim.py:129-156) and run_custom_physics (sar_vehicle_sim.py:102-123):
+//   raw[i][n] = sum_b amp_b exp(j 2 pi (-fc tau_bi + (k/2) (t_n - tau_bi - T_p/2)^2)) [|t_n - tau_bi - T_p/2| <= T_p/2]
+//
+// Work split: one CTA = one pulse x one chunk of CH = 256*SPT consecutive samples; each thread owns
+// SPT consecutive samples in registers and loops over every scatterer (no cross-thread reduction).
+//  * Prologue (fp64, once per scatterer per CTA, 256 scatterers at a time into shared memory): exact
+//    two-way range -> delay tau, the phase polynomial about the chunk centre reduced mod 1 and stored
+//    as 32-bit fixed-point turns, and the closed-interval chirp support [lo, hi) evaluated with the
+//    reference's own fp64 expression on the caller's sample-time table (boundary samples bit-exact).
+//    Scatterers whose support misses the chunk are dropped by an ordered (deterministic) compaction.
+//  * Inner loop (fp32): the phase is quadratic in the sample index, phase(m_t + jj) =
+//    phi_t + jj*delta_t + A jj^2.  A is the same for every scatterer, so exp(j 2 pi A jj^2) factors
+//    out of the scatterer sum and is applied once at the end; per scatterer a thread evaluates two
+//    fast sincos (u = amp cis(phi_t), v = cis(delta_t)) and then runs the phasor recurrence
+//    p <- p v outward from the centre sample: 1 complex multiply + 1 complex add per sample.
+#include <math.h>
+
+#include "common.cuh"
+
+using namespace nis;
+
+namespace {
+
+struct EchoConst {
+    double c, fc, k_rate, t_p, t_start, dt_fast;
+    double a_turns;  // (k/2) dt^2
+    int T, P0, S, per_target_velocity, accumulate, bistatic;
+};
+
+template <int SPT>
+struct EchoTail {
+    float2 e[SPT];  // exp(j 2 pi A jj^2), jj = j - SPT/2
+};
+
+__device__ __forceinline__ uint32_t frac32(double turns) {
+    turns -= floor(turns);
+    return (uint32_t)(unsigned long long)(turns * 4294967296.0);  // < 2^32 except turns==1-eps -> saturates below
+}
+
+// closed-interval gate of the reference, evaluated exactly as numpy does in fp64 (:164-166)
+__device__ __forceinline__ bool gate(const double* __restrict__ t_fast, int n, double tau, double half) {
+    return fabs(__dsub_rn(__dsub_rn(t_fast[n], tau), half)) <= half;
+}
+
+template <int SPT>
+__global__ void __launch_bounds__(256) k_echo(EchoConst k, EchoTail<SPT> tail, const double* __restrict__ pos0,
+                                              const double* __restrict__ vel, const double* __restrict__ amp,
+                                              const double* __restrict__ pos_tx, const double* __restrict__ pos_rx,
+                                              const double* __restrict__ t_slow, const double* __restrict__ t_fast,
+                                              float2* __restrict__ raw) {
+    constexpr int CH = 256 * SPT;
+    constexpr int HALF = SPT / 2;
+    __shared__ uint4 rec[256];
+    __shared__ int warp_cnt[8];
+
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int pulse = k.P0 + blockIdx.y;
+    const int n0 = blockIdx.x * CH;                 // first sample of the chunk
+    const int nc = n0 + CH / 2;                     // chunk centre: phase polynomial is expanded about it
+    const int mt = tid * SPT + HALF - CH / 2;       // this thread's centre sample relative to nc (signed)
+    const int t_lo = tid * SPT, t_hi = t_lo + SPT;  // this thread's samples relative to n0
+
+    // per-thread constants of the common quadratic term: A mt^2 and 2 A mt (mod 1)
+    const uint32_t k1 = frac32(k.a_turns * (double)mt * (double)mt);
+    const uint32_t k2 = frac32(2.0 * k.a_turns * (double)mt);
+
+    const double ti = t_slow[pulse];
+    const double tx0 = pos_tx[3 * pulse], tx1 = pos_tx[3 * pulse + 1], tx2 = pos_tx[3 * pulse + 2];
+    double rx0 = tx0, rx1 = tx1, rx2 = tx2;
+    if (k.bistatic) { rx0 = pos_rx[3 * pulse]; rx1 = pos_rx[3 * pulse + 1]; rx2 = pos_rx[3 * pulse + 2]; }
+    const double half = k.t_p / 2;
+    const double t_center = k.t_start + (double)nc * k.dt_fast;
+
+    float2 acc[SPT];
+#pragma unroll
+    for (int j = 0; j < SPT; ++j) acc[j] = make_float2(0.f, 0.f);
+
+    for (int b0 = 0; b0 < k.T; b0 += 256) {
+        // ------------------------------------------------ prologue: one scatterer per thread, fp64
+        const int b = b0 + tid;
+        bool keep = false;
+        uint4 r = make_uint4(0, 0, 0, 0);
+        if (b < k.T) {
+            const double* vb = k.per_target_velocity ? vel + 3 * b : vel;
+            // p = p0 + v t with separate roundings, as numpy / torch evaluate it (:151)
+            const double px = __dadd_rn(pos0[3 * b], __dmul_rn(vb[0], ti)),
+                         py = __dadd_rn(pos0[3 * b + 1], __dmul_rn(vb[1], ti)),
+                         pz = __dadd_rn(pos0[3 * b + 2], __dmul_rn(vb[2], ti));
+            double dx = px - tx0, dy = py - tx1, dz = pz - tx2;
+            const double d_tx = sqrt(__dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz)));
+            double tau;
+            if (k.bistatic) {
+                dx = px - rx0; dy = py - rx1; dz = pz - rx2;
+                const double d_rx = sqrt(__dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz)));
+                tau = __ddiv_rn(__dadd_rn(d_tx, d_rx), k.c);
+            } else {
+                tau = __ddiv_rn(__dmul_rn(2.0, d_tx), k.c);
+            }
+            // support [lo, hi) in absolute sample indices
+            int lo = (int)ceil((tau - k.t_start) / k.dt_fast);
+            int hi = (int)floor((tau + k.t_p - k.t_start) / k.dt_fast) + 1;
+            lo = max(0, min(lo, k.S));
+            hi = max(0, min(hi, k.S));
+#pragma unroll 1
+            for (int it = 0; it < 3 && lo > 0 && gate(t_fast, lo - 1, tau, half); ++it) --lo;
+#pragma unroll 1
+            for (int it = 0; it < 3 && lo < k.S && !gate(t_fast, lo, tau, half); ++it) ++lo;
+#pragma unroll 1
+            for (int it = 0; it < 3 && hi < k.S && gate(t_fast, hi, tau, half); ++it) ++hi;
+#pragma unroll 1
+            for (int it = 0; it < 3 && hi > 0 && !gate(t_fast, hi - 1, tau, half); ++it) --hi;
+            const int rlo = max(lo - n0, 0), rhi = min(hi - n0, CH);
+            if (rlo < rhi) {
+                keep = true;
+                const double uu = t_center - tau - half;
+                const double cq = fma(0.5 * k.k_rate * uu, uu, -k.fc * tau);  // turns at the chunk centre
+                const double bq = k.k_rate * uu * k.dt_fast;                  // turns per sample
+                r.x = frac32(cq);
+                r.y = frac32(bq);
+                r.z = __float_as_uint((float)amp[b]);
+                r.w = (uint32_t)rlo | ((uint32_t)rhi << 16);
+            }
+        }
+        // ordered compaction (deterministic summation order)
+        const unsigned ball = __ballot_sync(0xffffffffu, keep);
+        if (lane == 0) warp_cnt[wid] = __popc(ball);
+        __syncthreads();  // also: previous tile's consumers are done with rec[]
+        int off = __popc(ball & ((1u << lane) - 1u));
+        int total = 0;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) {
+            const int cw = warp_cnt[w];
+            if (w < wid) off += cw;
+            total += cw;
+        }
+        if (keep) rec[off] = r;
+        __syncthreads();
+
+        // ------------------------------------------------ inner loop: every thread, every kept scatterer
+#pragma unroll 1
+        for (int q = 0; q < total; ++q) {
+            const uint4 s = rec[q];
+            const int lo = (int)(s.w & 0xffffu), hi = (int)(s.w >> 16);
+            if (t_lo >= hi || t_hi <= lo) continue;
+            const uint32_t phi = s.x + s.y * (uint32_t)mt + k1;
+            const uint32_t dlt = s.y + k2;
+            const float a = __uint_as_float(s.z);
+            float2 u = cis_u32(phi);
+            u.x *= a; u.y *= a;
+            const float2 v = cis_u32(dlt);
+            if (t_lo >= lo && t_hi <= hi) {
+                float2 p = u;
+#pragma unroll
+                for (int j = HALF; j < SPT; ++j) { acc[j] = cadd(acc[j], p); p = cmul(p, v); }
+                p = cmul_conj(u, v);
+#pragma unroll
+                for (int j = HALF - 1; j >= 0; --j) { acc[j] = cadd(acc[j], p); p = cmul_conj(p, v); }
+            } else {
+                float2 p = u;
+#pragma unroll
+                for (int j = HALF; j < SPT; ++j) {
+                    if (t_lo + j >= lo && t_lo + j < hi) acc[j] = cadd(acc[j], p);
+                    p = cmul(p, v);
+                }
+                p = cmul_conj(u, v);
+#pragma unroll
+                for (int j = HALF - 1; j >= 0; --j) {
+                    if (t_lo + j >= lo && t_lo + j < hi) acc[j] = cadd(acc[j], p);
+                    p = cmul_conj(p, v);
+                }
+            }
+        }
+    }
+
+    // ------------------------------------------------ epilogue: common quadratic factor, store
+    float2* out = raw + (int64_t)pulse * k.S + n0 + t_lo;
+#pragma unroll
+    for (int j = 0; j < SPT; ++j) {
+        if (n0 + t_lo + j < k.S) {
+            float2 x = cmul(acc[j], tail.e[j]);
+            if (k.accumulate) { const float2 o = out[j]; x.x += o.x; x.y += o.y; }
+            out[j] = x;
+        }
+    }
+}
+
+template <int SPT>
+int launch_echo(nis_ctx* ctx, const EchoConst& k, const double* pos0, const double* vel, const double* amp,
+                const double* pos_tx, const double* pos_rx, const double* t_slow, const double* t_fast, float2* raw,
+                int n_pulses, cudaStream_t st) {
+    EchoTail<SPT> tail;
+    const double two_pi = 6.283185307179586476925286766559;
+    for (int j = 0; j < SPT; ++j) {
+        const double jj = (double)(j - SPT / 2);
+        double ph = k.a_turns * jj * jj;
+        ph -= floor(ph);
+        tail.e[j] = make_float2((float)cos(two_pi * ph), (float)sin(two_pi * ph));
+    }
+    constexpr int CH = 256 * SPT;
+    dim3 grid((k.S + CH - 1) / CH, n_pulses);
+    k_echo<SPT><<<grid, 256, 0, st>>>(k, tail, pos0, vel, amp, pos_tx, pos_rx, t_slow, t_fast, raw);
+    NIS_LAUNCH_CHECK(ctx);
+    return NIS_OK;
+}
+
+}  // namespace
+
+extern "C" int nis_echo_accumulate(nis_ctx* ctx, const nis_echo_params* prm, const double* tgt_pos0,
+                                   const double* tgt_vel, const double* tgt_amp, const double* pos_tx,
+                                   const double* pos_rx, const double* t_slow, const double* t_fast, int32_t T,
+                                   int32_t P0, int32_t P1, int32_t S, nis_c32* raw, int32_t accumulate,
+                                   nis_stream stream) {
+    NIS_REQUIRE(ctx && prm && tgt_pos0 && tgt_vel && tgt_amp && pos_tx && t_slow && t_fast && raw,
+                "nis_echo_accumulate: null argument");
+    NIS_REQUIRE(T >= 0 && S > 0 && P0 >= 0 && P1 >= P0, "nis_echo_accumulate: bad sizes T=%d S=%d P0=%d P1=%d", T, S, P0, P1);
+    NIS_REQUIRE(prm->c > 0 && prm->dt_fast > 0 && prm->t_p > 0, "nis_echo_accumulate: non-physical parameters");
+    if (P1 == P0) return NIS_OK;
+    NIS_REQUIRE(P1 - P0 <= 65535, "nis_echo_accumulate: at most 65535 pulses per call (got %d)", P1 - P0);
+    cudaStream_t st = (cudaStream_t)stream;
+    EchoConst k;
+    k.c = prm->c; k.fc = prm->fc; k.k_rate = prm->k_rate; k.t_p = prm->t_p;
+    k.t_start = prm->t_start; k.dt_fast = prm->dt_fast;
+    k.a_turns = 0.5 * prm->k_rate * prm->dt_fast * prm->dt_fast;
+    k.T = T; k.P0 = P0; k.S = S; k.per_target_velocity = prm->per_target_velocity;
+    k.accumulate = accumulate; k.bistatic = pos_rx != nullptr;
+    float2* r = reinterpret_cast<float2*>(raw);
+    // chunk = 256*SPT samples: take the wider chunk unless it wastes > 12 % of its threads past S
+    const int waste16 = ((S + 4095) / 4096) * 4096 - S;
+    if (waste16 * 8 <= S)
+        return launch_echo<16>(ctx, k, tgt_pos0, tgt_vel, tgt_amp, pos_tx, pos_rx, t_slow, t_fast, r, P1 - P0, st);
+    return launch_echo<8>(ctx, k, tgt_pos0, tgt_vel, tgt_amp, pos_tx, pos_rx, t_slow, t_fast, r, P1 - P0, st);
+}

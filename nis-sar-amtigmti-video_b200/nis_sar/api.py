@@ -1,0 +1,199 @@
+"""Drop-in replacements for the reference's hot-path entry points.
+
+Same names, positional signatures, return tuples, dtypes (complex128 / float64) and shapes as
+
+    run_bistatic_physics_gpu   sar_ati_dcpa_sim_csa.py:106-181
+    sar_focus_csa              sar_ati_dcpa_sim_csa.py:202-396
+    run_physics_engine         sar_satellite_sim.py:211-305
+    run_moving_physics         sar_satellite_moving_sim.py:111-159
+    run_custom_physics         sar_vehicle_sim.py:83-126
+
+plus ``gmti_products`` for the inline ATI/DPCA block (sar_ati_dcpa_sim_csa.py:414-419, :447-449).
+The reference functions read radar constants from their module's globals; here they come from a
+``RadarParams`` -- either the module default (``set_default_params``) or, after
+``install(module_globals)``, from the patched module's own ``C, R0, FC, BW, T_p, FS`` at call time.
+Everything is computed by the CUDA library; host arrays are only copied in and out.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from . import device as dev
+from .params import RadarParams, spaceborne_preset
+from .targets import targets_to_arrays
+
+_default_params: RadarParams | None = None
+_default_device = "cuda"
+
+
+def set_default_params(prm: RadarParams | None):
+    global _default_params
+    _default_params = prm
+
+
+def set_default_device(device):
+    global _default_device
+    _default_device = device
+
+
+def _params(prm):
+    if prm is not None:
+        return prm
+    return _default_params if _default_params is not None else spaceborne_preset()
+
+
+def _to_host_c128(t: torch.Tensor) -> np.ndarray:
+    """Device complex64 -> host complex128 numpy: widened on the device, one D2H copy into pinned memory."""
+    wide = dev.widen_c32(t)
+    host = torch.empty(wide.shape, dtype=torch.complex128, pin_memory=True)
+    host.copy_(wide, non_blocking=False)
+    return host.numpy()
+
+
+# ------------------------------------------------------------------------------------------ echo
+def run_bistatic_physics_gpu(targets, t_vec, pos_tx_np, vel_tx_np, rx_offset_dist, vel_target_np, *,
+                             params: RadarParams | None = None, device=None, return_device=False):
+    """Two-phase-centre echo (sar_ati_dcpa_sim_csa.py:106-181).  Returns (raw[P,S] complex128, t_start_fast)."""
+    prm = _params(params)
+    pos0, rcs = targets_to_arrays(targets)
+    vel_tx = np.asarray(vel_tx_np, dtype=np.float64).reshape(-1, 3)
+    pos_tx = np.asarray(pos_tx_np, dtype=np.float64).reshape(-1, 3)
+    v_dir = vel_tx / np.sqrt(np.sum(vel_tx * vel_tx, axis=1))[:, None]           # :145
+    pos_rx = pos_tx + v_dir * rx_offset_dist                                      # :148
+    S = int(22e-6 * prm.FS) if prm.n_samples == 0 else prm.n_samples              # :111
+    t0 = prm.t_start_fast                                                         # :112
+    raw = dev.echo_accumulate(pos0, np.asarray(vel_target_np, dtype=np.float64).reshape(3), rcs, pos_tx, pos_rx,
+                              np.asarray(t_vec, dtype=np.float64), c=prm.C, fc=prm.FC, k_rate=prm.k_rate, t_p=prm.T_p,
+                              t_start=t0, fs=prm.FS, n_samples=S, device=device or _default_device)
+    return (raw if return_device else _to_host_c128(raw)), t0
+
+
+def run_physics_engine(targets, pos_sat, t_vec, *, params: RadarParams | None = None, device=None,
+                       return_device=False):
+    """Monostatic, static scatterers (sar_satellite_sim.py:211-305).  Returns (raw, t_start_fast, fs);
+    fs is fixed at 600 MHz and S at int(22e-6 fs) inside the reference (:245-248)."""
+    return run_moving_physics(targets, t_vec, pos_sat, (0.0, 0.0, 0.0), params=params, device=device,
+                              return_device=return_device)
+
+
+def run_moving_physics(targets, t_vec, pos_sat, vel_target, *, params: RadarParams | None = None, device=None,
+                       return_device=False):
+    """Monostatic, scatterers translating with ``vel_target`` (sar_satellite_moving_sim.py:111-159)."""
+    prm = _params(params)
+    fs = 600e6                                                                    # :114
+    S = int(22e-6 * fs) if prm.n_samples == 0 else prm.n_samples
+    t0 = (2 * prm.R0 / prm.C) - (prm.T_p / 2) - 1e-6                              # :116
+    pos0, rcs = targets_to_arrays(targets)
+    raw = dev.echo_accumulate(pos0, np.asarray(vel_target, dtype=np.float64).reshape(3), rcs,
+                              np.asarray(pos_sat, dtype=np.float64), None, np.asarray(t_vec, dtype=np.float64),
+                              c=prm.C, fc=prm.FC, k_rate=prm.k_rate, t_p=prm.T_p, t_start=t0, fs=fs, n_samples=S,
+                              device=device or _default_device)
+    return (raw if return_device else _to_host_c128(raw)), t0, fs
+
+
+def run_custom_physics(targets, t_vec, pos, tuned_prp, t_p, fc, bw, *, params: RadarParams | None = None,
+                       device=None, return_device=False):
+    """Airborne engine (sar_vehicle_sim.py:83-126): fs = 360 MHz, S = 2048, window centred on 2 R0/C.
+    ``tuned_prp`` is unused by the reference as well.  Returns raw only."""
+    prm = _params(params)
+    fs, S = 360e6, 2048                                                           # :85-86
+    t0 = (2 * prm.R0 / prm.C) - (S / fs) / 2                                      # :89
+    pos0, rcs = targets_to_arrays(targets)
+    raw = dev.echo_accumulate(pos0, np.zeros(3), rcs, np.asarray(pos, dtype=np.float64), None,
+                              np.asarray(t_vec, dtype=np.float64), c=prm.C, fc=fc, k_rate=bw / t_p, t_p=t_p,
+                              t_start=t0, fs=fs, n_samples=S, device=device or _default_device)
+    return raw if return_device else _to_host_c128(raw)
+
+
+# ------------------------------------------------------------------------------------------- CSA
+def sar_focus_csa(phist, center_wavelength_m, pulse_width_sec, chirp_rate_hzpsec, sample_rate_hz, prf_hz,
+                  platform_speed_mps, range_ref_m, t_start_fast, *, device=None, return_device=False):
+    """Chirp Scaling focusing (sar_ati_dcpa_sim_csa.py:202-396).  ``phist`` is [N_az, N_rg]: a numpy
+    complex array (any complex dtype) or a complex64 CUDA tensor.  Returns (img, range_axis,
+    cross_range_axis) with img of shape [N_rg, N_az] -- the array the reference returns as ``img.T`` --
+    as complex128 numpy (C-contiguous; the reference's is the F-contiguous view of the same values).
+    ``pulse_width_sec`` is unused, as in the reference."""
+    device = device or _default_device
+    if torch.is_tensor(phist):
+        x = phist if phist.dtype == torch.complex64 else dev.narrow_c128(phist.to(torch.complex128).contiguous())
+    else:
+        h = np.asarray(phist)
+        if h.ndim != 2:
+            raise dev.NisError("sar_focus_csa: phist must be 2-D [N_az, N_rg]")
+        if h.dtype == np.complex64:
+            x = torch.from_numpy(np.ascontiguousarray(h)).to(device)
+        else:
+            x = dev.narrow_c128(torch.from_numpy(np.ascontiguousarray(h, dtype=np.complex128)).to(device))
+    n_az, n_rg = x.shape
+    plan = dev.cached_plan(n_az, n_rg, lam=float(center_wavelength_m), kr=float(chirp_rate_hzpsec),
+                           fs=float(sample_rate_hz), prf=float(prf_hz), vr=float(platform_speed_mps),
+                           r_ref=float(range_ref_m), t_start=float(t_start_fast), device=x.device)
+    slc = plan.focus(x)
+    rax, cax = plan.axes()
+    return (slc if return_device else _to_host_c128(slc)), rax, cax
+
+
+# ------------------------------------------------------------------------------------------ GMTI
+def gmti_products(slc1, slc2, thresh=0.05, cal_phase=0.0, *, device=None, return_device=False):
+    """ATI interferogram, phase, DPCA difference, magnitudes, 5 %-of-peak mask, masked phase and the
+    detected-pixel list (sar_ati_dcpa_sim_csa.py:414-419, :447-449).  Inputs [N_rg, N_az] complex."""
+    device = device or _default_device
+
+    def up(a):
+        if torch.is_tensor(a):
+            return a.contiguous() if a.dtype == torch.complex64 else dev.narrow_c128(a.to(torch.complex128).contiguous())
+        h = np.ascontiguousarray(a)
+        if h.dtype == np.complex64:
+            return torch.from_numpy(h).to(device)
+        return dev.narrow_c128(torch.from_numpy(h.astype(np.complex128, copy=False)).to(device))
+
+    out = dev.gmti_fused(up(slc1), up(slc2), thresh, cal_phase)
+    if return_device:
+        return out
+    res = {}
+    for k, v in out.items():
+        if not torch.is_tensor(v):
+            res[k] = v
+        elif v.dtype == torch.complex64:
+            res[k] = _to_host_c128(v)
+        elif v.dtype == torch.float32:
+            res[k] = v.to(torch.float64).cpu().numpy()
+        else:
+            res[k] = v.cpu().numpy()
+    return res
+
+
+def dpca_coregister(raw_rx1, raw_rx2):
+    """rx1[1:], rx2[:-1] (sar_ati_dcpa_sim_csa.py:402-403): views, no copy (numpy or torch)."""
+    return raw_rx1[1:, :], raw_rx2[:-1, :]
+
+
+# --------------------------------------------------------------------------------------- install
+_ENTRY_POINTS = ("run_bistatic_physics_gpu", "sar_focus_csa", "run_physics_engine", "run_moving_physics",
+                 "run_custom_physics")
+
+
+def install(namespace: dict, names=_ENTRY_POINTS):
+    """Patch the reference's entry points inside ``namespace`` (a simulator module's ``globals()``)
+    with the CUDA implementations.  The replacements read ``C, R0, FC, BW, T_p, FS`` from that
+    namespace on every call, exactly like the functions they replace."""
+    def live_params():
+        base = spaceborne_preset()
+        kw = {k: float(namespace[k]) for k in ("C", "R0", "FC", "BW", "T_p") if k in namespace}
+        if "FS" in namespace:
+            kw["FS"] = float(namespace["FS"])
+        return base.replace(**kw)
+
+    def _wrap(fn):
+        def patched(*a, **k):
+            k.setdefault("params", live_params())
+            return fn(*a, **k)
+        patched.__name__ = fn.__name__
+        patched.__doc__ = fn.__doc__
+        return patched
+
+    g = globals()
+    for n in names:
+        namespace[n] = g[n] if n == "sar_focus_csa" else _wrap(g[n])
+    return namespace

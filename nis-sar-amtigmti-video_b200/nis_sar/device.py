@@ -1,0 +1,254 @@
+"""Device-level operators: torch CUDA tensors in, torch CUDA tensors out, all work enqueued on
+torch's current stream through the C ABI (include/nis_sar.h).  torch is the buffer carrier only."""
+from __future__ import annotations
+
+import ctypes as C
+import math
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import NisError
+
+
+def _dev_index(device) -> int:
+    d = torch.device(device)
+    if d.type != "cuda":
+        raise NisError(f"nis_sar runs on CUDA devices only (got {d}); there is no CPU fallback")
+    return torch.cuda.current_device() if d.index is None else d.index
+
+
+def _stream_ptr(dev_index: int) -> int:
+    return torch.cuda.current_stream(dev_index).cuda_stream
+
+
+def _ptr(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
+
+
+def _f64(x, device):
+    return torch.as_tensor(np.ascontiguousarray(x, dtype=np.float64)).to(device, non_blocking=True)
+
+
+# ------------------------------------------------------------------------------------- echo
+MAX_PULSES_PER_LAUNCH = 65535
+
+
+def fast_time_axis(t_start: float, n_samples: int, fs: float) -> np.ndarray:
+    """The reference's receive-window grid: t_start + linspace(0, S/fs, S)
+    (sar_ati_dcpa_sim_csa.py:113-114) -- S points including the end point."""
+    return t_start + np.linspace(0.0, n_samples / fs, n_samples)
+
+
+def echo_accumulate(pos0, vel, rcs, pos_tx, pos_rx, t_slow, *, c, fc, k_rate, t_p, t_start, fs, n_samples,
+                    device="cuda", out=None, accumulate=False, pulse_range=None):
+    """K1.  Inputs are numpy / torch fp64 arrays (host or device); returns raw[P, S] complex64 on
+    ``device``.  ``vel`` is one xyz triple or a [T,3] array; ``pos_rx`` None selects the monostatic
+    delay 2|p - p_tx|/c.  ``pulse_range=(p0, p1)`` restricts the rows that are computed (the pulse
+    block of one rank); rows outside are left untouched."""
+    di = _dev_index(device)
+    dev = torch.device("cuda", di)
+    lib = _lib.load()
+    ctx = _lib.context(di)
+    with torch.cuda.device(di):
+        pos0_d = _f64(np.asarray(pos0).reshape(-1, 3) if not torch.is_tensor(pos0) else pos0.cpu().numpy().reshape(-1, 3), dev)
+        T = pos0_d.shape[0]
+        vel_np = np.asarray(vel.cpu().numpy() if torch.is_tensor(vel) else vel, dtype=np.float64)
+        per_target = int(vel_np.size == 3 * T and vel_np.ndim == 2 and T > 1)
+        vel_d = _f64(vel_np.reshape(-1), dev)
+        amp_d = _f64(np.sqrt(np.asarray(rcs.cpu().numpy() if torch.is_tensor(rcs) else rcs, dtype=np.float64)).reshape(-1), dev)
+        if amp_d.shape[0] != T:
+            raise NisError(f"echo_accumulate: {T} positions but {amp_d.shape[0]} rcs values")
+        ptx_d = _f64(np.asarray(pos_tx).reshape(-1, 3), dev)
+        P = ptx_d.shape[0]
+        prx_d = None if pos_rx is None else _f64(np.asarray(pos_rx).reshape(-1, 3), dev)
+        ts_d = _f64(np.asarray(t_slow).reshape(-1), dev)
+        if ts_d.shape[0] != P or (prx_d is not None and prx_d.shape[0] != P):
+            raise NisError("echo_accumulate: pos_tx / pos_rx / t_slow disagree on the number of pulses")
+        S = int(n_samples)
+        t_fast = fast_time_axis(t_start, S, fs)
+        tf_d = _f64(t_fast, dev)
+        if out is None:
+            out = torch.zeros((P, S), dtype=torch.complex64, device=dev)
+            accumulate = False if pulse_range is None else accumulate
+        elif out.shape != (P, S) or out.dtype != torch.complex64 or not out.is_contiguous():
+            raise NisError("echo_accumulate: out must be a contiguous complex64 [P, S] tensor")
+        p0, p1 = (0, P) if pulse_range is None else pulse_range
+        prm = _lib.EchoParams(c=c, fc=fc, k_rate=k_rate, t_p=t_p, t_start=float(t_fast[0]),
+                              dt_fast=(S / fs) / (S - 1) if S > 1 else 1.0 / fs,
+                              per_target_velocity=per_target, reserved=0)
+        for q0 in range(p0, p1, MAX_PULSES_PER_LAUNCH):
+            q1 = min(p1, q0 + MAX_PULSES_PER_LAUNCH)
+            rc = lib.nis_echo_accumulate(ctx, C.byref(prm), _ptr(pos0_d), _ptr(vel_d), _ptr(amp_d), _ptr(ptx_d),
+                                         _ptr(prx_d), _ptr(ts_d), _ptr(tf_d), T, q0, q1, S, _ptr(out),
+                                         1 if accumulate else 0, C.c_void_p(_stream_ptr(di)))
+            _lib.check(rc, "nis_echo_accumulate")
+        # the fp64 input tensors may be freed right away: torch's allocator only reuses their memory
+        # for later work on this same stream
+    return out
+
+
+# -------------------------------------------------------------------------------------- CSA
+class CsaPlan:
+    """K2 plan: twiddles, fp64-derived phase coefficients and workspace for one (n_az, n_rg) and one
+    parameter set of ``sar_focus_csa`` (sar_ati_dcpa_sim_csa.py:202)."""
+
+    def __init__(self, n_az, n_rg, *, lam, kr, fs, prf, vr, r_ref, t_start, c=299792458.0, device="cuda"):
+        self.di = _dev_index(device)
+        self.n_az, self.n_rg = int(n_az), int(n_rg)
+        lib = _lib.load()
+        prm = _lib.CsaParams(c=c, lambda_=lam, kr=kr, fs=fs, prf=prf, vr=vr, r_ref=r_ref, t_start=t_start)
+        h = C.c_void_p()
+        with torch.cuda.device(self.di):
+            _lib.check(lib.nis_csa_plan_create(_lib.context(self.di), self.n_az, self.n_rg, C.byref(prm), C.byref(h)),
+                       "nis_csa_plan_create")
+        self._h = h
+        self.key = (self.n_az, self.n_rg, lam, kr, fs, prf, vr, r_ref, t_start, c, self.di)
+
+    @staticmethod
+    def supported(n_az, n_rg) -> bool:
+        return _lib.load().nis_csa_size_class(int(n_az), int(n_rg)) != 0
+
+    def axes(self):
+        ra = np.empty(self.n_rg, dtype=np.float64)
+        ca = np.empty(self.n_az, dtype=np.float64)
+        _lib.check(_lib.load().nis_csa_axes(self._h, ra.ctypes.data_as(C.c_void_p), ca.ctypes.data_as(C.c_void_p)),
+                   "nis_csa_axes")
+        return ra, ca
+
+    def focus(self, phist, out=None, max_sq=None):
+        """phist: complex64 CUDA tensor [n_az, n_rg] (rows may be strided: a ``raw[1:]`` view is fine).
+        Returns slc [n_rg, n_az] complex64 -- the array the reference returns as ``img.T``."""
+        if phist.dtype != torch.complex64 or phist.dim() != 2 or phist.stride(1) != 1:
+            raise NisError("CsaPlan.focus: phist must be a complex64 [n_az, n_rg] tensor with unit column stride")
+        if tuple(phist.shape) != (self.n_az, self.n_rg):
+            raise NisError(f"CsaPlan.focus: plan is {self.n_az}x{self.n_rg}, got {tuple(phist.shape)}")
+        if out is None:
+            out = torch.empty((self.n_rg, self.n_az), dtype=torch.complex64, device=phist.device)
+        with torch.cuda.device(self.di):
+            rc = _lib.load().nis_csa_focus(self._h, _ptr(phist), phist.stride(0), _ptr(out), _ptr(max_sq),
+                                           C.c_void_p(_stream_ptr(self.di)))
+        _lib.check(rc, "nis_csa_focus")
+        return out
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h.value:
+            _lib.load().nis_csa_plan_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+_plan_cache: dict = {}
+
+
+def cached_plan(n_az, n_rg, **kw) -> CsaPlan:
+    di = _dev_index(kw.get("device", "cuda"))
+    key = (int(n_az), int(n_rg), kw["lam"], kw["kr"], kw["fs"], kw["prf"], kw["vr"], kw["r_ref"], kw["t_start"],
+           kw.get("c", 299792458.0), di)
+    pl = _plan_cache.get(key)
+    if pl is None:
+        if len(_plan_cache) >= 4:          # plans own an n_az*n_rg workspace: keep only a few
+            _plan_cache.pop(next(iter(_plan_cache))).close()
+        pl = CsaPlan(n_az, n_rg, **kw)
+        _plan_cache[key] = pl
+    return pl
+
+
+# ------------------------------------------------------------------------------------- GMTI
+GMTI_PRODUCTS = ("ati_interf", "ati_phase", "dpca_diff", "dpca_mag", "slc1_mag", "mag_mask", "ati_phase_masked")
+
+
+def gmti_fused(slc1, slc2, thresh_frac=0.05, cal_phase=0.0, want=GMTI_PRODUCTS, det_cap=None):
+    """K3.  slc1/slc2: complex64 CUDA tensors of one shape.  Returns a dict with the requested
+    product tensors plus ``det_idx`` (uint32 -> int64 tensor of flat indices, ascending),
+    ``det_count``, ``peak_idx``, ``max_mag`` (python scalars; reading them synchronises)."""
+    if slc1.dtype != torch.complex64 or slc2.dtype != torch.complex64 or slc1.shape != slc2.shape:
+        raise NisError("gmti_fused: slc1 and slc2 must be complex64 tensors of the same shape")
+    if not (slc1.is_contiguous() and slc2.is_contiguous()):
+        raise NisError("gmti_fused: SLCs must be contiguous")
+    di = _dev_index(slc1.device)
+    dev = slc1.device
+    n = slc1.numel()
+    shape = tuple(slc1.shape)
+    outs = {}
+    with torch.cuda.device(di):
+        def alloc(name, dtype):
+            if name in want:
+                outs[name] = torch.empty(shape, dtype=dtype, device=dev)
+                return outs[name]
+            return None
+        interf = alloc("ati_interf", torch.complex64)
+        phase = alloc("ati_phase", torch.float32)
+        diff = alloc("dpca_diff", torch.complex64)
+        dmag = alloc("dpca_mag", torch.float32)
+        mag1 = alloc("slc1_mag", torch.float32)
+        mask = alloc("mag_mask", torch.uint8)
+        pmask = alloc("ati_phase_masked", torch.float32)
+        cap = n if det_cap is None else int(det_cap)
+        det = torch.empty((max(cap, 1),), dtype=torch.int32, device=dev)
+        res = torch.zeros((16,), dtype=torch.uint8, device=dev)
+        rc = _lib.load().nis_gmti_fused(_lib.context(di), _ptr(slc1), _ptr(slc2), n, float(thresh_frac),
+                                        float(cal_phase), _ptr(interf), _ptr(phase), _ptr(diff), _ptr(dmag),
+                                        _ptr(mag1), _ptr(mask), _ptr(pmask), _ptr(det), cap, _ptr(res),
+                                        C.c_void_p(_stream_ptr(di)))
+        _lib.check(rc, "nis_gmti_fused")
+        raw = res.cpu().numpy().tobytes()          # synchronises: the 16-byte result record
+    r = _lib.GmtiResult.from_buffer_copy(raw)
+    k = min(int(r.det_count), cap)
+    if "mag_mask" in outs:
+        outs["mag_mask"] = outs["mag_mask"].view(torch.bool)
+    outs["det_idx"] = det[:k].to(torch.int64) & 0xFFFFFFFF
+    outs["det_count"] = int(r.det_count)
+    outs["peak_idx"] = int(r.peak_idx)
+    outs["max_mag"] = math.sqrt(r.max_mag_sq)
+    return outs
+
+
+def balance_phase(slc1, slc2) -> float:
+    """Viewer auto-balance angle(mean(slc1 conj(slc2))) (sar_ati_dcpa_viewer_csa.py:249-250)."""
+    di = _dev_index(slc1.device)
+    with torch.cuda.device(di):
+        acc = torch.zeros(2, dtype=torch.float64, device=slc1.device)
+        rc = _lib.load().nis_gmti_balance_sum(_lib.context(di), _ptr(slc1.contiguous()), _ptr(slc2.contiguous()),
+                                              slc1.numel(), _ptr(acc), C.c_void_p(_stream_ptr(di)))
+        _lib.check(rc, "nis_gmti_balance_sum")
+        re, im = acc.cpu().tolist()
+    return math.atan2(im, re)
+
+
+# ---------------------------------------------------------------------------------- formats
+def narrow_c128(x128, out=None):
+    di = _dev_index(x128.device)
+    if out is None:
+        out = torch.empty(x128.shape, dtype=torch.complex64, device=x128.device)
+    with torch.cuda.device(di):
+        _lib.check(_lib.load().nis_narrow_c128_to_c32(_lib.context(di), _ptr(x128), _ptr(out), x128.numel(),
+                                                      C.c_void_p(_stream_ptr(di))), "nis_narrow_c128_to_c32")
+    return out
+
+
+def widen_c32(x64, out=None):
+    di = _dev_index(x64.device)
+    if out is None:
+        out = torch.empty(x64.shape, dtype=torch.complex128, device=x64.device)
+    with torch.cuda.device(di):
+        _lib.check(_lib.load().nis_widen_c32_to_c128(_lib.context(di), _ptr(x64), _ptr(out), x64.numel(),
+                                                     C.c_void_p(_stream_ptr(di))), "nis_widen_c32_to_c128")
+    return out
+
+
+def transpose_c32(x, out=None):
+    di = _dev_index(x.device)
+    rows, cols = x.shape
+    if out is None:
+        out = torch.empty((cols, rows), dtype=torch.complex64, device=x.device)
+    with torch.cuda.device(di):
+        _lib.check(_lib.load().nis_transpose_c32(_lib.context(di), _ptr(x), _ptr(out), rows, cols,
+                                                 C.c_void_p(_stream_ptr(di))), "nis_transpose_c32")
+    return out

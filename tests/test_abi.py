@@ -1,0 +1,81 @@
+"""CPU-side checks of the boundary: the shared library loads without a GPU, exports every symbol
+that include/nis_sar.h declares, and refuses to compute without a device (no CPU fallback)."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+from conftest import ROOT
+
+from nis_sar import _lib, params, scenes
+
+
+def _declared_symbols():
+    hdr = open(os.path.join(ROOT, "include", "nis_sar.h")).read()
+    return sorted(set(re.findall(r"NIS_API\s+[a-z_0-9]+\s+(nis_[a-z0-9_]+)\s*\(", hdr)))
+
+
+def test_header_symbols_are_exported_and_bound():
+    names = _declared_symbols()
+    assert len(names) >= 16
+    lib = _lib.load()
+    for n in names:
+        assert hasattr(lib, n), f"{n} declared in nis_sar.h but not exported"
+        assert n in _lib.SIGNATURES, f"{n} has no ctypes signature"
+    assert set(_lib.SIGNATURES) == set(names)
+
+
+def test_version_and_struct_layouts():
+    lib = _lib.load()
+    assert lib.nis_version() == 1
+    assert C.sizeof(_lib.EchoParams) == 56
+    assert C.sizeof(_lib.CsaParams) == 64
+    assert C.sizeof(_lib.GmtiResult) == 16
+
+
+def test_no_cpu_fallback():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    lib = _lib.load()
+    out = C.c_void_p()
+    rc = lib.nis_ctx_create(0, C.byref(out))
+    assert rc != 0 and not out.value
+    assert "no CPU fallback" in _lib.last_error()
+    from nis_sar import api
+    with pytest.raises(Exception):
+        api.sar_focus_csa(np.zeros((64, 64), np.complex64), 0.03, 20e-6, 2.5e13, 600e6, 6000.0, 7500.0, 5e5, 3.3e-3)
+
+
+def test_size_classes():
+    lib = _lib.load()
+    assert lib.nis_csa_size_class(4096, 4096) == 1
+    assert lib.nis_csa_size_class(8192, 8192) == 1
+    assert lib.nis_csa_size_class(64, 16384) == 1
+    assert lib.nis_csa_size_class(48, 4096) == 0
+
+
+def test_presets_match_reference_constants():
+    p = params.spaceborne_preset()
+    # sar_ati_dcpa_sim_csa.py:18-46 evaluated by hand
+    assert abs(p.V_sat - np.sqrt(3.986004418e14 / (6371000.0 + 350000.0))) < 1e-9
+    assert abs(p.R0 - 509385.5) < 1.0 and abs(p.V_eff - 7497.9) < 0.5
+    assert abs(p.d_rx - 2 * p.V_sat / 6000.0) < 1e-12
+    assert p.num_samples == 13200 and p.t_start_fast == (2 * p.R0 / p.C) - 10e-6 - 1e-6
+    v = params.airborne_vehicle_preset()
+    assert v.num_samples == 2048 and v.k_rate == 300e6 / 1e-6
+
+
+def test_scene_builders_are_seeded():
+    a = scenes.ati_scene(seed=4, num_pulses=16, num_clutter=10)
+    b = scenes.ati_scene(seed=4, num_pulses=16, num_clutter=10)
+    c = scenes.ati_scene(seed=5, num_pulses=16, num_clutter=10)
+    assert np.array_equal(a["clutter_pos"], b["clutter_pos"]) and not np.array_equal(a["clutter_pos"], c["clutter_pos"])
+    assert a["pos_tx"].shape == (16, 3) and abs(np.linalg.norm(a["vel_tx"][0]) - a["prm"].V_sat) < 1e-6
+    # broadside slant range is R0
+    s = scenes.ati_scene(seed=0, num_pulses=3, num_clutter=0)
+    assert abs(np.linalg.norm(s["pos_tx"][1]) - s["prm"].R0) < 1e-3
+    pos, rcs = scenes.dense_vehicle_scene(1, 500)
+    assert pos.shape == (500, 3) and rcs.shape == (500,)
