@@ -1,0 +1,368 @@
+#!/usr/bin/env python
+"""bench.py -- throughput of the SAR hot path on B200 (contract: see the task statement).
+
+Workload (BASELINE.json configs[1]): spaceborne stripmap point-target grid, 8192 x 8192 raw echo
+synthesis (sar_satellite_sim.py echo model, 9 x 9 scatterer grid) followed by Chirp Scaling focusing
+of the 8192 x 8192 frame.  One step = echo synthesis + CSA focusing of one frame.  With --gpus N
+every rank focuses its own frame (VideoSAR-style frame parallelism, no data-path collective):
+weak scaling.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+prints ONE JSON line.  `value` is Mpixel/s of focused image over all ranks with inputs resident in
+HBM; `e2e` is the same step through the drop-in Python API with host buffers (scene arrays copied
+host->device, the complex128 focused image copied device->host, every step).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+PKG = os.path.join(ROOT, "nis-sar-amtigmti-video_b200")
+for _p in (ROOT, PKG):
+    if _p not in sys.path:
+        sys.path.insert(0, _p)
+
+import numpy as np  # noqa: E402
+
+N_AZ = N_RG = 8192
+GRID_SIDE = 9
+METRIC = "csa_focused_mpixels_per_s"
+UNIT = "Mpixel/s"
+CSA_ALGO_BYTES_PER_PIXEL = 48.0      # 3 fused passes x (8 B read + 8 B write), SURVEY.md section 8d
+STAGE_ALGO_BYTES_PER_PIXEL = 16.0    # one kernel: read + write one complex64
+
+
+def workload(n_az=N_AZ, n_rg=N_RG):
+    from nis_sar import scenes
+    sc = scenes.stripmap_scene(num_pulses=n_az, num_samples=n_rg, n_side=GRID_SIDE, half_extent=1000.0)
+    return sc
+
+
+def config_dict(args, extra=None):
+    cfg = {"workload": f"stripmap point-target grid {GRID_SIDE}x{GRID_SIDE}, {N_AZ}x{N_RG} raw echo (monostatic, "
+                       f"sar_satellite_sim.py model) + CSA focus; one frame per rank per step",
+           "n_az": N_AZ, "n_rg": N_RG, "scatterers": GRID_SIDE * GRID_SIDE,
+           "l2_policy": "inputs larger than L2 (537 MB workspace per frame vs 126 MB L2)",
+           "parallelism": f"frame-parallel x{args.gpus}"}
+    if extra:
+        cfg.update(extra)
+    return cfg
+
+
+# ------------------------------------------------------------------------------------ CPU arms
+def _cpu_echo_rate(sc, pulses):
+    """Oracle (numpy port of run_physics_engine) on a pulse subset: scatterer-samples per second."""
+    from oracle import sar_oracle as orc
+    prm = sc["prm"]
+    idx = np.linspace(0, len(sc["t_vec"]) - 1, pulses).astype(int)
+    t0 = time.perf_counter()
+    orc.echo_monostatic(sc["pos"], sc["rcs"], sc["t_vec"][idx], sc["pos_sat"][idx], prm.as_globals(), n_samples=N_RG)
+    dt = time.perf_counter() - t0
+    return len(sc["rcs"]) * pulses * N_RG / dt, dt
+
+
+def _cpu_csa_rate(n, seed=0):
+    from oracle import sar_oracle as orc
+    from nis_sar import params
+    prm = params.spaceborne_preset()
+    rng = np.random.default_rng(seed)
+    x = (rng.standard_normal((n, n)) + 1j * rng.standard_normal((n, n)))
+    t0 = time.perf_counter()
+    orc.focus_csa(x, prm.Lambda, prm.k_rate, prm.FS, prm.PRF, prm.V_eff, prm.R0, prm.t_start_fast)
+    dt = time.perf_counter() - t0
+    return n * n / dt, dt
+
+
+def _cpu_worker(args):
+    seed, pulses, n_csa = args
+    sc = workload()
+    e_rate, e_dt = _cpu_echo_rate(sc, pulses)
+    c_rate, c_dt = _cpu_csa_rate(n_csa, seed)
+    return e_rate, c_rate, e_dt + c_dt
+
+
+def cpu_step_throughput(procs, pulses=4, n_csa=1024):
+    """Mpixel/s of the step (echo + CSA) on `procs` host processes, each running the single-threaded
+    numpy port on its own bounded sample.  Per-pixel CPU cost = scatterers / echo_rate + 1 / csa_rate."""
+    import multiprocessing as mp
+    if procs <= 1:
+        res = [_cpu_worker((0, pulses, n_csa))]
+    else:
+        with mp.get_context("fork").Pool(procs) as pool:
+            res = pool.map(_cpu_worker, [(i, pulses, n_csa) for i in range(procs)])
+    T = GRID_SIDE * GRID_SIDE
+    per_proc = [1.0 / (T / e + 1.0 / c) for e, c, _ in res]
+    return sum(per_proc) / 1e6, float(np.mean([e for e, _, _ in res])), float(np.mean([c for _, c, _ in res])), \
+        float(max(d for _, _, d in res))
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = max(1, len(os.sched_getaffinity(0)))
+    os.environ.setdefault("OMP_NUM_THREADS", "1")
+    vals = []
+    sample = None
+    for i in range(args.warmup + args.steps):
+        t0 = time.perf_counter()
+        v, e_rate, c_rate, dt = cpu_step_throughput(cores, pulses=2, n_csa=1024)
+        if i >= args.warmup:
+            vals.append((v, time.perf_counter() - t0))
+        sample = (f"{cores} processes, each: numpy port of run_physics_engine on 2 of {N_AZ} pulses x {N_RG} samples x "
+                  f"{GRID_SIDE * GRID_SIDE} scatterers ({e_rate:.3g} scatterer-samples/s) + sar_focus_csa port on a "
+                  f"1024x1024 frame ({c_rate / 1e6:.3g} Mpixel/s); per-pixel costs added")
+    v = float(np.mean([x for x, _ in vals]))
+    line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * float(np.mean([d for _, d in vals])),
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": config_dict(args),
+            "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------- GPU arm
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                       "-lms", "100", "-i", str(gpu_index)], stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        if self.p is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        self.f.seek(0)
+        sm, mx, reasons = [], [], set()
+        names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
+        for ln in self.f.read().splitlines():
+            parts = [x.strip() for x in ln.split(",")]
+            if len(parts) < 9:
+                continue
+            try:
+                sm.append(float(parts[1]))
+                mx.append(float(parts[2]))
+            except ValueError:
+                continue
+            for nm, val in zip(names, parts[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(nm)
+        try:
+            os.unlink(self.f.name)
+        except OSError:
+            pass
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def run_gpu_arm(args):
+    import torch
+    import torch.distributed as dist
+    from nis_sar import api, device as dev, _lib
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the product path has no CPU fallback")
+    torch.cuda.set_device(local)
+    device = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=device)
+
+    sc = workload()
+    prm = sc["prm"]
+    targets = [{"position": p, "rcs": r} for p, r in zip(sc["pos"], sc["rcs"])]
+    echo_kw = dict(c=prm.C, fc=prm.FC, k_rate=prm.k_rate, t_p=prm.T_p, t_start=prm.t_start_fast, fs=600e6,
+                   n_samples=N_RG, device=device)
+    plan = dev.cached_plan(N_AZ, N_RG, lam=prm.Lambda, kr=prm.k_rate, fs=prm.FS, prf=prm.PRF, vr=prm.V_eff,
+                           r_ref=prm.R0, t_start=prm.t_start_fast, device=device)
+    plan.set_profiling(True)
+    raw = torch.zeros((N_AZ, N_RG), dtype=torch.complex64, device=device)
+    slc = torch.empty((N_RG, N_AZ), dtype=torch.complex64, device=device)
+    # scene arrays resident in HBM for the device-timed region
+    import ctypes as C
+    pos0_d = torch.from_numpy(np.ascontiguousarray(sc["pos"])).to(device)
+    vel_d = torch.zeros(3, dtype=torch.float64, device=device)
+    amp_d = torch.from_numpy(np.sqrt(sc["rcs"])).to(device)
+    ptx_d = torch.from_numpy(np.ascontiguousarray(sc["pos_sat"])).to(device)
+    ts_d = torch.from_numpy(np.ascontiguousarray(sc["t_vec"])).to(device)
+    tf_d = torch.from_numpy(dev.fast_time_axis(prm.t_start_fast, N_RG, 600e6)).to(device)
+    eprm = _lib.EchoParams(c=prm.C, fc=prm.FC, k_rate=prm.k_rate, t_p=prm.T_p, t_start=float(tf_d[0].item()),
+                           dt_fast=(N_RG / 600e6) / (N_RG - 1), per_target_velocity=0, reserved=0)
+    lib, ctx = _lib.load(), _lib.context(local)
+    stream = torch.cuda.current_stream(device)
+
+    def echo_resident():
+        for q0 in range(0, N_AZ, 65535):
+            q1 = min(N_AZ, q0 + 65535)
+            _lib.check(lib.nis_echo_accumulate(ctx, C.byref(eprm), C.c_void_p(pos0_d.data_ptr()),
+                                               C.c_void_p(vel_d.data_ptr()), C.c_void_p(amp_d.data_ptr()),
+                                               C.c_void_p(ptx_d.data_ptr()), C.c_void_p(0), C.c_void_p(ts_d.data_ptr()),
+                                               C.c_void_p(tf_d.data_ptr()), len(sc["rcs"]), q0, q1, N_RG,
+                                               C.c_void_p(raw.data_ptr()), 0, C.c_void_p(stream.cuda_stream)),
+                       "nis_echo_accumulate")
+
+    def step_resident(ev=None):
+        if ev:
+            ev[0].record(stream)
+        echo_resident()
+        if ev:
+            ev[1].record(stream)
+        plan.focus(raw, out=slc)
+        if ev:
+            ev[2].record(stream)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(device)
+
+    for _ in range(max(args.warmup, 3)):
+        step_resident()
+    barrier()
+
+    # ------------------------------------------------ device-timed region (inputs resident in HBM)
+    sampler = ClockSampler(local) if rank == 0 else None
+    launches0 = _lib.launch_count(local)
+    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(args.steps)]
+    t_begin, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    t_begin.record(stream)
+    for k in range(args.steps):
+        step_resident(evs[k])
+    t_end.record(stream)
+    barrier()
+    launches = _lib.launch_count(local) - launches0
+    clocks = sampler.stop() if sampler else None
+    total_ms = t_begin.elapsed_time(t_end)
+    echo_ms = float(np.mean([e[0].elapsed_time(e[1]) for e in evs]))
+    csa_ms = float(np.mean([e[1].elapsed_time(e[2]) for e in evs]))
+    nprof = min(args.steps, 64)
+    stage = {k: 0.0 for k in plan.STAGES}
+    for b in range(nprof):
+        for k, v in plan.stage_times(b).items():
+            stage[k] += v / nprof
+
+    # ------------------------------------------------ e2e through the drop-in API (host buffers)
+    args_csa = (prm.Lambda, prm.T_p, prm.k_rate, prm.FS, prm.PRF, prm.V_eff, prm.R0, prm.t_start_fast)
+    api.set_default_device(device)
+    prm_api = prm
+
+    def step_e2e():
+        r, t0, _fs = api.run_physics_engine(targets, sc["pos_sat"], sc["t_vec"], params=prm_api, return_device=True)
+        img, rax, cax = api.sar_focus_csa(r, *args_csa)        # complex128 numpy [N_rg, N_az] on the host
+        return img
+
+    e2e_steps = max(2, min(args.steps, 5))
+    step_e2e()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        img = step_e2e()
+    torch.cuda.synchronize(device)
+    e2e_s = (time.perf_counter() - t0) / e2e_steps
+    h2d = int(sc["pos"].nbytes + sc["rcs"].nbytes + sc["pos_sat"].nbytes + sc["t_vec"].nbytes + 8 * N_RG + 24)
+    d2h = int(img.nbytes)
+    del img
+
+    # ------------------------------------------------ reduce over ranks (max time)
+    times = torch.tensor([total_ms, e2e_s * 1e3, echo_ms, csa_ms], dtype=torch.float64, device=device)
+    if world > 1:
+        dist.all_reduce(times, op=dist.ReduceOp.MAX)
+    total_ms, e2e_ms, echo_ms_max, csa_ms_max = (float(x) for x in times.cpu())
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    pixels = float(N_AZ) * N_RG
+    ms_per_step = total_ms / args.steps
+    value = world * pixels / (ms_per_step * 1e-3) / 1e6
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.isfile(peaks_path):
+        peak_gbs, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    else:
+        peak_gbs, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+    dom = max(stage, key=stage.get)
+    dom_gbs = STAGE_ALGO_BYTES_PER_PIXEL * pixels / (stage[dom] * 1e-3) / 1e9
+    csa_gbs = CSA_ALGO_BYTES_PER_PIXEL * pixels / (csa_ms * 1e-3) / 1e9
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.isfile(tpath):
+        traffic = json.load(open(tpath)).get(dom)
+
+    cpu_v, e_rate, c_rate, cpu_dt = cpu_step_throughput(1, pulses=4, n_csa=2048) if world == 1 else (None, 0, 0, 0)
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32 (complex64 samples; fp64 geometry and phase coefficients)", "data": "synthetic",
+        "config": config_dict(args),
+        "e2e": {"value": world * pixels / (e2e_ms * 1e-3) / 1e6, "unit": UNIT, "h2d_bytes_per_step": h2d,
+                "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms,
+                "path": "nis_sar.api.run_physics_engine(return_device=True) -> nis_sar.api.sar_focus_csa -> "
+                        "complex128 numpy image on the host"},
+        "gpu_launches": int(launches),
+        "roofline": {"bound": "hbm", "kernel": f"csa:{dom}", "achieved": dom_gbs, "peak": peak_gbs, "unit": "GB/s",
+                     "frac": dom_gbs / peak_gbs, "traffic": traffic, "peak_source": peak_src,
+                     "algorithmic_bytes_per_launch": STAGE_ALGO_BYTES_PER_PIXEL * pixels,
+                     "launch_ms": stage[dom],
+                     "csa_whole": {"achieved": csa_gbs, "frac": csa_gbs / peak_gbs,
+                                   "algorithmic_bytes_per_frame": CSA_ALGO_BYTES_PER_PIXEL * pixels, "ms": csa_ms},
+                     "stages_ms": stage},
+        "echo": {"ms": echo_ms, "gsamples_per_s": pixels / (echo_ms * 1e-3) / 1e9,
+                 "g_scatterer_samples_per_s": GRID_SIDE * GRID_SIDE * pixels / (echo_ms * 1e-3) / 1e9,
+                 "bound": "fp32 issue / MUFU (not HBM)"},
+        "csa": {"ms": csa_ms, "mpixels_per_s": pixels / (csa_ms * 1e-3) / 1e6},
+        "clocks": clocks,
+    }
+    if cpu_v is not None:
+        line["cpu_baseline"] = {
+            "value": cpu_v, "unit": UNIT, "cores": 1, "kind": "port",
+            "sample": f"numpy port of run_physics_engine on 4 of {N_AZ} pulses ({e_rate:.3g} scatterer-samples/s) + "
+                      f"sar_focus_csa port on a 2048x2048 frame ({c_rate / 1e6:.3g} Mpixel/s); per-pixel costs added; "
+                      f"{cpu_dt:.1f} s of CPU work"}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="native", choices=["native", "reference"])
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference_arm(args)
+    else:
+        run_gpu_arm(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -125,6 +125,13 @@ NIS_API int nis_csa_axes(const nis_csa_plan* plan, double* range_axis, double* c
 NIS_API int nis_csa_focus(nis_csa_plan* plan, const nis_c32* phist, int64_t pitch, nis_c32* slc,
                   float* max_sq, nis_stream stream);
 
+/* Per-kernel timing for bench.py's roofline: when enabled every nis_csa_focus call records CUDA
+ * events between its five kernels (az-outer-fwd, az-inner-fwd, range, az-inner-inv, az-outer-inv)
+ * on the launching stream; nis_csa_stage_times waits for the call `calls_back` calls ago (0 = most
+ * recent, ring of 64) and returns the five durations in milliseconds (host buffer). */
+NIS_API int nis_csa_plan_set_profiling(nis_csa_plan* plan, int32_t enable);
+NIS_API int nis_csa_stage_times(nis_csa_plan* plan, int32_t calls_back, float* ms5);
+
 /* ------------------------------------------------------------------ K3: DPCA + ATI + detection
  * Replaces the inline numpy passes sar_ati_dcpa_sim_csa.py:414-419, :447-449 and
  * SARData.compute_all (sar_ati_dcpa_viewer_csa.py:42-52):

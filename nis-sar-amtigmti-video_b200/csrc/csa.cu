@@ -190,6 +190,11 @@ struct nis_csa_plan {
     float2* tw_rg = nullptr;
     RowCoef* coef = nullptr;
     std::vector<double> range_axis, cross_range;
+    // optional per-stage timing: a ring of event sets, one per nis_csa_focus call
+    static constexpr int kProfRing = 64;
+    bool profiling = false;
+    uint64_t prof_calls = 0;
+    cudaEvent_t prof_ev[kProfRing][6] = {};
     az_outer_fwd_fn outer_fwd = nullptr;
     az_outer_inv_fn outer_inv = nullptr;
     az_inner_fn inner = nullptr;
@@ -316,6 +321,9 @@ extern "C" int nis_csa_plan_destroy(nis_csa_plan* pl) {
     cudaFree(pl->tw_full);
     cudaFree(pl->tw_rg);
     cudaFree(pl->coef);
+    for (auto& set : pl->prof_ev)
+        for (auto& e : set)
+            if (e) cudaEventDestroy(e);
     delete pl;
     return NIS_OK;
 }
@@ -448,11 +456,44 @@ extern "C" int nis_csa_focus(nis_csa_plan* pl, const nis_c32* phist, int64_t pit
     NIS_REQUIRE(pl && phist && slc, "nis_csa_focus: null argument");
     NIS_REQUIRE(pitch >= pl->n_rg, "nis_csa_focus: pitch %lld < n_rg %d", (long long)pitch, pl->n_rg);
     cudaStream_t st = (cudaStream_t)stream;
+    cudaEvent_t* ev = pl->profiling ? pl->prof_ev[pl->prof_calls % nis_csa_plan::kProfRing] : nullptr;
+#define STAGE_MARK(i) do { if (ev) NIS_CUDA_TRY(cudaEventRecord(ev[i], st)); } while (0)
     int rc;
+    STAGE_MARK(0);
     if ((rc = pl->outer_fwd(pl, reinterpret_cast<const float2*>(phist), pitch, st)) != NIS_OK) return rc;
+    STAGE_MARK(1);
     if ((rc = pl->inner(pl, false, st)) != NIS_OK) return rc;
+    STAGE_MARK(2);
     if ((rc = pl->range(pl, st)) != NIS_OK) return rc;
+    STAGE_MARK(3);
     if ((rc = pl->inner(pl, true, st)) != NIS_OK) return rc;
+    STAGE_MARK(4);
     if ((rc = pl->outer_inv(pl, reinterpret_cast<float2*>(slc), max_sq, st)) != NIS_OK) return rc;
+    STAGE_MARK(5);
+#undef STAGE_MARK
+    if (ev) pl->prof_calls++;
+    return NIS_OK;
+}
+
+extern "C" int nis_csa_plan_set_profiling(nis_csa_plan* pl, int32_t enable) {
+    NIS_REQUIRE(pl, "nis_csa_plan_set_profiling: null plan");
+    if (enable && !pl->prof_ev[0][0]) {
+        for (auto& set : pl->prof_ev)
+            for (auto& e : set) NIS_CUDA_TRY(cudaEventCreate(&e));
+    }
+    pl->profiling = enable != 0;
+    pl->prof_calls = 0;
+    return NIS_OK;
+}
+
+extern "C" int nis_csa_stage_times(nis_csa_plan* pl, int32_t calls_back, float* ms5) {
+    NIS_REQUIRE(pl && ms5, "nis_csa_stage_times: null argument");
+    NIS_REQUIRE(pl->profiling && calls_back >= 0 && (uint64_t)calls_back < pl->prof_calls &&
+                    calls_back < nis_csa_plan::kProfRing,
+                "nis_csa_stage_times: no profiled call %d back (have %llu)", calls_back,
+                (unsigned long long)pl->prof_calls);
+    cudaEvent_t* ev = pl->prof_ev[(pl->prof_calls - 1 - calls_back) % nis_csa_plan::kProfRing];
+    NIS_CUDA_TRY(cudaEventSynchronize(ev[5]));
+    for (int i = 0; i < 5; ++i) NIS_CUDA_TRY(cudaEventElapsedTime(&ms5[i], ev[i], ev[i + 1]));
     return NIS_OK;
 }

@@ -50,6 +50,8 @@ SIGNATURES = {
     "nis_csa_size_class": (C.c_int, [C.c_int32, C.c_int32]),
     "nis_csa_axes": (C.c_int, [_P, _P, _P]),
     "nis_csa_focus": (C.c_int, [_P, _P, C.c_int64, _P, _P, _P]),
+    "nis_csa_plan_set_profiling": (C.c_int, [_P, C.c_int32]),
+    "nis_csa_stage_times": (C.c_int, [_P, C.c_int32, _P]),
     "nis_gmti_fused": (C.c_int, [_P, _P, _P, C.c_uint64, C.c_double, C.c_double,
                                  _P, _P, _P, _P, _P, _P, _P, _P, C.c_uint32, _P, _P]),
     "nis_gmti_balance_sum": (C.c_int, [_P, _P, _P, C.c_uint64, _P, _P]),

@@ -132,6 +132,17 @@ class CsaPlan:
         _lib.check(rc, "nis_csa_focus")
         return out
 
+    STAGES = ("az_outer_fwd", "az_inner_fwd", "range", "az_inner_inv", "az_outer_inv")
+
+    def set_profiling(self, enable=True):
+        _lib.check(_lib.load().nis_csa_plan_set_profiling(self._h, 1 if enable else 0), "nis_csa_plan_set_profiling")
+
+    def stage_times(self, calls_back=0):
+        """Milliseconds spent in each of the five kernels of the focus call ``calls_back`` calls ago."""
+        ms = (C.c_float * 5)()
+        _lib.check(_lib.load().nis_csa_stage_times(self._h, int(calls_back), C.cast(ms, C.c_void_p)), "nis_csa_stage_times")
+        return dict(zip(self.STAGES, (float(x) for x in ms)))
+
     def close(self):
         if getattr(self, "_h", None) is not None and self._h.value:
             _lib.load().nis_csa_plan_destroy(self._h)
