@@ -95,14 +95,15 @@ __global__ void __launch_bounds__(256) k_widen(const float2* __restrict__ src, d
     }
 }
 // 32 x 32 tiles, 256 threads, padded shared tile: both sides move 256 B row pieces
-__global__ void __launch_bounds__(256) k_transpose(const float2* __restrict__ in, float2* __restrict__ out, int rows, int cols) {
+__global__ void __launch_bounds__(256) k_transpose(const float2* __restrict__ in, int64_t in_pitch,
+                                                   float2* __restrict__ out, int rows, int cols) {
     __shared__ float2 tile[32][33];
     const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
         const int r = r0 + ty + 8 * i, c = c0 + tx;
-        if (r < rows && c < cols) tile[ty + 8 * i][tx] = in[(int64_t)r * cols + c];
+        if (r < rows && c < cols) tile[ty + 8 * i][tx] = in[(int64_t)r * in_pitch + c];
     }
     __syncthreads();
 #pragma unroll
@@ -137,12 +138,19 @@ extern "C" int nis_widen_c32_to_c128(nis_ctx* ctx, const nis_c32* src, double* d
     return NIS_OK;
 }
 
+namespace nis {
+int launch_transpose(nis_ctx* ctx, const float2* in, int64_t in_pitch, float2* out, int rows, int cols,
+                     cudaStream_t st) {
+    dim3 grid((cols + 31) / 32, (rows + 31) / 32);
+    k_transpose<<<grid, 256, 0, st>>>(in, in_pitch, out, rows, cols);
+    NIS_LAUNCH_CHECK(ctx);
+    return NIS_OK;
+}
+}  // namespace nis
+
 extern "C" int nis_transpose_c32(nis_ctx* ctx, const nis_c32* in, nis_c32* out, int32_t rows, int32_t cols,
                                  nis_stream stream) {
     NIS_REQUIRE(ctx && in && out && rows > 0 && cols > 0, "nis_transpose_c32: bad argument");
-    dim3 grid((cols + 31) / 32, (rows + 31) / 32);
-    k_transpose<<<grid, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const float2*>(in),
-                                                        reinterpret_cast<float2*>(out), rows, cols);
-    NIS_LAUNCH_CHECK(ctx);
-    return NIS_OK;
+    return launch_transpose(ctx, reinterpret_cast<const float2*>(in), cols, reinterpret_cast<float2*>(out), rows, cols,
+                            (cudaStream_t)stream);
 }

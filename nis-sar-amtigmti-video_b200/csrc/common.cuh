@@ -53,6 +53,10 @@ struct nis_ctx {
 
 namespace nis {
 
+// out[c][r] = in[r][c]; `in` rows are in_pitch elements apart (api.cu)
+int launch_transpose(nis_ctx* ctx, const float2* in, int64_t in_pitch, float2* out, int rows, int cols,
+                     cudaStream_t st);
+
 // ---------------------------------------------------------------- device helpers
 #ifdef __CUDA_ARCH__
 #define NIS_LDG(p) __ldg(p)

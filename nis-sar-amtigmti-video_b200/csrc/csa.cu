@@ -24,25 +24,14 @@
 
 #include <vector>
 
-#include "common.cuh"
+#include "csa_internal.cuh"
 #include "fft.cuh"
 
 using namespace nis;
 using namespace nis::fft;
+using namespace nis::csa;
 
 namespace {
-
-struct RowCoef {          // one per azimuth row (permuted order)
-    uint64_t a1, b1, c1;  // Phi1: a1 n^2 + b1 n + c1
-    uint64_t a2, b2, bn2; // Phi2: a2 k'^2 + b2 k', bn2 = b2 * n_rg (subtracted for negative bins)
-    uint64_t a3, b3, c3;  // Phi3
-    uint64_t pad;
-};
-static_assert(sizeof(RowCoef) == 80, "RowCoef layout");
-
-__device__ __forceinline__ uint64_t quad_phase(uint64_t a, uint64_t b, uint64_t c, uint32_t n) {
-    return a * (uint64_t)(n * n) + b * (uint64_t)n + c;  // n < 65536: n*n fits 32 bits
-}
 
 // ------------------------------------------------------------------------------ azimuth, outer
 // Forward: Y[k1*A2 + a2][n] = w_N^(a2 k1) * sum_a1 x[a1*A2 + a2][n] w_A1^(a1 k1)
@@ -155,10 +144,7 @@ __global__ void __launch_bounds__(P::NT* RPB, (P::NT * RPB <= 256 && P::E <= 16)
         transform<P, false, 1, PAD>(v, t, sm, tw);
 #pragma unroll
         for (int s = 0; s < E; ++s) {
-            const uint32_t k = t + NT * s;
-            const bool neg = k >= N / 2;
-            const uint32_t ka = neg ? N - k : k;
-            uint64_t ph = rc.a2 * (uint64_t)(ka * ka) + rc.b2 * (uint64_t)k - (neg ? rc.bn2 : 0ull);
+            const uint64_t ph = phi2_phase(rc, (uint32_t)(t + NT * s), (uint32_t)N);
             v[s] = cmul(v[s], cis_u64(ph));
         }
         __syncthreads();
@@ -173,33 +159,7 @@ __global__ void __launch_bounds__(P::NT* RPB, (P::NT * RPB <= 256 && P::E <= 16)
 }
 
 // ------------------------------------------------------------------------------ host: plan
-typedef int (*az_outer_fwd_fn)(nis_csa_plan*, const float2*, int64_t, cudaStream_t);
-typedef int (*az_outer_inv_fn)(nis_csa_plan*, float2*, float*, cudaStream_t);
-typedef int (*az_inner_fn)(nis_csa_plan*, bool, cudaStream_t);
-typedef int (*range_fn)(nis_csa_plan*, cudaStream_t);
-
 }  // namespace
-
-struct nis_csa_plan {
-    nis_ctx* ctx = nullptr;
-    int n_az = 0, n_rg = 0, A1 = 0, A2 = 0;
-    nis_csa_params prm{};
-    float2* work = nullptr;
-    float2* tw_inner = nullptr;
-    float2* tw_full = nullptr;
-    float2* tw_rg = nullptr;
-    RowCoef* coef = nullptr;
-    std::vector<double> range_axis, cross_range;
-    // optional per-stage timing: a ring of event sets, one per nis_csa_focus call
-    static constexpr int kProfRing = 64;
-    bool profiling = false;
-    uint64_t prof_calls = 0;
-    cudaEvent_t prof_ev[kProfRing][6] = {};
-    az_outer_fwd_fn outer_fwd = nullptr;
-    az_outer_inv_fn outer_inv = nullptr;
-    az_inner_fn inner = nullptr;
-    range_fn range = nullptr;
-};
 
 namespace {
 
@@ -301,21 +261,72 @@ bool az_supported(int n) {
     return false;
 }
 
-uint64_t to_fix(long double turns) {
-    long double f = turns - floorl(turns);
-    long double s = f * 18446744073709551616.0L;
-    if (s >= 18446744073709551615.0L) return 0xFFFFFFFFFFFFFFFFull;
-    return (uint64_t)s;
-}
-
 }  // namespace
 
+// ---- shared builders (also used by csa_generic.cu)
+namespace nis {
+namespace csa {
+
+void build_axes(int n_az, int n_rg, const nis_csa_params& prm, std::vector<double>& range_axis,
+                std::vector<double>& cross_range) {
+    const double dt = 1.0 / prm.fs;
+    range_axis.resize(n_rg);
+    for (int n = 0; n < n_rg; ++n) range_axis[n] = prm.c * (prm.t_start + n * dt) / 2.0;  // :219, :346
+    cross_range.resize(n_az);
+    // t_slow = arange(N)/prf; t_slow -= mean(t_slow)  (:392-394); numpy's pairwise mean is reproduced to
+    // the last few ulps by an extended-precision sum
+    long double acc = 0;
+    for (int i = 0; i < n_az; ++i) acc += (long double)((double)i / prm.prf);
+    const double mean = (double)(acc / n_az);
+    for (int i = 0; i < n_az; ++i) cross_range[i] = ((double)i / prm.prf - mean) * prm.vr;
+}
+
+std::vector<RowCoef> build_row_coefs(int n_az, int n_rg, const nis_csa_params& prm, int A1, int A2) {
+    const double c = prm.c, lam = prm.lambda, Kr = prm.kr, Vr = prm.vr, R_ref = prm.r_ref;
+    const double dt = 1.0 / prm.fs;
+    std::vector<RowCoef> h(n_az);
+    const long double dtl = dt, t0 = prm.t_start;
+    const long double df = (long double)prm.fs / n_rg;
+    const double fa_unit = 1.0 / ((double)n_az * (1.0 / prm.prf));  // np.fft.fftfreq(n, d): k * (1/(n d))
+    for (int rho = 0; rho < n_az; ++rho) {
+        const int k1 = rho / A2, k2 = rho % A2;
+        const int kk = k1 + A1 * k2;                            // Doppler bin held by this row
+        const int ks = (kk < (n_az + 1) / 2) ? kk : kk - n_az;  // fftfreq sign convention
+        const double fa = (double)ks * fa_unit;
+        double arg = 1.0 - (lam * fa / (2.0 * Vr)) * (lam * fa / (2.0 * Vr));
+        if (arg < 0) arg = 1e-9;                                 // :246
+        const double D = sqrt(arg);
+        const double Cs = (1.0 / D) - 1.0;
+        const double tau_ref = 2.0 * R_ref / (c * D);
+        const long double cs = Cs, d1 = t0 - (long double)tau_ref;
+        RowCoef r{};
+        r.a1 = to_fix(-(Kr * cs / 2) * dtl * dtl);
+        r.b1 = to_fix(-(Kr * cs) * dtl * d1);
+        r.c1 = to_fix(-(Kr * cs / 2) * d1 * d1);
+        r.a2 = to_fix(df * df / (2.0L * Kr * (1.0L + cs)));
+        r.b2 = to_fix(2.0L * R_ref * cs * df / c);
+        r.bn2 = r.b2 * (uint64_t)n_rg;
+        const long double e3 = t0 - 2.0L * R_ref / c;
+        const long double q3 = (long double)Kr * cs * (1.0L + cs);
+        r.a3 = to_fix(-(q3 / 2) * dtl * dtl);
+        r.b3 = to_fix((long double)c * D * dtl / lam - q3 * dtl * e3);
+        r.c3 = to_fix((long double)c * D * t0 / lam - (q3 / 2) * e3 * e3);
+        h[rho] = r;
+    }
+    return h;
+}
+
+}  // namespace csa
+}  // namespace nis
+
 extern "C" int nis_csa_size_class(int32_t n_az, int32_t n_rg) {
-    return (az_supported(n_az) && range_supported(n_rg)) ? 1 : 0;
+    if (az_supported(n_az) && range_supported(n_rg)) return 1;
+    return generic_supported(n_az, n_rg) ? 2 : 0;
 }
 
 extern "C" int nis_csa_plan_destroy(nis_csa_plan* pl) {
     if (!pl) return NIS_OK;
+    generic_destroy(pl);
     cudaFree(pl->work);
     cudaFree(pl->tw_inner);
     cudaFree(pl->tw_full);
@@ -331,8 +342,10 @@ extern "C" int nis_csa_plan_destroy(nis_csa_plan* pl) {
 extern "C" int nis_csa_plan_create(nis_ctx* ctx, int32_t n_az, int32_t n_rg, const nis_csa_params* prm,
                                    nis_csa_plan** out) {
     NIS_REQUIRE(ctx && prm && out, "nis_csa_plan_create: null argument");
-    if (!nis_csa_size_class(n_az, n_rg)) {
-        set_error("nis_csa_plan_create: size %d x %d not supported (power-of-two 64..16384 per axis)", n_az, n_rg);
+    const int cls = nis_csa_size_class(n_az, n_rg);
+    if (!cls) {
+        set_error("nis_csa_plan_create: size %d x %d not supported (per axis: power of two 64..16384, or any length "
+                  "<= 14000 whose prime factors are <= 13, or any length <= 8192)", n_az, n_rg);
         return NIS_ERR_UNSUPPORTED;
     }
     NIS_REQUIRE(prm->fs > 0 && prm->prf > 0 && prm->vr > 0 && prm->kr != 0 && prm->lambda > 0 && prm->c > 0,
@@ -343,12 +356,34 @@ extern "C" int nis_csa_plan_create(nis_ctx* ctx, int32_t n_az, int32_t n_rg, con
     pl->n_az = n_az;
     pl->n_rg = n_rg;
     pl->prm = *prm;
-    for (const auto& s : kAzSplits)
-        if (s.n == n_az) { pl->A1 = s.a1; pl->A2 = s.a2; }
+    pl->size_class = cls;
     int rc = NIS_OK;
 #define FAIL_IF(x) do { rc = (x); if (rc != NIS_OK) { nis_csa_plan_destroy(pl); return rc; } } while (0)
+    build_axes(n_az, n_rg, *prm, pl->range_axis, pl->cross_range);
+    if (cudaMalloc(&pl->work, (size_t)n_az * n_rg * sizeof(float2)) != cudaSuccess) {
+        set_error("nis_csa_plan_create: cannot allocate %zu-byte workspace", (size_t)n_az * n_rg * sizeof(float2));
+        nis_csa_plan_destroy(pl);
+        return NIS_ERR_NOMEM;
+    }
+    if (cls == 2) {
+        pl->A1 = 1;
+        pl->A2 = n_az;
+    } else {
+        for (const auto& s : kAzSplits)
+            if (s.n == n_az) { pl->A1 = s.a1; pl->A2 = s.a2; }
+    }
+    {
+        std::vector<RowCoef> h = build_row_coefs(n_az, n_rg, *prm, pl->A1, pl->A2);
+        FAIL_IF(cudaMalloc(&pl->coef, n_az * sizeof(RowCoef)) == cudaSuccess ? NIS_OK : NIS_ERR_NOMEM);
+        NIS_CUDA_TRY(cudaMemcpy(pl->coef, h.data(), n_az * sizeof(RowCoef), cudaMemcpyHostToDevice));
+    }
+    if (cls == 2) {
+        FAIL_IF(generic_create(pl));
+        *out = pl;
+        return NIS_OK;
+    }
 
-    // ---- kernel selection
+    // ---- kernel selection (power-of-two path)
     switch (pl->A1) {
         case 4: pl->outer_fwd = launch_outer_fwd<4>; pl->outer_inv = launch_outer_inv<4, 16>; break;
         case 8: pl->outer_fwd = launch_outer_fwd<8>;
@@ -374,7 +409,6 @@ extern "C" int nis_csa_plan_create(nis_ctx* ctx, int32_t n_az, int32_t n_rg, con
         case 8192: pl->range = launch_range<P8192, 5, 1>; FAIL_IF(upload_twiddles<P8192>(&pl->tw_rg)); break;
         default: pl->range = launch_range<P16384, 5, 1>; FAIL_IF(upload_twiddles<P16384>(&pl->tw_rg)); break;
     }
-
     // ---- full-length azimuth twiddles w_N^m
     {
         std::vector<float2> h(n_az);
@@ -385,59 +419,6 @@ extern "C" int nis_csa_plan_create(nis_ctx* ctx, int32_t n_az, int32_t n_rg, con
         }
         FAIL_IF(cudaMalloc(&pl->tw_full, n_az * sizeof(float2)) == cudaSuccess ? NIS_OK : NIS_ERR_NOMEM);
         NIS_CUDA_TRY(cudaMemcpy(pl->tw_full, h.data(), n_az * sizeof(float2), cudaMemcpyHostToDevice));
-    }
-
-    // ---- axes and per-row phase coefficients (reference arithmetic in fp64, polynomial in long double)
-    {
-        const double c = prm->c, lam = prm->lambda, Kr = prm->kr, Vr = prm->vr, R_ref = prm->r_ref;
-        const double dt = 1.0 / prm->fs;
-        pl->range_axis.resize(n_rg);
-        for (int n = 0; n < n_rg; ++n) pl->range_axis[n] = c * (prm->t_start + n * dt) / 2.0;  // :219, :346
-        pl->cross_range.resize(n_az);
-        {
-            // t_slow = arange(N)/prf; t_slow -= mean(t_slow)  (:392-394); numpy's pairwise mean is
-            // reproduced to the last few ulps by an extended-precision sum
-            long double acc = 0;
-            for (int i = 0; i < n_az; ++i) acc += (long double)((double)i / prm->prf);
-            const double mean = (double)(acc / n_az);
-            for (int i = 0; i < n_az; ++i) pl->cross_range[i] = ((double)i / prm->prf - mean) * Vr;
-        }
-        std::vector<RowCoef> h(n_az);
-        const long double dtl = dt, t0 = prm->t_start;
-        const long double df = (long double)prm->fs / n_rg;
-        for (int rho = 0; rho < n_az; ++rho) {
-            const int k1 = rho / pl->A2, k2 = rho % pl->A2;
-            const int kk = k1 + pl->A1 * k2;                       // Doppler bin held by this row
-            const int ks = (kk < (n_az + 1) / 2) ? kk : kk - n_az;  // fftfreq sign convention
-            const double fa = (double)ks / ((double)n_az * (1.0 / prm->prf));  // np.fft.fftfreq(n, d): k/(n d)
-            double arg = 1.0 - (lam * fa / (2.0 * Vr)) * (lam * fa / (2.0 * Vr));
-            if (arg < 0) arg = 1e-9;                                // :246
-            const double D = sqrt(arg);
-            const double Cs = (1.0 / D) - 1.0;
-            const double tau_ref = 2.0 * R_ref / (c * D);
-            const long double cs = Cs, d1 = t0 - (long double)tau_ref;
-            RowCoef r{};
-            r.a1 = to_fix(-(Kr * cs / 2) * dtl * dtl);
-            r.b1 = to_fix(-(Kr * cs) * dtl * d1);
-            r.c1 = to_fix(-(Kr * cs / 2) * d1 * d1);
-            r.a2 = to_fix(df * df / (2.0L * Kr * (1.0L + cs)));
-            const long double b2 = 2.0L * R_ref * cs * df / c;
-            r.b2 = to_fix(b2);
-            r.bn2 = r.b2 * (uint64_t)n_rg;
-            const long double e3 = t0 - 2.0L * R_ref / c;
-            const long double q3 = (long double)Kr * cs * (1.0L + cs);
-            r.a3 = to_fix(-(q3 / 2) * dtl * dtl);
-            r.b3 = to_fix((long double)c * D * dtl / lam - q3 * dtl * e3);
-            r.c3 = to_fix((long double)c * D * t0 / lam - (q3 / 2) * e3 * e3);
-            h[rho] = r;
-        }
-        FAIL_IF(cudaMalloc(&pl->coef, n_az * sizeof(RowCoef)) == cudaSuccess ? NIS_OK : NIS_ERR_NOMEM);
-        NIS_CUDA_TRY(cudaMemcpy(pl->coef, h.data(), n_az * sizeof(RowCoef), cudaMemcpyHostToDevice));
-    }
-    if (cudaMalloc(&pl->work, (size_t)n_az * n_rg * sizeof(float2)) != cudaSuccess) {
-        set_error("nis_csa_plan_create: cannot allocate %zu-byte workspace", (size_t)n_az * n_rg * sizeof(float2));
-        nis_csa_plan_destroy(pl);
-        return NIS_ERR_NOMEM;
     }
 #undef FAIL_IF
     *out = pl;
@@ -456,6 +437,8 @@ extern "C" int nis_csa_focus(nis_csa_plan* pl, const nis_c32* phist, int64_t pit
     NIS_REQUIRE(pl && phist && slc, "nis_csa_focus: null argument");
     NIS_REQUIRE(pitch >= pl->n_rg, "nis_csa_focus: pitch %lld < n_rg %d", (long long)pitch, pl->n_rg);
     cudaStream_t st = (cudaStream_t)stream;
+    if (pl->size_class == 2)
+        return generic_focus(pl, reinterpret_cast<const float2*>(phist), pitch, reinterpret_cast<float2*>(slc), max_sq, st);
     cudaEvent_t* ev = pl->profiling ? pl->prof_ev[pl->prof_calls % nis_csa_plan::kProfRing] : nullptr;
 #define STAGE_MARK(i) do { if (ev) NIS_CUDA_TRY(cudaEventRecord(ev[i], st)); } while (0)
     int rc;

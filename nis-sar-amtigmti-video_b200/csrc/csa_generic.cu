@@ -1,0 +1,452 @@
+// csa_generic.cu -- Chirp Scaling focusing for sizes that are not powers of two (the reference's
+// default scene is 7199 x 13200 after the DPCA pulse shift, sar_ati_dcpa_sim_csa.py:402-403).
+//
+// Every transform is a row transform; the two azimuth transforms run on corner-turned data:
+//   transpose  raw[n_az][n_rg] -> T[n_rg][n_az]      (T is the caller's slc buffer)
+//   k_row<AZ_FWD>   T   rows: azimuth DFT
+//   transpose  T -> W[n_az][n_rg]
+//   k_row<RANGE>    W   rows: x Phi1, range DFT, x Phi2, inverse range DFT, x Phi3
+//   transpose  W -> T
+//   k_row<AZ_INV>   T   rows: inverse azimuth DFT, 1/(n_az n_rg)  => slc[n_rg][n_az]
+// A length is handled by one of two engines:
+//   mixed radix  (all prime factors <= 13, length <= 14000): generalised Stockham passes between two
+//                shared-memory row buffers, radix-2/4/8/16 butterflies from fft.cuh, odd radices as a
+//                small DFT with twiddles from the exp(-2 pi i m / N) table;
+//   Bluestein    (any length <= 8192): x[n] a[n] -> FFT_M -> x FFT_M(b)/M -> IFFT_M -> x a[k], a[n] =
+//                exp(-i pi n^2 / N), M in {64, 256, 1024, 4096, 16384} >= 2N-1, on the register-resident
+//                power-of-two transforms of fft.cuh.
+#include <complex>
+
+#include "csa_internal.cuh"
+#include "fft.cuh"
+
+using namespace nis;
+using namespace nis::fft;
+using namespace nis::csa;
+
+namespace {
+
+constexpr int kMaxPass = 12;
+constexpr int kMaxMixedLen = 14000;   // 2 row buffers of float2 must fit 227 KB of shared memory
+constexpr int kMaxBluesteinLen = 8192;
+
+enum Mode { AZ_FWD = 0, RANGE = 1, AZ_INV = 2 };
+
+struct GenDev {   // by-value kernel argument
+    int N, npass, M;
+    int radix[kMaxPass];
+    const float2* twN;
+    const float2* chirp;
+    const float2* bfft;
+    const float2* tw_pow2;
+};
+
+struct GenLen {
+    int N = 0, kind = 0 /* 0 mixed, 1 Bluestein */, npass = 0, M = 0;
+    int radix[kMaxPass] = {};
+    float2 *twN = nullptr, *chirp = nullptr, *bfft = nullptr, *tw_pow2 = nullptr;
+    GenDev dev() const {
+        GenDev d{};
+        d.N = N; d.npass = npass; d.M = M;
+        for (int i = 0; i < kMaxPass; ++i) d.radix[i] = radix[i];
+        d.twN = twN; d.chirp = chirp; d.bfft = bfft; d.tw_pow2 = tw_pow2;
+        return d;
+    }
+    void release() { cudaFree(twN); cudaFree(chirp); cudaFree(bfft); cudaFree(tw_pow2); }
+};
+
+bool factorize(int n, int* radix, int* npass) {
+    int k = 0;
+    const int pow2[] = {16, 8, 4, 2};
+    for (int p : pow2)
+        while (n % p == 0 && k < kMaxPass) { radix[k++] = p; n /= p; }
+    const int odd[] = {13, 11, 7, 5, 3};
+    for (int p : odd)
+        while (n % p == 0 && k < kMaxPass) { radix[k++] = p; n /= p; }
+    *npass = k;
+    return n == 1 && k > 0;
+}
+bool smooth(int n) {
+    int r[kMaxPass], k;
+    return n >= 2 && n <= kMaxMixedLen && factorize(n, r, &k);
+}
+int bluestein_m(int n) {
+    const int ms[] = {64, 256, 1024, 4096, 16384};
+    for (int m : ms)
+        if (m >= 2 * n - 1) return m;
+    return 0;
+}
+bool length_supported(int n) { return smooth(n) || (n >= 2 && n <= kMaxBluesteinLen && bluestein_m(n) > 0); }
+
+// ----------------------------------------------------------------------------- mixed radix engine
+template <int R, bool INV>
+__device__ __forceinline__ void mixed_pass(const float2* __restrict__ src, float2* __restrict__ dst, int N, int Ns,
+                                           const float2* __restrict__ twN) {
+    const int nb = N / R, stride = N / (Ns * R);
+    constexpr bool kPow2 = (R & (R - 1)) == 0;
+    float2 wr[R];
+    if constexpr (!kPow2) {
+#pragma unroll
+        for (int m = 0; m < R; ++m) wr[m] = __ldg(twN + m * nb);
+    }
+    for (int j = threadIdx.x; j < nb; j += blockDim.x) {
+        const int k = j % Ns, base = (j / Ns) * Ns * R + k;
+        float2 v[R];
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            float2 x = src[j + r * nb];
+            if (r > 0 && Ns > 1) {
+                const float2 w = __ldg(twN + k * r * stride);
+                x = INV ? cmul_conj(x, w) : cmul(x, w);
+            }
+            v[r] = x;
+        }
+        if constexpr (kPow2) {
+            fft_dif<R, INV, 1>(v);
+            constexpr int L = ilog2(R);
+#pragma unroll
+            for (int q = 0; q < R; ++q) dst[base + q * Ns] = v[brev(q, L)];
+        } else {
+#pragma unroll
+            for (int q = 0; q < R; ++q) {
+                float2 acc = v[0];
+#pragma unroll
+                for (int r = 1; r < R; ++r) {
+                    const float2 w = wr[(r * q) % R];
+                    const float2 t = INV ? cmul_conj(v[r], w) : cmul(v[r], w);
+                    acc.x += t.x; acc.y += t.y;
+                }
+                dst[base + q * Ns] = acc;
+            }
+        }
+    }
+}
+
+// DFT of the row in `a` using `b` as the other buffer; returns the buffer that holds the result.
+// Ends with a __syncthreads().
+template <bool INV>
+__device__ float2* mixed_dft(const GenDev& g, float2* a, float2* b) {
+    int Ns = 1;
+    for (int p = 0; p < g.npass; ++p) {
+        const int R = g.radix[p];
+        switch (R) {
+            case 2: mixed_pass<2, INV>(a, b, g.N, Ns, g.twN); break;
+            case 3: mixed_pass<3, INV>(a, b, g.N, Ns, g.twN); break;
+            case 4: mixed_pass<4, INV>(a, b, g.N, Ns, g.twN); break;
+            case 5: mixed_pass<5, INV>(a, b, g.N, Ns, g.twN); break;
+            case 7: mixed_pass<7, INV>(a, b, g.N, Ns, g.twN); break;
+            case 8: mixed_pass<8, INV>(a, b, g.N, Ns, g.twN); break;
+            case 11: mixed_pass<11, INV>(a, b, g.N, Ns, g.twN); break;
+            case 13: mixed_pass<13, INV>(a, b, g.N, Ns, g.twN); break;
+            default: mixed_pass<16, INV>(a, b, g.N, Ns, g.twN); break;
+        }
+        __syncthreads();
+        Ns *= R;
+        float2* t = a; a = b; b = t;
+    }
+    return a;
+}
+
+template <int MODE>
+__global__ void k_row_mixed(GenDev g, float2* __restrict__ data, int64_t pitch, int n_rows,
+                            const RowCoef* __restrict__ coef, float scale, float* __restrict__ max_sq) {
+    extern __shared__ float2 sm[];
+    float2* b0 = sm;
+    float2* b1 = sm + g.N;
+    float mx = 0.f;
+    for (int row = blockIdx.x; row < n_rows; row += gridDim.x) {
+        float2* p = data + (int64_t)row * pitch;
+        RowCoef rc{};
+        if (MODE == RANGE) rc = coef[row];
+        for (int n = threadIdx.x; n < g.N; n += blockDim.x) {
+            float2 x = p[n];
+            if (MODE == RANGE) x = cmul(x, cis_u64(quad_phase(rc.a1, rc.b1, rc.c1, (uint32_t)n)));
+            b0[n] = x;
+        }
+        __syncthreads();
+        float2* cur = (MODE == AZ_INV) ? mixed_dft<true>(g, b0, b1) : mixed_dft<false>(g, b0, b1);
+        if (MODE == RANGE) {
+            float2* other = (cur == b0) ? b1 : b0;
+            for (int k = threadIdx.x; k < g.N; k += blockDim.x)
+                cur[k] = cmul(cur[k], cis_u64(phi2_phase(rc, (uint32_t)k, (uint32_t)g.N)));
+            __syncthreads();
+            cur = mixed_dft<true>(g, cur, other);
+            for (int n = threadIdx.x; n < g.N; n += blockDim.x)
+                p[n] = cmul(cur[n], cis_u64(quad_phase(rc.a3, rc.b3, rc.c3, (uint32_t)n)));
+        } else {
+            for (int n = threadIdx.x; n < g.N; n += blockDim.x) {
+                float2 x = cur[n];
+                if (MODE == AZ_INV) {
+                    x.x *= scale; x.y *= scale;
+                    mx = fmaxf(mx, fmaf(x.x, x.x, x.y * x.y));
+                }
+                p[n] = x;
+            }
+        }
+        __syncthreads();
+    }
+    if (MODE == AZ_INV && max_sq != nullptr) {
+        mx = warp_max(mx);
+        if ((threadIdx.x & 31) == 0) atomicMax(reinterpret_cast<unsigned int*>(max_sq), __float_as_uint(mx));
+    }
+}
+
+// ------------------------------------------------------------------------------- Bluestein engine
+// On entry v[s] = x[idx] a[idx] (idx = t + NT s < N, else 0) for the forward transform (conj(a) for
+// the inverse); on exit v[s] = X[idx] for idx < N.
+template <class P, int PAD, bool INV>
+__device__ __forceinline__ void bluestein_core(float2* v, int t, float2* sm, const GenDev& g) {
+    constexpr int E = P::E, NT = P::NT;
+    transform<P, false, 1, PAD>(v, t, sm, g.tw_pow2);
+#pragma unroll
+    for (int s = 0; s < E; ++s) {
+        const float2 h = __ldg(g.bfft + t + NT * s);
+        v[s] = INV ? cmul_conj(v[s], h) : cmul(v[s], h);
+    }
+    __syncthreads();
+    transform<P, true, 1, PAD>(v, t, sm, g.tw_pow2);
+#pragma unroll
+    for (int s = 0; s < E; ++s) {
+        const int idx = t + NT * s;
+        if (idx < g.N) {
+            const float2 a = __ldg(g.chirp + idx);
+            v[s] = INV ? cmul_conj(v[s], a) : cmul(v[s], a);
+        }
+    }
+    __syncthreads();
+}
+
+template <int MODE, class P, int PAD>
+__global__ void __launch_bounds__(P::NT) k_row_blue(GenDev g, float2* __restrict__ data, int64_t pitch, int n_rows,
+                                                    const RowCoef* __restrict__ coef, float scale,
+                                                    float* __restrict__ max_sq) {
+    extern __shared__ float2 sm[];
+    constexpr int E = P::E, NT = P::NT;
+    const int t = threadIdx.x;
+    float mx = 0.f;
+    for (int row = blockIdx.x; row < n_rows; row += gridDim.x) {
+        float2* p = data + (int64_t)row * pitch;
+        RowCoef rc{};
+        if (MODE == RANGE) rc = coef[row];
+        float2 v[E];
+#pragma unroll
+        for (int s = 0; s < E; ++s) {
+            const int idx = t + NT * s;
+            float2 x = make_float2(0.f, 0.f);
+            if (idx < g.N) {
+                x = p[idx];
+                if (MODE == RANGE) x = cmul(x, cis_u64(quad_phase(rc.a1, rc.b1, rc.c1, (uint32_t)idx)));
+                const float2 a = __ldg(g.chirp + idx);
+                x = (MODE == AZ_INV) ? cmul_conj(x, a) : cmul(x, a);
+            }
+            v[s] = x;
+        }
+        if (MODE == AZ_INV) bluestein_core<P, PAD, true>(v, t, sm, g);
+        else bluestein_core<P, PAD, false>(v, t, sm, g);
+        if (MODE == RANGE) {
+#pragma unroll
+            for (int s = 0; s < E; ++s) {
+                const int idx = t + NT * s;
+                float2 x = make_float2(0.f, 0.f);
+                if (idx < g.N) {
+                    x = cmul(v[s], cis_u64(phi2_phase(rc, (uint32_t)idx, (uint32_t)g.N)));
+                    x = cmul_conj(x, __ldg(g.chirp + idx));
+                }
+                v[s] = x;
+            }
+            bluestein_core<P, PAD, true>(v, t, sm, g);
+        }
+#pragma unroll
+        for (int s = 0; s < E; ++s) {
+            const int idx = t + NT * s;
+            if (idx < g.N) {
+                float2 x = v[s];
+                if (MODE == RANGE) x = cmul(x, cis_u64(quad_phase(rc.a3, rc.b3, rc.c3, (uint32_t)idx)));
+                if (MODE == AZ_INV) {
+                    x.x *= scale; x.y *= scale;
+                    mx = fmaxf(mx, fmaf(x.x, x.x, x.y * x.y));
+                }
+                p[idx] = x;
+            }
+        }
+    }
+    if (MODE == AZ_INV && max_sq != nullptr) {
+        mx = warp_max(mx);
+        if ((threadIdx.x & 31) == 0) atomicMax(reinterpret_cast<unsigned int*>(max_sq), __float_as_uint(mx));
+    }
+}
+
+// --------------------------------------------------------------------------------------- host side
+using P64 = Plan<64, 8, 8, 8, 1>;
+using P256 = Plan<256, 16, 16, 16, 1>;
+using P1024 = Plan<1024, 16, 16, 8, 8>;
+using P4096 = Plan<4096, 16, 16, 16, 16>;
+using P16384 = Plan<16384, 32, 32, 32, 16>;
+
+void host_fft(std::vector<std::complex<double>>& a) {   // in-place radix-2, forward
+    const size_t n = a.size();
+    for (size_t i = 1, j = 0; i < n; ++i) {
+        size_t bit = n >> 1;
+        for (; j & bit; bit >>= 1) j ^= bit;
+        j ^= bit;
+        if (i < j) std::swap(a[i], a[j]);
+    }
+    const double two_pi = 6.283185307179586476925286766559;
+    for (size_t len = 2; len <= n; len <<= 1) {
+        for (size_t i = 0; i < n; i += len)
+            for (size_t k = 0; k < len / 2; ++k) {
+                const double ang = -two_pi * (double)k / (double)len;
+                const std::complex<double> w(cos(ang), sin(ang));
+                const std::complex<double> u = a[i + k], v = a[i + k + len / 2] * w;
+                a[i + k] = u + v;
+                a[i + k + len / 2] = u - v;
+            }
+    }
+}
+
+int upload(const std::vector<float2>& h, float2** dev) {
+    NIS_CUDA_TRY(cudaMalloc(dev, (h.size() + 1) * sizeof(float2)));
+    NIS_CUDA_TRY(cudaMemcpy(*dev, h.data(), h.size() * sizeof(float2), cudaMemcpyHostToDevice));
+    return NIS_OK;
+}
+
+template <class P>
+int upload_pow2_twiddles(float2** dev) {
+    std::vector<float2> h(P::tw_len + 1);
+    build_twiddles<P>(h.data());
+    return upload(h, dev);
+}
+
+int build_length(int n, GenLen* g) {
+    g->N = n;
+    const double pi = 3.14159265358979323846264338327950288;
+    if (smooth(n)) {
+        g->kind = 0;
+        factorize(n, g->radix, &g->npass);
+        std::vector<float2> tw(n);
+        for (int m = 0; m < n; ++m) {
+            const double a = -2.0 * pi * (double)m / (double)n;
+            tw[m] = make_float2((float)cos(a), (float)sin(a));
+        }
+        return upload(tw, &g->twN);
+    }
+    g->kind = 1;
+    g->M = bluestein_m(n);
+    const int M = g->M;
+    std::vector<float2> chirp(n);
+    std::vector<std::complex<double>> b(M, 0.0);
+    for (int i = 0; i < n; ++i) {
+        const long long q = ((long long)i * i) % (2LL * n);   // n^2 mod 2N keeps the argument exact
+        const double a = pi * (double)q / (double)n;
+        chirp[i] = make_float2((float)cos(a), (float)-sin(a));        // a[n] = exp(-i pi n^2 / N)
+        const std::complex<double> bv(cos(a), sin(a));                // b[n] = conj(a[n])
+        b[i] = bv;
+        if (i > 0) b[M - i] = bv;
+    }
+    host_fft(b);
+    std::vector<float2> bf(M);
+    for (int i = 0; i < M; ++i) bf[i] = make_float2((float)(b[i].real() / M), (float)(b[i].imag() / M));
+    int rc;
+    if ((rc = upload(chirp, &g->chirp)) != NIS_OK) return rc;
+    if ((rc = upload(bf, &g->bfft)) != NIS_OK) return rc;
+    switch (M) {
+        case 64: return upload_pow2_twiddles<P64>(&g->tw_pow2);
+        case 256: return upload_pow2_twiddles<P256>(&g->tw_pow2);
+        case 1024: return upload_pow2_twiddles<P1024>(&g->tw_pow2);
+        case 4096: return upload_pow2_twiddles<P4096>(&g->tw_pow2);
+        default: return upload_pow2_twiddles<P16384>(&g->tw_pow2);
+    }
+}
+
+template <int MODE, class P, int PAD>
+int launch_blue(nis_ctx* ctx, const GenLen& g, float2* data, int64_t pitch, int n_rows, const RowCoef* coef,
+                float scale, float* max_sq, cudaStream_t st) {
+    constexpr int SMROW = P::N + (PAD ? (P::N >> PAD) : 0);
+    const size_t smem = (size_t)SMROW * sizeof(float2);
+    static bool attr_done = false;
+    if (!attr_done) {
+        NIS_CUDA_TRY(cudaFuncSetAttribute(k_row_blue<MODE, P, PAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_done = true;
+    }
+    int per_sm = 1;
+    NIS_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_row_blue<MODE, P, PAD>, P::NT, smem));
+    int grid = ctx->num_sms * (per_sm < 1 ? 1 : per_sm);
+    if (grid > n_rows) grid = n_rows;
+    k_row_blue<MODE, P, PAD><<<grid, P::NT, smem, st>>>(g.dev(), data, pitch, n_rows, coef, scale, max_sq);
+    NIS_LAUNCH_CHECK(ctx);
+    return NIS_OK;
+}
+
+template <int MODE>
+int launch_row(nis_ctx* ctx, const GenLen& g, float2* data, int64_t pitch, int n_rows, const RowCoef* coef,
+               float scale, float* max_sq, cudaStream_t st) {
+    if (g.kind == 1) {
+        switch (g.M) {
+            case 64: return launch_blue<MODE, P64, 3>(ctx, g, data, pitch, n_rows, coef, scale, max_sq, st);
+            case 256: return launch_blue<MODE, P256, 4>(ctx, g, data, pitch, n_rows, coef, scale, max_sq, st);
+            case 1024: return launch_blue<MODE, P1024, 4>(ctx, g, data, pitch, n_rows, coef, scale, max_sq, st);
+            case 4096: return launch_blue<MODE, P4096, 4>(ctx, g, data, pitch, n_rows, coef, scale, max_sq, st);
+            default: return launch_blue<MODE, P16384, 5>(ctx, g, data, pitch, n_rows, coef, scale, max_sq, st);
+        }
+    }
+    const size_t smem = 2 * (size_t)g.N * sizeof(float2);
+    static bool attr_done = false;
+    if (!attr_done) {
+        NIS_CUDA_TRY(cudaFuncSetAttribute(k_row_mixed<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        attr_done = true;
+    }
+    int threads = (g.N / 8 + 31) / 32 * 32;
+    if (threads < 64) threads = 64;
+    if (threads > 512) threads = 512;
+    int per_sm = 1;
+    NIS_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_row_mixed<MODE>, threads, smem));
+    int grid = ctx->num_sms * (per_sm < 1 ? 1 : per_sm);
+    if (grid > n_rows) grid = n_rows;
+    k_row_mixed<MODE><<<grid, threads, smem, st>>>(g.dev(), data, pitch, n_rows, coef, scale, max_sq);
+    NIS_LAUNCH_CHECK(ctx);
+    return NIS_OK;
+}
+
+}  // namespace
+
+namespace nis {
+namespace csa {
+
+struct GenericState {
+    GenLen az, rg;
+};
+
+int generic_supported(int n_az, int n_rg) { return length_supported(n_az) && length_supported(n_rg); }
+
+int generic_create(nis_csa_plan* pl) {
+    pl->generic = new GenericState();
+    int rc;
+    if ((rc = build_length(pl->n_az, &pl->generic->az)) != NIS_OK) return rc;
+    if ((rc = build_length(pl->n_rg, &pl->generic->rg)) != NIS_OK) return rc;
+    return NIS_OK;
+}
+
+void generic_destroy(nis_csa_plan* pl) {
+    if (!pl->generic) return;
+    pl->generic->az.release();
+    pl->generic->rg.release();
+    delete pl->generic;
+    pl->generic = nullptr;
+}
+
+int generic_focus(nis_csa_plan* pl, const float2* phist, int64_t pitch, float2* slc, float* max_sq, cudaStream_t st) {
+    nis_ctx* ctx = pl->ctx;
+    const int n_az = pl->n_az, n_rg = pl->n_rg;
+    const float scale = (float)(1.0 / ((double)n_az * (double)n_rg));
+    int rc;
+    if ((rc = launch_transpose(ctx, phist, pitch, slc, n_az, n_rg, st)) != NIS_OK) return rc;
+    if ((rc = launch_row<AZ_FWD>(ctx, pl->generic->az, slc, n_az, n_rg, nullptr, 1.f, nullptr, st)) != NIS_OK) return rc;
+    if ((rc = launch_transpose(ctx, slc, n_az, pl->work, n_rg, n_az, st)) != NIS_OK) return rc;
+    if ((rc = launch_row<RANGE>(ctx, pl->generic->rg, pl->work, n_rg, n_az, pl->coef, 1.f, nullptr, st)) != NIS_OK) return rc;
+    if ((rc = launch_transpose(ctx, pl->work, n_rg, slc, n_az, n_rg, st)) != NIS_OK) return rc;
+    if ((rc = launch_row<AZ_INV>(ctx, pl->generic->az, slc, n_az, n_rg, nullptr, scale, max_sq, st)) != NIS_OK) return rc;
+    return NIS_OK;
+}
+
+}  // namespace csa
+}  // namespace nis

@@ -1,0 +1,105 @@
+#!/usr/bin/env python
+"""Kernel-level timing harness (development tool): per-stage CSA times, echo and GMTI throughput for a
+list of sizes.  Prints one JSON line per measurement.  Usage: python tools/kbench.py [sizes...]"""
+import json
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "nis-sar-amtigmti-video_b200"))
+
+import numpy as np
+import torch
+
+from nis_sar import device as dev, params, scenes
+
+PEAK = 6549.1
+
+
+def time_cuda(fn, iters=10, warm=3):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(iters):
+        fn()
+    b.record()
+    torch.cuda.synchronize()
+    return a.elapsed_time(b) / iters
+
+
+def csa_stages(n_az, n_rg, iters=10):
+    prm = params.spaceborne_preset()
+    plan = dev.CsaPlan(n_az, n_rg, lam=prm.Lambda, kr=prm.k_rate, fs=prm.FS, prf=prm.PRF, vr=prm.V_eff, r_ref=prm.R0,
+                       t_start=prm.t_start_fast)
+    x = torch.view_as_complex(torch.randn((n_az, n_rg, 2), device="cuda"))
+    out = torch.empty((n_rg, n_az), dtype=torch.complex64, device="cuda")
+    total = time_cuda(lambda: plan.focus(x, out=out), iters)
+    rec = {"what": "csa", "n_az": n_az, "n_rg": n_rg, "ms": total,
+           "GBps_48B": 48.0 * n_az * n_rg / total * 1e-6, "frac": 48.0 * n_az * n_rg / total * 1e-6 / PEAK}
+    try:
+        plan.set_profiling(True)
+        for _ in range(iters):
+            plan.focus(x, out=out)
+        st = {k: 0.0 for k in plan.STAGES}
+        for b in range(iters):
+            for k, v in plan.stage_times(b).items():
+                st[k] += v / iters
+        rec["stages_ms"] = st
+        rec["stages_GBps"] = {k: 16.0 * n_az * n_rg / v * 1e-6 for k, v in st.items()}
+    except Exception as e:  # general-size path has no stage events
+        rec["stages_ms"] = str(e)[:60]
+    plan.close()
+    print(json.dumps(rec), flush=True)
+
+
+def gmti(n):
+    a = torch.view_as_complex(torch.randn((n, n, 2), device="cuda"))
+    b = torch.view_as_complex(torch.randn((n, n, 2), device="cuda"))
+    ms = time_cuda(lambda: dev.gmti_fused(a, b), 5)
+    print(json.dumps({"what": "gmti_all_products", "n": n, "ms": ms, "GBps_49B": 49.0 * n * n / ms * 1e-6}), flush=True)
+    ms = time_cuda(lambda: dev.gmti_fused(a, b, want=("ati_phase_masked",)), 5)
+    print(json.dumps({"what": "gmti_phase_det_only", "n": n, "ms": ms, "GBps_20B": 20.0 * n * n / ms * 1e-6}), flush=True)
+
+
+def echo(kind):
+    if kind == "stripmap8192":
+        sc = scenes.stripmap_scene(8192, 8192)
+        prm = sc["prm"]
+        kw = dict(c=prm.C, fc=prm.FC, k_rate=prm.k_rate, t_p=prm.T_p, t_start=prm.t_start_fast, fs=600e6, n_samples=8192)
+        args = (sc["pos"], np.zeros(3), sc["rcs"], sc["pos_sat"], None, sc["t_vec"])
+    elif kind == "ati_default_256p":
+        sc = scenes.ati_scene(seed=0, num_pulses=256, num_clutter=5000)
+        prm = sc["prm"]
+        kw = dict(c=prm.C, fc=prm.FC, k_rate=prm.k_rate, t_p=prm.T_p, t_start=prm.t_start_fast, fs=prm.FS, n_samples=13200)
+        vhat = sc["vel_tx"] / np.linalg.norm(sc["vel_tx"], axis=1)[:, None]
+        args = (sc["clutter_pos"], np.zeros(3), sc["clutter_rcs"], sc["pos_tx"], sc["pos_tx"] + vhat * sc["rx_offsets"][0], sc["t_vec"])
+    else:
+        sc = scenes.vehicle_scene(seed=0, num_pulses=1024, num_scatterers=20000)
+        prm = sc["prm"]
+        from oracle import sar_oracle as orc
+        kw = dict(c=prm.C, fc=prm.FC, k_rate=prm.k_rate, t_p=prm.T_p, t_start=orc.vehicle_window_start(prm.as_globals()),
+                  fs=360e6, n_samples=2048)
+        args = (sc["pos"], np.zeros(3), sc["rcs"], sc["pos_sat"], None, sc["t_vec"])
+    out = dev.echo_accumulate(*args, **kw)
+    ms = time_cuda(lambda: dev.echo_accumulate(*args, out=out, **kw), 3, 1)
+    T, P, S = len(args[2]), len(args[5]), kw["n_samples"]
+    print(json.dumps({"what": "echo", "kind": kind, "T": T, "P": P, "S": S, "ms": ms,
+                      "G_updates_per_s_nominal": T * P * S / ms * 1e-6,
+                      "Gsamples_per_s": P * S / ms * 1e-6}), flush=True)
+
+
+if __name__ == "__main__":
+    what = sys.argv[1:] or ["csa:4096x4096", "csa:8192x8192", "gmti:4096", "echo:stripmap8192", "echo:ati_default_256p",
+                            "echo:vehicle"]
+    for w in what:
+        k, _, arg = w.partition(":")
+        if k == "csa":
+            a, b = arg.split("x")
+            csa_stages(int(a), int(b))
+        elif k == "gmti":
+            gmti(int(arg))
+        elif k == "echo":
+            echo(arg)
