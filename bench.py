@@ -242,12 +242,19 @@ def run_gpu_arm(args):
             dist.barrier()
         torch.cuda.synchronize(device)
 
-    for _ in range(max(args.warmup, 3)):
+    # clocks are sampled from before the warm-up to the end of the timed region (nvidia-smi needs a
+    # few 100 ms to start; the warm-up runs at least that long under the same load)
+    sampler = ClockSampler(local) if rank == 0 else None
+    t_w = time.perf_counter()
+    n_warm = 0
+    while n_warm < max(args.warmup, 3) or time.perf_counter() - t_w < 1.0:
         step_resident()
+        n_warm += 1
+        if n_warm % 16 == 0:
+            torch.cuda.synchronize(device)
     barrier()
 
     # ------------------------------------------------ device-timed region (inputs resident in HBM)
-    sampler = ClockSampler(local) if rank == 0 else None
     launches0 = _lib.launch_count(local)
     evs = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(args.steps)]
     t_begin, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -279,7 +286,9 @@ def run_gpu_arm(args):
         return img
 
     e2e_steps = max(2, min(args.steps, 5))
-    step_e2e()
+    for _ in range(3):          # pinned host blocks of the caching allocator are in steady state after 2 calls
+        img = step_e2e()
+    del img
     barrier()
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
@@ -302,6 +311,14 @@ def run_gpu_arm(args):
 
     pixels = float(N_AZ) * N_RG
     ms_per_step = total_ms / args.steps
+    # share of (scatterer, pulse, sample) triples that fall inside the chirp support (exact count on a pulse subset)
+    sub = np.linspace(0, N_AZ - 1, 64).astype(int)
+    d = np.linalg.norm(sc["pos"][None, :, :] - sc["pos_sat"][sub][:, None, :], axis=2)
+    tau = 2 * d / prm.C
+    tf = dev.fast_time_axis(prm.t_start_fast, N_RG, 600e6)
+    lo = np.searchsorted(tf, tau.ravel(), side="left")
+    hi = np.searchsorted(tf, tau.ravel() + prm.T_p, side="right")
+    in_support = float(np.mean((hi - lo) / N_RG))
     value = world * pixels / (ms_per_step * 1e-3) / 1e6
     peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.isfile(peaks_path):
@@ -336,6 +353,8 @@ def run_gpu_arm(args):
                      "stages_ms": stage},
         "echo": {"ms": echo_ms, "gsamples_per_s": pixels / (echo_ms * 1e-3) / 1e9,
                  "g_scatterer_samples_per_s": GRID_SIDE * GRID_SIDE * pixels / (echo_ms * 1e-3) / 1e9,
+                 "in_support_fraction": in_support,
+                 "g_in_support_updates_per_s": in_support * GRID_SIDE * GRID_SIDE * pixels / (echo_ms * 1e-3) / 1e9,
                  "bound": "fp32 issue / MUFU (not HBM)"},
         "csa": {"ms": csa_ms, "mpixels_per_s": pixels / (csa_ms * 1e-3) / 1e6},
         "clocks": clocks,

@@ -120,41 +120,77 @@ __global__ void __launch_bounds__(P::NT* W) k_az_inner(float2* __restrict__ data
 }
 
 // ------------------------------------------------------------------------------ range
-// One Doppler row per thread group: x Phi1 -> FFT -> x Phi2 -> IFFT -> x Phi3, one HBM round trip.
-template <class P, int PAD, int RPB>
-__global__ void __launch_bounds__(P::NT* RPB, (P::NT * RPB <= 256 && P::E <= 16) ? 2 : 1) k_range(float2* __restrict__ data, int64_t pitch, int n_rows,
-                                                      const RowCoef* __restrict__ coef,
-                                                      const float2* __restrict__ tw) {
+// Quadratic phase a n^2 + b n + c (64-bit fixed-point turns) stepped along n = n0, n0+step, ... by
+// second differences: two 64-bit adds per sample, exact (integer wrap-around == mod 1).
+struct PhaseStepper {
+    uint64_t ph, d, dd;
+    __device__ __forceinline__ void init(uint64_t a, uint64_t b, uint64_t c, uint32_t n0, uint32_t step) {
+        ph = a * (uint64_t)(n0 * n0) + b * (uint64_t)n0 + c;
+        d = a * (uint64_t)(2u * n0 * step + step * step) + b * (uint64_t)step;
+        dd = a * (uint64_t)(2u * step * step);
+    }
+    // descending argument m0, m0-step, ... of the quadratic term with an ascending linear term
+    // (negative range-frequency bins of Phi2: a (N-k)^2 + b k - b N)
+    __device__ __forceinline__ void init_mirror(uint64_t a, uint64_t b, uint64_t bn, uint32_t m0, uint32_t k0,
+                                                uint32_t step) {
+        ph = a * (uint64_t)(m0 * m0) + b * (uint64_t)k0 - bn;
+        d = a * (uint64_t)(step * step) - a * (uint64_t)(2u * m0 * step) + b * (uint64_t)step;
+        dd = a * (uint64_t)(2u * step * step);
+    }
+    __device__ __forceinline__ float2 next() {
+        const float2 w = cis_u64(ph);
+        ph += d;
+        d += dd;
+        return w;
+    }
+};
+
+// One Doppler row per group of NT threads: x Phi1 -> FFT -> x Phi2 -> IFFT -> x Phi3, one HBM round
+// trip.  RPB independent row groups share a CTA (named barriers, so groups drift apart and overlap
+// each other's load / exchange / store phases).
+template <class P, int PAD, int RPB, int MINB>
+__global__ void __launch_bounds__(P::NT* RPB, MINB) k_range(float2* __restrict__ data, int64_t pitch, int n_rows,
+                                                            const RowCoef* __restrict__ coef,
+                                                            const float2* __restrict__ tw) {
     extern __shared__ float2 smem[];
     constexpr int E = P::E, NT = P::NT, N = P::N;
     constexpr int SMROW = N + (PAD ? (N >> PAD) : 0);
+    static_assert(E % 2 == 0, "positive / negative frequency halves split the register slots");
     const int t = threadIdx.x;
     float2* sm = smem + threadIdx.y * SMROW;
-    for (int rb = blockIdx.x * RPB; rb < n_rows; rb += gridDim.x * RPB) {
-        const int row = min(rb + (int)threadIdx.y, n_rows - 1);
-        const bool live = rb + (int)threadIdx.y < n_rows;
-        const RowCoef rc = coef[row];
+    const NamedBarrier bar{1 + (int)threadIdx.y, NT};
+    for (int row = blockIdx.x * RPB + threadIdx.y; row < n_rows; row += gridDim.x * RPB) {
+        const RowCoef* rc = coef + row;
         float2* p = data + (int64_t)row * pitch;
         float2 v[E];
 #pragma unroll
         for (int s = 0; s < E; ++s) v[s] = p[t + NT * s];
+        {
+            PhaseStepper ps;
+            ps.init(__ldg(&rc->a1), __ldg(&rc->b1), __ldg(&rc->c1), (uint32_t)t, NT);
 #pragma unroll
-        for (int s = 0; s < E; ++s)
-            v[s] = cmul(v[s], cis_u64(quad_phase(rc.a1, rc.b1, rc.c1, (uint32_t)(t + NT * s))));
-        transform<P, false, 1, PAD>(v, t, sm, tw);
-#pragma unroll
-        for (int s = 0; s < E; ++s) {
-            const uint64_t ph = phi2_phase(rc, (uint32_t)(t + NT * s), (uint32_t)N);
-            v[s] = cmul(v[s], cis_u64(ph));
+            for (int s = 0; s < E; ++s) v[s] = cmul(v[s], ps.next());
         }
-        __syncthreads();
-        transform<P, true, 1, PAD>(v, t, sm, tw);
-        if (live) {
+        transform<P, false, 1, PAD>(v, t, sm, tw, bar);
+        {
+            const uint64_t a2 = __ldg(&rc->a2), b2 = __ldg(&rc->b2);
+            PhaseStepper ps;
+            ps.init(a2, b2, 0ull, (uint32_t)t, NT);
 #pragma unroll
-            for (int s = 0; s < E; ++s)
-                p[t + NT * s] = cmul(v[s], cis_u64(quad_phase(rc.a3, rc.b3, rc.c3, (uint32_t)(t + NT * s))));
+            for (int s = 0; s < E / 2; ++s) v[s] = cmul(v[s], ps.next());
+            ps.init_mirror(a2, b2, __ldg(&rc->bn2), (uint32_t)(N / 2 - t), (uint32_t)(N / 2 + t), NT);
+#pragma unroll
+            for (int s = E / 2; s < E; ++s) v[s] = cmul(v[s], ps.next());
         }
-        __syncthreads();
+        bar();
+        transform<P, true, 1, PAD>(v, t, sm, tw, bar);
+        {
+            PhaseStepper ps;
+            ps.init(__ldg(&rc->a3), __ldg(&rc->b3), __ldg(&rc->c3), (uint32_t)t, NT);
+#pragma unroll
+            for (int s = 0; s < E; ++s) p[t + NT * s] = cmul(v[s], ps.next());
+        }
+        bar();
     }
 }
 
@@ -209,22 +245,22 @@ int launch_inner(nis_csa_plan* pl, bool inv, cudaStream_t st) {
     return NIS_OK;
 }
 
-template <class P, int PAD, int RPB>
+template <class P, int PAD, int RPB, int MINB>
 int launch_range(nis_csa_plan* pl, cudaStream_t st) {
     constexpr int SMROW = P::N + (PAD ? (P::N >> PAD) : 0);
     const size_t smem = (size_t)SMROW * RPB * sizeof(float2);
     static bool attr_done = false;
     if (!attr_done) {
-        NIS_CUDA_TRY(cudaFuncSetAttribute(k_range<P, PAD, RPB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        NIS_CUDA_TRY(cudaFuncSetAttribute(k_range<P, PAD, RPB, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr_done = true;
     }
     int per_sm = 1;
-    NIS_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_range<P, PAD, RPB>, P::NT * RPB, smem));
+    NIS_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_range<P, PAD, RPB, MINB>, P::NT * RPB, smem));
     if (per_sm < 1) per_sm = 1;
     const int blocks_needed = (pl->n_az + RPB - 1) / RPB;
     int grid = pl->ctx->num_sms * per_sm;
     if (grid > blocks_needed) grid = blocks_needed;
-    k_range<P, PAD, RPB><<<grid, dim3(P::NT, RPB), smem, st>>>(pl->work, pl->n_rg, pl->n_az, pl->coef, pl->tw_rg);
+    k_range<P, PAD, RPB, MINB><<<grid, dim3(P::NT, RPB), smem, st>>>(pl->work, pl->n_rg, pl->n_az, pl->coef, pl->tw_rg);
     NIS_LAUNCH_CHECK(pl->ctx);
     return NIS_OK;
 }
@@ -238,8 +274,8 @@ using P512 = Plan<512, 16, 8, 8, 8>;
 using P1024 = Plan<1024, 16, 16, 8, 8>;
 using P2048 = Plan<2048, 16, 16, 16, 8>;
 using P4096 = Plan<4096, 16, 16, 16, 16>;
-using P8192 = Plan<8192, 32, 32, 16, 16>;
-using P16384 = Plan<16384, 32, 32, 32, 16>;
+using P8192 = Plan<8192, 16, 16, 8, 8, 8>;
+using P16384 = Plan<16384, 16, 16, 16, 8, 8>;
 
 template <class P>
 int upload_twiddles(float2** dev) {
@@ -394,20 +430,20 @@ extern "C" int nis_csa_plan_create(nis_ctx* ctx, int32_t n_az, int32_t n_rg, con
     switch (pl->A2) {
         case 16: pl->inner = launch_inner<P16, 32>; FAIL_IF(upload_twiddles<P16>(&pl->tw_inner)); break;
         case 64: pl->inner = launch_inner<P64, 32>; FAIL_IF(upload_twiddles<P64>(&pl->tw_inner)); break;
-        case 256: pl->inner = launch_inner<P256, 32>; FAIL_IF(upload_twiddles<P256>(&pl->tw_inner)); break;
-        case 512: pl->inner = launch_inner<P512, 16>; FAIL_IF(upload_twiddles<P512>(&pl->tw_inner)); break;
+        case 256: pl->inner = launch_inner<P256, 16>; FAIL_IF(upload_twiddles<P256>(&pl->tw_inner)); break;
+        case 512: pl->inner = launch_inner<P512, 8>; FAIL_IF(upload_twiddles<P512>(&pl->tw_inner)); break;
         default: pl->inner = launch_inner<P1024, 16>; FAIL_IF(upload_twiddles<P1024>(&pl->tw_inner)); break;
     }
     switch (n_rg) {
-        case 64: pl->range = launch_range<P64, 3, 8>; FAIL_IF(upload_twiddles<P64>(&pl->tw_rg)); break;
-        case 128: pl->range = launch_range<P128, 4, 8>; FAIL_IF(upload_twiddles<P128>(&pl->tw_rg)); break;
-        case 256: pl->range = launch_range<P256, 4, 8>; FAIL_IF(upload_twiddles<P256>(&pl->tw_rg)); break;
-        case 512: pl->range = launch_range<P512, 3, 4>; FAIL_IF(upload_twiddles<P512>(&pl->tw_rg)); break;
-        case 1024: pl->range = launch_range<P1024, 4, 4>; FAIL_IF(upload_twiddles<P1024>(&pl->tw_rg)); break;
-        case 2048: pl->range = launch_range<P2048, 4, 2>; FAIL_IF(upload_twiddles<P2048>(&pl->tw_rg)); break;
-        case 4096: pl->range = launch_range<P4096, 4, 1>; FAIL_IF(upload_twiddles<P4096>(&pl->tw_rg)); break;
-        case 8192: pl->range = launch_range<P8192, 5, 1>; FAIL_IF(upload_twiddles<P8192>(&pl->tw_rg)); break;
-        default: pl->range = launch_range<P16384, 5, 1>; FAIL_IF(upload_twiddles<P16384>(&pl->tw_rg)); break;
+        case 64: pl->range = launch_range<P64, 3, 8, 1>; FAIL_IF(upload_twiddles<P64>(&pl->tw_rg)); break;
+        case 128: pl->range = launch_range<P128, 4, 8, 1>; FAIL_IF(upload_twiddles<P128>(&pl->tw_rg)); break;
+        case 256: pl->range = launch_range<P256, 4, 8, 1>; FAIL_IF(upload_twiddles<P256>(&pl->tw_rg)); break;
+        case 512: pl->range = launch_range<P512, 3, 4, 2>; FAIL_IF(upload_twiddles<P512>(&pl->tw_rg)); break;
+        case 1024: pl->range = launch_range<P1024, 4, 4, 2>; FAIL_IF(upload_twiddles<P1024>(&pl->tw_rg)); break;
+        case 2048: pl->range = launch_range<P2048, 4, 2, 2>; FAIL_IF(upload_twiddles<P2048>(&pl->tw_rg)); break;
+        case 4096: pl->range = launch_range<P4096, 4, 2, 1>; FAIL_IF(upload_twiddles<P4096>(&pl->tw_rg)); break;
+        case 8192: pl->range = launch_range<P8192, 4, 1, 1>; FAIL_IF(upload_twiddles<P8192>(&pl->tw_rg)); break;
+        default: pl->range = launch_range<P16384, 4, 1, 1>; FAIL_IF(upload_twiddles<P16384>(&pl->tw_rg)); break;
     }
     // ---- full-length azimuth twiddles w_N^m
     {

@@ -152,25 +152,38 @@ __global__ void __launch_bounds__(256) k_echo(EchoConst k, EchoTail<SPT> tail, c
             float2 u = cis_u32(phi);
             u.x *= a; u.y *= a;
             const float2 v = cis_u32(dlt);
+            // four independent phasor chains (even / odd samples, forward / backward from the centre
+            // sample) stepped by v^2, so that consecutive multiplies do not wait on each other
+            const float2 v2 = cmul(v, v);
+            float2 pf0 = u, pf1 = cmul(u, v), pb0 = cmul_conj(u, v), pb1 = cmul_conj(u, v2);
             if (t_lo >= lo && t_hi <= hi) {
-                float2 p = u;
 #pragma unroll
-                for (int j = HALF; j < SPT; ++j) { acc[j] = cadd(acc[j], p); p = cmul(p, v); }
-                p = cmul_conj(u, v);
-#pragma unroll
-                for (int j = HALF - 1; j >= 0; --j) { acc[j] = cadd(acc[j], p); p = cmul_conj(p, v); }
-            } else {
-                float2 p = u;
-#pragma unroll
-                for (int j = HALF; j < SPT; ++j) {
-                    if (t_lo + j >= lo && t_lo + j < hi) acc[j] = cadd(acc[j], p);
-                    p = cmul(p, v);
+                for (int i = 0; i < SPT / 4; ++i) {
+                    acc[HALF + 2 * i] = cadd(acc[HALF + 2 * i], pf0);
+                    acc[HALF + 2 * i + 1] = cadd(acc[HALF + 2 * i + 1], pf1);
+                    acc[HALF - 1 - 2 * i] = cadd(acc[HALF - 1 - 2 * i], pb0);
+                    acc[HALF - 2 - 2 * i] = cadd(acc[HALF - 2 - 2 * i], pb1);
+                    if (i + 1 < SPT / 4) {
+                        pf0 = cmul(pf0, v2); pf1 = cmul(pf1, v2);
+                        pb0 = cmul_conj(pb0, v2); pb1 = cmul_conj(pb1, v2);
+                    }
                 }
-                p = cmul_conj(u, v);
+            } else {
+                const int a = lo - t_lo, b = hi - t_lo;   // live samples: a <= j < b
 #pragma unroll
-                for (int j = HALF - 1; j >= 0; --j) {
-                    if (t_lo + j >= lo && t_lo + j < hi) acc[j] = cadd(acc[j], p);
-                    p = cmul_conj(p, v);
+                for (int i = 0; i < SPT / 4; ++i) {
+                    int j = HALF + 2 * i;
+                    if (j >= a && j < b) acc[j] = cadd(acc[j], pf0);
+                    j = HALF + 2 * i + 1;
+                    if (j >= a && j < b) acc[j] = cadd(acc[j], pf1);
+                    j = HALF - 1 - 2 * i;
+                    if (j >= a && j < b) acc[j] = cadd(acc[j], pb0);
+                    j = HALF - 2 - 2 * i;
+                    if (j >= a && j < b) acc[j] = cadd(acc[j], pb1);
+                    if (i + 1 < SPT / 4) {
+                        pf0 = cmul(pf0, v2); pf1 = cmul(pf1, v2);
+                        pb0 = cmul_conj(pb0, v2); pb1 = cmul_conj(pb1, v2);
+                    }
                 }
             }
         }

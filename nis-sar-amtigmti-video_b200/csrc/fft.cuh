@@ -84,17 +84,20 @@ __host__ __device__ __forceinline__ void fft_dif(float2* v) {
 }
 
 // ---------------------------------------------------------------------------------------------
-// Plan of up to three radix passes R0*R1*R2 = N (R2 == 1 means a two-pass plan, R1 == 1 one pass).
-template <int N_, int E_, int R0_, int R1_, int R2_>
+// Plan of up to four radix passes R0*R1*R2*R3 = N (trailing radices equal to 1 are skipped).
+template <int N_, int E_, int R0_, int R1_, int R2_, int R3_ = 1>
 struct Plan {
-    static constexpr int N = N_, E = E_, NT = N_ / E_, R0 = R0_, R1 = R1_, R2 = R2_;
-    static_assert(R0_ * R1_ * R2_ == N_, "radices must multiply to N");
-    static_assert(E_ >= R0_ && E_ >= R1_ && E_ >= R2_, "E must hold the largest butterfly");
-    static constexpr int passes = (R2_ > 1) ? 3 : ((R1_ > 1) ? 2 : 1);
-    // twiddle table: pass 1 has (R1-1)*R0 entries, pass 2 has (R2-1)*R0*R1 entries
+    static constexpr int N = N_, E = E_, NT = N_ / E_, R0 = R0_, R1 = R1_, R2 = R2_, R3 = R3_;
+    static_assert(R0_ * R1_ * R2_ * R3_ == N_, "radices must multiply to N");
+    static_assert(E_ >= R0_ && E_ >= R1_ && E_ >= R2_ && E_ >= R3_, "E must hold the largest butterfly");
+    static_assert(R3_ == 1 || R2_ > 1, "radices must be packed to the front");
+    static_assert(R2_ == 1 || R1_ > 1, "radices must be packed to the front");
+    static constexpr int passes = (R3_ > 1) ? 4 : ((R2_ > 1) ? 3 : ((R1_ > 1) ? 2 : 1));
+    // twiddle table: pass p >= 1 has (Rp - 1) * (R0..Rp-1) entries
     static constexpr int tw_off1 = 0;
     static constexpr int tw_off2 = (R1_ > 1) ? (R1_ - 1) * R0_ : 0;
-    static constexpr int tw_len = tw_off2 + ((R2_ > 1) ? (R2_ - 1) * R0_ * R1_ : 0);
+    static constexpr int tw_off3 = tw_off2 + ((R2_ > 1) ? (R2_ - 1) * R0_ * R1_ : 0);
+    static constexpr int tw_len = tw_off3 + ((R3_ > 1) ? (R3_ - 1) * R0_ * R1_ * R2_ : 0);
 };
 
 template <int PADSHIFT>
@@ -158,26 +161,43 @@ __host__ __device__ __forceinline__ void pass_unpermute(float2* v) {
 // inverse share one table.
 // sm: base pointer of this transform's shared buffer (already offset to this column when SMS > 1).
 // All threads of the CTA must call it (it uses __syncthreads()).
-template <class P, bool INV, int SMS, int PADSHIFT>
-__device__ __forceinline__ void transform(float2* v, int t, float2* sm, const float2* __restrict__ tw) {
+struct CtaBarrier {   // default: the whole CTA takes part in the transform
+    __device__ __forceinline__ void operator()() const { __syncthreads(); }
+};
+struct NamedBarrier {  // a sub-group of the CTA (e.g. one row of a multi-row block): bar.sync id, count
+    int id, count;
+    __device__ __forceinline__ void operator()() const { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
+};
+
+template <class P, bool INV, int SMS, int PADSHIFT, class Bar = CtaBarrier>
+__device__ __forceinline__ void transform(float2* v, int t, float2* sm, const float2* __restrict__ tw, Bar bar = Bar()) {
     constexpr int E = P::E, NT = P::NT;
     pass_compute<E, NT, P::R0, 1, INV>(v, t, tw);
     if constexpr (P::passes == 1) {
         pass_unpermute<E, P::R0>(v);
     } else {
         pass_scatter<E, NT, P::R0, 1, SMS, PADSHIFT>(v, t, sm);
-        __syncthreads();
+        bar();
         gather_slots<E, NT, SMS, PADSHIFT>(v, t, sm);
         pass_compute<E, NT, P::R1, P::R0, INV>(v, t, tw + P::tw_off1);
         if constexpr (P::passes == 2) {
             pass_unpermute<E, P::R1>(v);
         } else {
-            __syncthreads();
+            bar();
             pass_scatter<E, NT, P::R1, P::R0, SMS, PADSHIFT>(v, t, sm);
-            __syncthreads();
+            bar();
             gather_slots<E, NT, SMS, PADSHIFT>(v, t, sm);
             pass_compute<E, NT, P::R2, P::R0 * P::R1, INV>(v, t, tw + P::tw_off2);
-            pass_unpermute<E, P::R2>(v);
+            if constexpr (P::passes == 3) {
+                pass_unpermute<E, P::R2>(v);
+            } else {
+                bar();
+                pass_scatter<E, NT, P::R2, P::R0 * P::R1, SMS, PADSHIFT>(v, t, sm);
+                bar();
+                gather_slots<E, NT, SMS, PADSHIFT>(v, t, sm);
+                pass_compute<E, NT, P::R3, P::R0 * P::R1 * P::R2, INV>(v, t, tw + P::tw_off3);
+                pass_unpermute<E, P::R3>(v);
+            }
         }
     }
 }
@@ -200,6 +220,14 @@ inline void build_twiddles(float2* out) {
             for (int k = 0; k < Ns; ++k) {
                 double a = -two_pi * (double)r * (double)k / ((double)Ns * R);
                 out[P::tw_off2 + (r - 1) * Ns + k] = make_float2((float)cos(a), (float)sin(a));
+            }
+    }
+    if (P::R3 > 1) {
+        const int Ns = P::R0 * P::R1 * P::R2, R = P::R3;
+        for (int r = 1; r < R; ++r)
+            for (int k = 0; k < Ns; ++k) {
+                double a = -two_pi * (double)r * (double)k / ((double)Ns * R);
+                out[P::tw_off3 + (r - 1) * Ns + k] = make_float2((float)cos(a), (float)sin(a));
             }
     }
 }

@@ -37,7 +37,16 @@ double run_plan() {
             for (int t = 0; t < NT; ++t) gather_slots<E, NT, SMS, PADSHIFT>(v[t].data(), t, sm.data());
             for (int t = 0; t < NT; ++t)
                 pass_compute<E, NT, P::R2, P::R0 * P::R1, INV>(v[t].data(), t, tw.data() + P::tw_off2);
-            for (int t = 0; t < NT; ++t) pass_unpermute<E, P::R2>(v[t].data());
+            if (P::passes == 3) {
+                for (int t = 0; t < NT; ++t) pass_unpermute<E, P::R2>(v[t].data());
+            } else {
+                for (int t = 0; t < NT; ++t)
+                    pass_scatter<E, NT, P::R2, P::R0 * P::R1, SMS, PADSHIFT>(v[t].data(), t, sm.data());
+                for (int t = 0; t < NT; ++t) gather_slots<E, NT, SMS, PADSHIFT>(v[t].data(), t, sm.data());
+                for (int t = 0; t < NT; ++t)
+                    pass_compute<E, NT, P::R3, P::R0 * P::R1 * P::R2, INV>(v[t].data(), t, tw.data() + P::tw_off3);
+                for (int t = 0; t < NT; ++t) pass_unpermute<E, P::R3>(v[t].data());
+            }
         }
     }
     // reference DFT in double
@@ -88,6 +97,11 @@ int main() {
     CHECK(P2048, 1, 4);
     CHECK(P4096, 1, 4);
     CHECK(P8192, 1, 5);
+    using Q8192 = Plan<8192, 16, 16, 8, 8, 8>;
+    using Q16384 = Plan<16384, 16, 16, 16, 8, 8>;
+    using Q512 = Plan<512, 8, 8, 8, 8>;
+    using Q4096 = Plan<4096, 8, 8, 8, 8, 8>;
+    CHECK(Q8192, 1, 4); CHECK(Q16384, 1, 4); CHECK(Q512, 1, 3); CHECK(Q4096, 1, 3);
     printf(fails ? "FAILED %d\n" : "all ok\n", fails);
     return fails != 0;
 }
