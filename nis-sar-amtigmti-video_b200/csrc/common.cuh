@@ -86,11 +86,14 @@ __host__ __device__ __forceinline__ uint64_t turns_to_u64(double t) {
 // exp(j 2 pi u/2^32): top 32 bits of the phase -> signed turns in [-0.5,0.5) -> MUFU sin/cos.
 // Absolute error ~5e-7 (MUFU.SIN/COS on a reduced argument).
 __device__ __forceinline__ float2 cis_u32(uint32_t u) {
-    float t = (float)(int32_t)u * 2.3283064365386963e-10f;  // * 2^-32 -> turns in [-0.5, 0.5)
-    float a = t * 6.283185307179586f;
+    // top 23 phase bits become the mantissa of a float in [1, 2): no int->float conversion (which
+    // would share the quarter-rate pipe with the two MUFU ops).  a = 2 pi (f - 1.5) in [-pi, pi);
+    // the half-turn offset is undone by negating both outputs.
+    const float f = __uint_as_float(((u + 0x100u) >> 9) | 0x3f800000u);   // rounded, wraps mod 1
+    const float a = fmaf(f, 6.283185307179586f, -9.42477796076938f);
     float s, c;
     __sincosf(a, &s, &c);
-    return make_float2(c, s);
+    return make_float2(-c, -s);
 }
 __device__ __forceinline__ float2 cis_u64(uint64_t u) { return cis_u32((uint32_t)(u >> 32)); }
 

@@ -24,6 +24,8 @@
 
 #include <vector>
 
+#include <type_traits>
+
 #include "csa_internal.cuh"
 #include "fft.cuh"
 
@@ -158,8 +160,20 @@ __global__ void __launch_bounds__(P::NT* RPB, MINB) k_range(float2* __restrict__
     static_assert(E % 2 == 0, "positive / negative frequency halves split the register slots");
     const int t = threadIdx.x;
     float2* sm = smem + threadIdx.y * SMROW;
-    const NamedBarrier bar{1 + (int)threadIdx.y, NT};
-    for (int row = blockIdx.x * RPB + threadIdx.y; row < n_rows; row += gridDim.x * RPB) {
+    // bar.sync counts whole warps: row groups narrower than a warp (or a single group) use the CTA barrier
+    constexpr bool kNamed = (NT >= 32) && (RPB > 1);
+    using Bar = typename std::conditional<kNamed, NamedBarrier, CtaBarrier>::type;
+    Bar bar;
+    if constexpr (kNamed) bar = NamedBarrier{1 + (int)threadIdx.y, NT};
+    // with the CTA barrier every group must run the same number of iterations: the last ones may idle
+    const int n_iter = (n_rows + gridDim.x * RPB - 1) / (gridDim.x * RPB);
+    for (int it = 0; it < n_iter; ++it) {
+        int row = (it * gridDim.x + blockIdx.x) * RPB + threadIdx.y;
+        const bool live = row < n_rows;
+        if (!live) {
+            if constexpr (kNamed) break;
+            row = n_rows - 1;
+        }
         const RowCoef* rc = coef + row;
         float2* p = data + (int64_t)row * pitch;
         float2 v[E];
@@ -188,7 +202,10 @@ __global__ void __launch_bounds__(P::NT* RPB, MINB) k_range(float2* __restrict__
             PhaseStepper ps;
             ps.init(__ldg(&rc->a3), __ldg(&rc->b3), __ldg(&rc->c3), (uint32_t)t, NT);
 #pragma unroll
-            for (int s = 0; s < E; ++s) p[t + NT * s] = cmul(v[s], ps.next());
+            for (int s = 0; s < E; ++s) {
+                const float2 x = cmul(v[s], ps.next());
+                if (live) p[t + NT * s] = x;
+            }
         }
         bar();
     }

@@ -1,0 +1,126 @@
+"""Multi-GPU partitioning of the hot path (one process per GPU, torch.distributed for the plumbing).
+
+The path shards along independent units; a collective appears only where the
+algorithm has a real exchange step:
+
+  echo, few scatterers / many pulses   pulse blocks            no collective (optional all-gather of rows)
+  echo, dense scatterer scenes         scatterer shards        sum all-reduce / reduce of the partial echoes
+  CSA, VideoSAR frame sequences        whole frames            none
+  HRWS / ATI receive channels          one channel per rank    neighbour exchange of one SLC, then K3 per pair
+
+Every function takes the per-rank compute step as a callable, so the same partition / collective logic
+runs under NCCL with the CUDA operators (``nis_sar.device``) and, in the CPU test-suite, under gloo.
+Complex tensors travel as their float32 (re, im) view: NCCL reduces real dtypes.
+"""
+from __future__ import annotations
+
+from typing import Callable, Sequence
+
+import torch
+import torch.distributed as dist
+
+
+def world(group=None):
+    if not dist.is_available() or not dist.is_initialized():
+        return 0, 1
+    return dist.get_rank(group), dist.get_world_size(group)
+
+
+def block_range(n: int, rank: int, nranks: int):
+    """Contiguous block partition of range(n): the first n % nranks ranks get one extra unit."""
+    base, extra = divmod(n, nranks)
+    lo = rank * base + min(rank, extra)
+    return lo, lo + base + (1 if rank < extra else 0)
+
+
+def _as_real(t: torch.Tensor) -> torch.Tensor:
+    return torch.view_as_real(t) if t.is_complex() else t
+
+
+# ------------------------------------------------------------------------------------------ echo
+def echo_pulse_blocks(compute: Callable[[int, int, torch.Tensor], None], raw: torch.Tensor, gather: bool = False,
+                      group=None) -> torch.Tensor:
+    """Pulse-block sharding: rank r fills rows [p0, p1) of ``raw`` ([P, S] complex64, same shape on every
+    rank) by calling ``compute(p0, p1, raw)``.  With ``gather`` the blocks are exchanged so that every
+    rank ends with the whole aperture (needed only when one rank must focus the full frame)."""
+    rank, n = world(group)
+    P = raw.shape[0]
+    p0, p1 = block_range(P, rank, n)
+    if p1 > p0:
+        compute(p0, p1, raw)
+    if gather and n > 1:
+        # equal-sized padded blocks for all_gather_into_tensor
+        blk = -(-P // n)
+        send = torch.zeros((blk,) + tuple(raw.shape[1:]), dtype=raw.dtype, device=raw.device)
+        send[: p1 - p0] = raw[p0:p1]
+        recv = torch.empty((n * blk,) + tuple(raw.shape[1:]), dtype=raw.dtype, device=raw.device)
+        dist.all_gather_into_tensor(_as_real(recv), _as_real(send), group=group)
+        for r in range(n):
+            q0, q1 = block_range(P, r, n)
+            raw[q0:q1] = recv[r * blk: r * blk + (q1 - q0)]
+    return raw
+
+
+def echo_scatterer_shards(compute: Callable[[int, int], torch.Tensor], num_scatterers: int, dst: int | None = None,
+                          group=None) -> torch.Tensor:
+    """Scatterer sharding (config 3: 1e5 scatterers): rank r synthesises the partial echo of scatterers
+    [t0, t1) over the whole [P, S] grid with ``compute(t0, t1)`` and the partial sums are added across
+    ranks -- ``dst`` None: all-reduce (every rank gets the echo); else reduce to rank ``dst``.
+    fp32 summation order differs from the one-GPU run, so results agree to rounding, not bit-wise."""
+    rank, n = world(group)
+    t0, t1 = block_range(num_scatterers, rank, n)
+    part = compute(t0, t1)
+    if n > 1:
+        if dst is None:
+            dist.all_reduce(_as_real(part), op=dist.ReduceOp.SUM, group=group)
+        else:
+            dist.reduce(_as_real(part), dst=dst, op=dist.ReduceOp.SUM, group=group)
+    return part
+
+
+# ------------------------------------------------------------------------------------------- CSA
+def frame_indices(num_frames: int, group=None) -> range:
+    """Round-robin frame ownership for VideoSAR sequences: rank r focuses frames r, r+n, r+2n, ..."""
+    rank, n = world(group)
+    return range(rank, num_frames, n)
+
+
+def focus_frames(focus: Callable[[int], torch.Tensor], num_frames: int, group=None) -> dict:
+    """Frame-parallel focusing: no data-path collective.  Returns {frame index: focused SLC} for the
+    frames this rank owns."""
+    return {f: focus(f) for f in frame_indices(num_frames, group)}
+
+
+# ------------------------------------------------------------------------------- channel pairing
+def exchange_with_next(slc_local: torch.Tensor, group=None) -> torch.Tensor | None:
+    """One receive channel per rank: returns the SLC of channel rank+1 (None on the last rank) so that
+    rank k can form the DPCA/ATI pair (k, k+1).  A ring shift of one [N_rg, N_az] complex64 image
+    (134 MB at 4096^2) over NVLink: isend to rank-1, irecv from rank+1."""
+    rank, n = world(group)
+    if n == 1:
+        return None
+    ops = []
+    recv = None
+    if rank > 0:
+        ops.append(dist.P2POp(dist.isend, _as_real(slc_local.contiguous()), rank - 1, group=group))
+    if rank < n - 1:
+        recv = torch.empty_like(slc_local)
+        ops.append(dist.P2POp(dist.irecv, _as_real(recv), rank + 1, group=group))
+    for req in dist.batch_isend_irecv(ops):
+        req.wait()
+    return recv
+
+
+def pair_products(slc_local: torch.Tensor, products: Callable[[torch.Tensor, torch.Tensor], dict], group=None):
+    """HRWS-style chain: exchange with the neighbour, then run the fused DPCA/ATI stage on the pair
+    (k, k+1) held by rank k.  The detection threshold is per reference channel, so no global reduction."""
+    other = exchange_with_next(slc_local, group)
+    return None if other is None else products(slc_local, other)
+
+
+def max_over_ranks(value: float, device, group=None) -> float:
+    """Timing reduction used by bench.py: device-measured milliseconds, maximum over ranks."""
+    t = torch.tensor([value], dtype=torch.float64, device=device)
+    if world(group)[1] > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX, group=group)
+    return float(t.item())
