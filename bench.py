@@ -213,7 +213,8 @@ def run_gpu_arm(args):
     ts_d = torch.from_numpy(np.ascontiguousarray(sc["t_vec"])).to(device)
     tf_d = torch.from_numpy(dev.fast_time_axis(prm.t_start_fast, N_RG, 600e6)).to(device)
     eprm = _lib.EchoParams(c=prm.C, fc=prm.FC, k_rate=prm.k_rate, t_p=prm.T_p, t_start=float(tf_d[0].item()),
-                           dt_fast=(N_RG / 600e6) / (N_RG - 1), per_target_velocity=0, reserved=0)
+                           dt_fast=(N_RG / 600e6) / (N_RG - 1), per_target_velocity=0,
+                           samples_per_thread=dev.chunk_hint(pos0_d, ptx_d, tf_d.cpu().numpy(), prm.T_p, prm.C))
     lib, ctx = _lib.load(), _lib.context(local)
     stream = torch.cuda.current_stream(device)
 

@@ -78,7 +78,8 @@ typedef struct {
     double t_start;  /* t_fast[0] (s) */
     double dt_fast;  /* nominal fast-time step: t_fast[n] ~= t_start + n * dt_fast */
     int32_t per_target_velocity; /* 0: tgt_vel is one xyz triple; 1: tgt_vel is [T*3] */
-    int32_t reserved;
+    int32_t samples_per_thread;  /* 0: library chooses; 8 or 16: chunk = 256 * this many samples per CTA.
+                                  * 8 suits scenes whose chirps cover well under the whole window */
 } nis_echo_params;
 
 NIS_API int nis_echo_accumulate(nis_ctx* ctx, const nis_echo_params* prm,

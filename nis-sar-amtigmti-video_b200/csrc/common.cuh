@@ -95,6 +95,14 @@ __device__ __forceinline__ float2 cis_u32(uint32_t u) {
     __sincosf(a, &s, &c);
     return make_float2(-c, -s);
 }
+// same, for a phase that already carries the +0x100 rounding offset
+__device__ __forceinline__ float2 cis_u32_pre(uint32_t u) {
+    const float f = __uint_as_float((u >> 9) | 0x3f800000u);
+    const float a = fmaf(f, 6.283185307179586f, -9.42477796076938f);
+    float s, c;
+    __sincosf(a, &s, &c);
+    return make_float2(-c, -s);
+}
 __device__ __forceinline__ float2 cis_u64(uint64_t u) { return cis_u32((uint32_t)(u >> 32)); }
 
 __device__ __forceinline__ float warp_max(float v) {

@@ -28,6 +28,7 @@
 
 #include "csa_internal.cuh"
 #include "fft.cuh"
+#include "tma.cuh"
 
 using namespace nis;
 using namespace nis::fft;
@@ -121,26 +122,82 @@ __global__ void __launch_bounds__(P::NT* W) k_az_inner(float2* __restrict__ data
     }
 }
 
+// Persistent, TMA-fed variant: each CTA walks tiles tile = x + n_col_tiles * k1; while tile i is transformed the
+// [A2 x W] box of tile i+1 is already in flight into the other shared buffer (cp.async.bulk.tensor.2d, completion
+// on an mbarrier).  The tile buffer doubles as the exchange buffer of the transform, so global loads never stall a
+// warp and stores leave straight from registers.
+template <class P, bool INV, int W>
+__global__ void __launch_bounds__(P::NT* W) k_az_inner_tma(const __grid_constant__ CUtensorMap map,
+                                                           float2* __restrict__ data, int64_t pitch, int n_az,
+                                                           int n_col_tiles, int n_tiles, const float2* __restrict__ tw,
+                                                           const float2* __restrict__ twN) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    __shared__ uint64_t full[2];
+    constexpr int E = P::E, NT = P::NT, A2 = P::N;
+    constexpr int TILE_ELEMS = A2 * W;
+    constexpr uint32_t TILE_BYTES = TILE_ELEMS * sizeof(float2);
+    constexpr int BOX_ROWS = A2 < 256 ? A2 : 256, NBOX = A2 / BOX_ROWS;
+    float2* const buf0 = reinterpret_cast<float2*>(smem_raw);
+    const int tid = threadIdx.x, c = tid % W, t = tid / W;
+    if (tid == 0) {
+        tma::mbar_init(&full[0], 1);
+        tma::mbar_init(&full[1], 1);
+        tma::fence_barrier_init();
+    }
+    __syncthreads();
+    auto issue = [&](int tile, int b) {
+        const int x = tile % n_col_tiles, k1 = tile / n_col_tiles;
+        tma::mbar_arrive_expect_tx(&full[b], TILE_BYTES);
+#pragma unroll
+        for (int i = 0; i < NBOX; ++i)
+            tma::tile_load_2d(buf0 + b * TILE_ELEMS + i * BOX_ROWS * W, &map, x * W, k1 * A2 + i * BOX_ROWS, &full[b]);
+    };
+    int tile = blockIdx.x;
+    if (tid == 0 && tile < n_tiles) issue(tile, 0);
+    for (int i = 0; tile < n_tiles; ++i, tile += gridDim.x) {
+        const int b = i & 1;
+        float2* buf = buf0 + b * TILE_ELEMS;
+        if (tid == 0 && tile + (int)gridDim.x < n_tiles) issue(tile + gridDim.x, b ^ 1);
+        tma::mbar_wait(&full[b], (i >> 1) & 1);
+        float2 v[E];
+#pragma unroll
+        for (int s = 0; s < E; ++s) v[s] = buf[(t + NT * s) * W + c];
+        __syncthreads();   // every element is in registers before the exchange overwrites the tile
+        transform<P, INV, W, 0>(v, t, buf + c, tw);
+        const int x = tile % n_col_tiles, k1 = tile / n_col_tiles;
+        float2* base = data + (int64_t)k1 * A2 * pitch + x * W + c;
+#pragma unroll
+        for (int s = 0; s < E; ++s) {
+            float2 xo = v[s];
+            if (INV) xo = cmul_conj(xo, __ldg(twN + ((k1 * (t + NT * s)) & (n_az - 1))));
+            base[(int64_t)(t + NT * s) * pitch] = xo;
+        }
+        tma::fence_proxy_async();   // this thread's exchange writes are ordered before the TMA refill of buf
+        __syncthreads();
+    }
+}
+
 // ------------------------------------------------------------------------------ range
 // Quadratic phase a n^2 + b n + c (64-bit fixed-point turns) stepped along n = n0, n0+step, ... by
 // second differences: two 64-bit adds per sample, exact (integer wrap-around == mod 1).
 struct PhaseStepper {
-    uint64_t ph, d, dd;
+    uint32_t ph, d, dd;   // top 32 bits of the exact 64-bit values: (E^2/2) 2^-32 turns of drift at most
+    static constexpr uint32_t kRound = 0x100u;   // cis_u32_pre() truncates to 23 bits: pre-add half an ulp once
     __device__ __forceinline__ void init(uint64_t a, uint64_t b, uint64_t c, uint32_t n0, uint32_t step) {
-        ph = a * (uint64_t)(n0 * n0) + b * (uint64_t)n0 + c;
-        d = a * (uint64_t)(2u * n0 * step + step * step) + b * (uint64_t)step;
-        dd = a * (uint64_t)(2u * step * step);
+        ph = (uint32_t)((a * (uint64_t)(n0 * n0) + b * (uint64_t)n0 + c) >> 32) + kRound;
+        d = (uint32_t)((a * (uint64_t)(2u * n0 * step + step * step) + b * (uint64_t)step) >> 32);
+        dd = (uint32_t)((a * (uint64_t)(2u * step * step)) >> 32);
     }
     // descending argument m0, m0-step, ... of the quadratic term with an ascending linear term
     // (negative range-frequency bins of Phi2: a (N-k)^2 + b k - b N)
     __device__ __forceinline__ void init_mirror(uint64_t a, uint64_t b, uint64_t bn, uint32_t m0, uint32_t k0,
                                                 uint32_t step) {
-        ph = a * (uint64_t)(m0 * m0) + b * (uint64_t)k0 - bn;
-        d = a * (uint64_t)(step * step) - a * (uint64_t)(2u * m0 * step) + b * (uint64_t)step;
-        dd = a * (uint64_t)(2u * step * step);
+        ph = (uint32_t)((a * (uint64_t)(m0 * m0) + b * (uint64_t)k0 - bn) >> 32) + kRound;
+        d = (uint32_t)((a * (uint64_t)(step * step) - a * (uint64_t)(2u * m0 * step) + b * (uint64_t)step) >> 32);
+        dd = (uint32_t)((a * (uint64_t)(2u * step * step)) >> 32);
     }
     __device__ __forceinline__ float2 next() {
-        const float2 w = cis_u64(ph);
+        const float2 w = cis_u32_pre(ph);
         ph += d;
         d += dd;
         return w;
@@ -154,31 +211,61 @@ template <class P, int PAD, int RPB, int MINB>
 __global__ void __launch_bounds__(P::NT* RPB, MINB) k_range(float2* __restrict__ data, int64_t pitch, int n_rows,
                                                             const RowCoef* __restrict__ coef,
                                                             const float2* __restrict__ tw) {
-    extern __shared__ float2 smem[];
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    __shared__ uint64_t full[RPB];
     constexpr int E = P::E, NT = P::NT, N = P::N;
     constexpr int SMROW = N + (PAD ? (N >> PAD) : 0);
     static_assert(E % 2 == 0, "positive / negative frequency halves split the register slots");
-    const int t = threadIdx.x;
-    float2* sm = smem + threadIdx.y * SMROW;
     // bar.sync counts whole warps: row groups narrower than a warp (or a single group) use the CTA barrier
     constexpr bool kNamed = (NT >= 32) && (RPB > 1);
+    // the next row is prefetched into shared memory by a 1-D bulk copy (TMA) while this one is transformed
+    constexpr bool kPrefetch = (NT >= 32);
+    constexpr int GROUP_ELEMS = SMROW + (kPrefetch ? N : 0);
+    const int t = threadIdx.x;
+    float2* sm = reinterpret_cast<float2*>(smem_raw) + threadIdx.y * GROUP_ELEMS;
+    float2* pf = sm + SMROW;
+    uint64_t* mb = &full[threadIdx.y];
     using Bar = typename std::conditional<kNamed, NamedBarrier, CtaBarrier>::type;
     Bar bar;
     if constexpr (kNamed) bar = NamedBarrier{1 + (int)threadIdx.y, NT};
     // with the CTA barrier every group must run the same number of iterations: the last ones may idle
-    const int n_iter = (n_rows + gridDim.x * RPB - 1) / (gridDim.x * RPB);
+    const int row_stride = gridDim.x * RPB;
+    const int n_iter = (n_rows + row_stride - 1) / row_stride;
+    const int row0 = blockIdx.x * RPB + threadIdx.y;
+    if constexpr (kPrefetch) {
+        if (t == 0) {
+            tma::mbar_init(mb, 1);
+            tma::fence_barrier_init();
+            if (row0 < n_rows) {
+                tma::mbar_arrive_expect_tx(mb, N * sizeof(float2));
+                tma::bulk_load_1d(pf, data + (int64_t)row0 * pitch, N * sizeof(float2), mb);
+            }
+        }
+        __syncthreads();
+    }
     for (int it = 0; it < n_iter; ++it) {
-        int row = (it * gridDim.x + blockIdx.x) * RPB + threadIdx.y;
+        int row = row0 + it * row_stride;
         const bool live = row < n_rows;
         if (!live) {
-            if constexpr (kNamed) break;
+            if constexpr (kNamed || (kPrefetch && RPB == 1)) break;
             row = n_rows - 1;
         }
         const RowCoef* rc = coef + row;
         float2* p = data + (int64_t)row * pitch;
         float2 v[E];
+        if constexpr (kPrefetch) {
+            tma::mbar_wait(mb, it & 1);
 #pragma unroll
-        for (int s = 0; s < E; ++s) v[s] = p[t + NT * s];
+            for (int s = 0; s < E; ++s) v[s] = pf[t + NT * s];
+            bar();   // the whole row is in registers: the prefetch buffer may be refilled
+            if (t == 0 && row + row_stride < n_rows) {
+                tma::mbar_arrive_expect_tx(mb, N * sizeof(float2));
+                tma::bulk_load_1d(pf, data + (int64_t)(row + row_stride) * pitch, N * sizeof(float2), mb);
+            }
+        } else {
+#pragma unroll
+            for (int s = 0; s < E; ++s) v[s] = p[t + NT * s];
+        }
         {
             PhaseStepper ps;
             ps.init(__ldg(&rc->a1), __ldg(&rc->b1), __ldg(&rc->c1), (uint32_t)t, NT);
@@ -244,20 +331,27 @@ int launch_outer_inv(nis_csa_plan* pl, float2* slc, float* max_sq, cudaStream_t 
 
 template <class P, int W>
 int launch_inner(nis_csa_plan* pl, bool inv, cudaStream_t st) {
-    const size_t smem = (size_t)P::N * W * sizeof(float2);
+    const size_t smem = 2 * (size_t)P::N * W * sizeof(float2);   // double-buffered tile
     static bool attr_done = false;
     if (!attr_done) {
-        NIS_CUDA_TRY(cudaFuncSetAttribute(k_az_inner<P, false, W>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        NIS_CUDA_TRY(cudaFuncSetAttribute(k_az_inner_tma<P, false, W>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                           (int)smem));
-        NIS_CUDA_TRY(cudaFuncSetAttribute(k_az_inner<P, true, W>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        NIS_CUDA_TRY(cudaFuncSetAttribute(k_az_inner_tma<P, true, W>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                           (int)smem));
         attr_done = true;
     }
-    dim3 grid(pl->n_rg / W, pl->A1);
+    int per_sm = 1;
+    NIS_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_az_inner_tma<P, false, W>, P::NT * W, smem));
+    if (per_sm < 1) per_sm = 1;
+    const int n_col_tiles = pl->n_rg / W, n_tiles = n_col_tiles * pl->A1;
+    int grid = pl->ctx->num_sms * per_sm;
+    if (grid > n_tiles) grid = n_tiles;
     if (inv)
-        k_az_inner<P, true, W><<<grid, P::NT * W, smem, st>>>(pl->work, pl->n_rg, pl->n_az, pl->tw_inner, pl->tw_full);
+        k_az_inner_tma<P, true, W><<<grid, P::NT * W, smem, st>>>(pl->tile_map, pl->work, pl->n_rg, pl->n_az,
+                                                                  n_col_tiles, n_tiles, pl->tw_inner, pl->tw_full);
     else
-        k_az_inner<P, false, W><<<grid, P::NT * W, smem, st>>>(pl->work, pl->n_rg, pl->n_az, pl->tw_inner, pl->tw_full);
+        k_az_inner_tma<P, false, W><<<grid, P::NT * W, smem, st>>>(pl->tile_map, pl->work, pl->n_rg, pl->n_az,
+                                                                   n_col_tiles, n_tiles, pl->tw_inner, pl->tw_full);
     NIS_LAUNCH_CHECK(pl->ctx);
     return NIS_OK;
 }
@@ -265,7 +359,8 @@ int launch_inner(nis_csa_plan* pl, bool inv, cudaStream_t st) {
 template <class P, int PAD, int RPB, int MINB>
 int launch_range(nis_csa_plan* pl, cudaStream_t st) {
     constexpr int SMROW = P::N + (PAD ? (P::N >> PAD) : 0);
-    const size_t smem = (size_t)SMROW * RPB * sizeof(float2);
+    constexpr int GROUP_ELEMS = SMROW + (P::NT >= 32 ? P::N : 0);   // exchange buffer + prefetch buffer
+    const size_t smem = (size_t)GROUP_ELEMS * RPB * sizeof(float2);
     static bool attr_done = false;
     if (!attr_done) {
         NIS_CUDA_TRY(cudaFuncSetAttribute(k_range<P, PAD, RPB, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -445,15 +540,15 @@ extern "C" int nis_csa_plan_create(nis_ctx* ctx, int32_t n_az, int32_t n_rg, con
                  pl->outer_inv = (pl->A2 >= 32) ? launch_outer_inv<16, 32> : launch_outer_inv<16, 16>; break;
     }
     switch (pl->A2) {
-        case 16: pl->inner = launch_inner<P16, 32>; FAIL_IF(upload_twiddles<P16>(&pl->tw_inner)); break;
-        case 64: pl->inner = launch_inner<P64, 32>; FAIL_IF(upload_twiddles<P64>(&pl->tw_inner)); break;
-        case 256: pl->inner = launch_inner<P256, 16>; FAIL_IF(upload_twiddles<P256>(&pl->tw_inner)); break;
-        case 512: pl->inner = launch_inner<P512, 8>; FAIL_IF(upload_twiddles<P512>(&pl->tw_inner)); break;
-        default: pl->inner = launch_inner<P1024, 16>; FAIL_IF(upload_twiddles<P1024>(&pl->tw_inner)); break;
+        case 16: pl->inner_w = 32; pl->inner = launch_inner<P16, 32>; FAIL_IF(upload_twiddles<P16>(&pl->tw_inner)); break;
+        case 64: pl->inner_w = 32; pl->inner = launch_inner<P64, 32>; FAIL_IF(upload_twiddles<P64>(&pl->tw_inner)); break;
+        case 256: pl->inner_w = 16; pl->inner = launch_inner<P256, 16>; FAIL_IF(upload_twiddles<P256>(&pl->tw_inner)); break;
+        case 512: pl->inner_w = 8; pl->inner = launch_inner<P512, 8>; FAIL_IF(upload_twiddles<P512>(&pl->tw_inner)); break;
+        default: pl->inner_w = 16; pl->inner = launch_inner<P1024, 16>; FAIL_IF(upload_twiddles<P1024>(&pl->tw_inner)); break;
     }
     switch (n_rg) {
         case 64: pl->range = launch_range<P64, 3, 8, 1>; FAIL_IF(upload_twiddles<P64>(&pl->tw_rg)); break;
-        case 128: pl->range = launch_range<P128, 4, 8, 1>; FAIL_IF(upload_twiddles<P128>(&pl->tw_rg)); break;
+        case 128: pl->range = launch_range<P128, 0, 8, 1>; FAIL_IF(upload_twiddles<P128>(&pl->tw_rg)); break;
         case 256: pl->range = launch_range<P256, 4, 8, 1>; FAIL_IF(upload_twiddles<P256>(&pl->tw_rg)); break;
         case 512: pl->range = launch_range<P512, 3, 4, 2>; FAIL_IF(upload_twiddles<P512>(&pl->tw_rg)); break;
         case 1024: pl->range = launch_range<P1024, 4, 4, 2>; FAIL_IF(upload_twiddles<P1024>(&pl->tw_rg)); break;
@@ -462,6 +557,7 @@ extern "C" int nis_csa_plan_create(nis_ctx* ctx, int32_t n_az, int32_t n_rg, con
         case 8192: pl->range = launch_range<P8192, 4, 1, 1>; FAIL_IF(upload_twiddles<P8192>(&pl->tw_rg)); break;
         default: pl->range = launch_range<P16384, 4, 1, 1>; FAIL_IF(upload_twiddles<P16384>(&pl->tw_rg)); break;
     }
+    FAIL_IF(tma::make_tile_map(&pl->tile_map, pl->work, n_az, n_rg, n_rg, pl->A2 < 256 ? pl->A2 : 256, pl->inner_w));
     // ---- full-length azimuth twiddles w_N^m
     {
         std::vector<float2> h(n_az);

@@ -2,6 +2,7 @@
 // (csa_generic.cu) Chirp Scaling paths.
 #pragma once
 
+#include <cuda.h>
 #include <math.h>
 
 #include <vector>
@@ -67,6 +68,8 @@ struct nis_csa_plan {
     float2* tw_full = nullptr;
     float2* tw_rg = nullptr;
     nis::csa::RowCoef* coef = nullptr;
+    CUtensorMap tile_map{};   // [n_az][n_rg] workspace, box = min(A2,256) rows x inner_w columns
+    int inner_w = 0;
     std::vector<double> range_axis, cross_range;
     // optional per-stage timing: a ring of event sets, one per nis_csa_focus call
     static constexpr int kProfRing = 64;

@@ -241,9 +241,11 @@ extern "C" int nis_echo_accumulate(nis_ctx* ctx, const nis_echo_params* prm, con
     k.T = T; k.P0 = P0; k.S = S; k.per_target_velocity = prm->per_target_velocity;
     k.accumulate = accumulate; k.bistatic = pos_rx != nullptr;
     float2* r = reinterpret_cast<float2*>(raw);
-    // chunk = 256*SPT samples: take the wider chunk unless it wastes > 12 % of its threads past S
+    // chunk = 256*SPT samples: take the wider chunk unless it wastes > 12 % of its threads past S, or the
+    // caller knows that the chirps cover only part of the window (samples_per_thread hint)
     const int waste16 = ((S + 4095) / 4096) * 4096 - S;
-    if (waste16 * 8 <= S)
+    const bool wide = prm->samples_per_thread == 16 || (prm->samples_per_thread != 8 && waste16 * 8 <= S);
+    if (wide)
         return launch_echo<16>(ctx, k, tgt_pos0, tgt_vel, tgt_amp, pos_tx, pos_rx, t_slow, t_fast, r, P1 - P0, st);
     return launch_echo<8>(ctx, k, tgt_pos0, tgt_vel, tgt_amp, pos_tx, pos_rx, t_slow, t_fast, r, P1 - P0, st);
 }

@@ -124,23 +124,42 @@ __host__ __device__ __forceinline__ void pass_compute(float2* v, int t, const fl
     }
 }
 
+// Shared-memory index padding i -> i + (i >> PADSHIFT).  All accesses below are "runtime base + compile-time
+// offset": padidx(base + c) == padidx(base) + c + (c >> PADSHIFT) whenever c is a multiple of 2^PADSHIFT, and for the
+// first pass (Ns == 1, R == 2^PADSHIFT) padidx(j R + q) == j (R + 1) + q.  The static_asserts pin the plans to those cases.
+template <int PADSHIFT>
+__host__ __device__ constexpr int padoff(int c) {
+    return PADSHIFT > 0 ? c + (c >> PADSHIFT) : c;
+}
+
 // scatter pass output to shared memory: y[(j div Ns) Ns R + k + q Ns] = V[q]
 template <int E, int NT, int R, int Ns, int SMS, int PADSHIFT>
 __host__ __device__ __forceinline__ void pass_scatter(const float2* v, int t, float2* sm) {
     constexpr int B = E / R;
     constexpr int LR = ilog2(R);
+    constexpr int G = 1 << PADSHIFT;
+    static_assert(PADSHIFT == 0 || (Ns == 1 && R <= G) || (Ns % G == 0), "padding rule needs Ns == 1 or Ns % 2^PAD == 0");
 #pragma unroll
     for (int b = 0; b < B; ++b) {
         const int j = t + b * NT;
         const int base = ((j & ~(Ns - 1)) * R) + (j & (Ns - 1));
+        float2* p = sm + padidx<PADSHIFT>(base) * SMS;
 #pragma unroll
-        for (int q = 0; q < R; ++q) sm[padidx<PADSHIFT>(base + q * Ns) * SMS] = v[b + brev(q, LR) * B];
+        for (int q = 0; q < R; ++q) {
+            // Ns == 1: base = j R is a multiple of R, q < R <= 2^PAD never carries into the padded digit
+            constexpr int dummy = 0;
+            (void)dummy;
+            const int off = (Ns == 1) ? q : padoff<PADSHIFT>(q * Ns);
+            p[off * SMS] = v[b + brev(q, LR) * B];
+        }
     }
 }
 template <int E, int NT, int SMS, int PADSHIFT>
 __host__ __device__ __forceinline__ void gather_slots(float2* v, int t, const float2* sm) {
+    static_assert(PADSHIFT == 0 || NT % (1 << PADSHIFT) == 0 || E == 1, "padding rule needs NT % 2^PAD == 0");
+    const float2* p = sm + padidx<PADSHIFT>(t) * SMS;
 #pragma unroll
-    for (int s = 0; s < E; ++s) v[s] = sm[padidx<PADSHIFT>(t + NT * s) * SMS];
+    for (int s = 0; s < E; ++s) v[s] = p[padoff<PADSHIFT>(NT * s) * SMS];
 }
 // last pass: natural-order result back into canonical slots (pure register renaming)
 template <int E, int R>

@@ -90,7 +90,7 @@ int main() {
     CHECK(P2, 1, 0); CHECK(P4, 1, 0); CHECK(P8, 1, 0);
     CHECK(P16, 1, 0); CHECK(P32, 1, 0);
     CHECK(P64, 1, 3); CHECK(P64, 32, 0);
-    CHECK(P128, 1, 4);
+    CHECK(P128, 1, 0);
     CHECK(P256, 1, 4); CHECK(P256, 16, 0);
     CHECK(P512, 1, 3);
     CHECK(P1024, 1, 4);

@@ -23,7 +23,7 @@ class NisError(RuntimeError):
 class EchoParams(C.Structure):
     _fields_ = [("c", C.c_double), ("fc", C.c_double), ("k_rate", C.c_double), ("t_p", C.c_double),
                 ("t_start", C.c_double), ("dt_fast", C.c_double),
-                ("per_target_velocity", C.c_int32), ("reserved", C.c_int32)]
+                ("per_target_velocity", C.c_int32), ("samples_per_thread", C.c_int32)]
 
 
 class CsaParams(C.Structure):

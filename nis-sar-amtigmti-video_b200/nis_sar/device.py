@@ -41,6 +41,24 @@ def fast_time_axis(t_start: float, n_samples: int, fs: float) -> np.ndarray:
     return t_start + np.linspace(0.0, n_samples / fs, n_samples)
 
 
+def chunk_hint(pos0_d, ptx_d, t_fast, t_p, c, prx_d=None) -> int:
+    """Pick the CTA chunk width of K1: when the chirps of a scene cover well under the whole receive window
+    (estimated from a few scatterers at the mid-aperture pulse), narrow chunks keep more warps busy."""
+    T, P = pos0_d.shape[0], ptx_d.shape[0]
+    if T == 0 or P == 0:
+        return 0
+    idx = torch.linspace(0, T - 1, min(T, 16)).long().to(pos0_d.device)
+    p = pos0_d[idx]
+    tx = ptx_d[P // 2]
+    d = torch.linalg.vector_norm(p - tx, dim=1)
+    d2 = d if prx_d is None else torch.linalg.vector_norm(p - prx_d[P // 2], dim=1)
+    tau = ((d + d2) / c).cpu().numpy()
+    lo = np.clip(tau, t_fast[0], t_fast[-1])
+    hi = np.clip(tau + t_p, t_fast[0], t_fast[-1])
+    frac = float(np.mean(hi - lo) / max(t_fast[-1] - t_fast[0], 1e-30))
+    return 8 if frac < 0.6 else 0
+
+
 def echo_accumulate(pos0, vel, rcs, pos_tx, pos_rx, t_slow, *, c, fc, k_rate, t_p, t_start, fs, n_samples,
                     device="cuda", out=None, accumulate=False, pulse_range=None):
     """K1.  Inputs are numpy / torch fp64 arrays (host or device); returns raw[P, S] complex64 on
@@ -77,7 +95,8 @@ def echo_accumulate(pos0, vel, rcs, pos_tx, pos_rx, t_slow, *, c, fc, k_rate, t_
         p0, p1 = (0, P) if pulse_range is None else pulse_range
         prm = _lib.EchoParams(c=c, fc=fc, k_rate=k_rate, t_p=t_p, t_start=float(t_fast[0]),
                               dt_fast=(S / fs) / (S - 1) if S > 1 else 1.0 / fs,
-                              per_target_velocity=per_target, reserved=0)
+                              per_target_velocity=per_target,
+                              samples_per_thread=chunk_hint(pos0_d, ptx_d, t_fast, t_p, c, prx_d))
         for q0 in range(p0, p1, MAX_PULSES_PER_LAUNCH):
             q1 = min(p1, q0 + MAX_PULSES_PER_LAUNCH)
             rc = lib.nis_echo_accumulate(ctx, C.byref(prm), _ptr(pos0_d), _ptr(vel_d), _ptr(amp_d), _ptr(ptx_d),
