@@ -3,10 +3,10 @@
 //
 // Data flow (complex64, one workspace W[n_az][n_rg]):
 //   k_az_outer_fwd   raw  -> W   radix-A1 butterflies down the columns (registers only) x w_N^(a2 k1)
-//   k_az_inner<fwd>  W   -> W   A2-point column FFTs on [A2 rows x 32 cols] tiles in shared memory
+//   k_az_inner_tma<fwd> W -> W  A2-point column FFTs on TMA-prefetched [A2 rows x 8..32 cols] tiles in shared memory
 //   k_range          W   -> W   per Doppler row: x Phi1, range FFT, x Phi2, range IFFT, x Phi3
-//   k_az_inner<inv>  W   -> W   A2-point inverse column FFTs x w_N^-(k1 a2)
-//   k_az_outer_inv   W   -> slc radix-A1 inverse butterflies, 1/(n_az n_rg), corner turn to [n_rg][n_az]
+//   k_az_inner_tma<inv> W -> W  A2-point inverse column FFTs
+//   k_az_outer_inv   W   -> slc x w_N^-(k1 a2), radix-A1 inverse butterflies, 1/(n_az n_rg), corner turn to [n_rg][n_az]
 // Azimuth length n_az = A1*A2 (four-step split).  Between the two azimuth transforms rows live in
 // the permuted order rho = k1*A2 + k2 <-> Doppler bin kk = k1 + A1*k2; every per-row quantity is
 // tabulated in that order, and the reference's fftshift / ifftshift pairs (:234, :280, :331, :385)
@@ -64,7 +64,8 @@ __global__ void __launch_bounds__(256) k_az_outer_fwd(const float2* __restrict__
 template <int A1, int TA>
 __global__ void __launch_bounds__(256) k_az_outer_inv(const float2* __restrict__ in, int64_t pitch,
                                                       float2* __restrict__ slc, int n_rg, int A2, int n_az,
-                                                      float scale, float* __restrict__ max_sq) {
+                                                      float scale, float* __restrict__ max_sq,
+                                                      const float2* __restrict__ twN) {
     constexpr int TN = 16;
     extern __shared__ float2 tile[];  // [A1][TN][TA+1]
     const int n0 = blockIdx.x * TN, a20 = blockIdx.y * TA;
@@ -75,7 +76,11 @@ __global__ void __launch_bounds__(256) k_az_outer_inv(const float2* __restrict__
         const int a2 = a20 + a_off + 16 * it;
         float2 v[A1];
 #pragma unroll
-        for (int k1 = 0; k1 < A1; ++k1) v[k1] = in[(int64_t)(k1 * A2 + a2) * pitch + n0 + n_off];
+        for (int k1 = 0; k1 < A1; ++k1) {
+            float2 x = in[(int64_t)(k1 * A2 + a2) * pitch + n0 + n_off];
+            if (k1 > 0) x = cmul_conj(x, __ldg(twN + ((k1 * a2) & (n_az - 1))));   // four-step twiddle w_N^-(k1 a2)
+            v[k1] = x;
+        }
         fft_dif<A1, true, 1>(v);
 #pragma unroll
         for (int a1 = 0; a1 < A1; ++a1) {
@@ -101,36 +106,16 @@ __global__ void __launch_bounds__(256) k_az_outer_inv(const float2* __restrict__
 }
 
 // ------------------------------------------------------------------------------ azimuth, inner
-// A2-point transforms down W adjacent columns of the row block [k1*A2, (k1+1)*A2); lanes <-> columns.
-template <class P, bool INV, int W>
-__global__ void __launch_bounds__(P::NT* W) k_az_inner(float2* __restrict__ data, int64_t pitch, int n_az,
-                                                       const float2* __restrict__ tw, const float2* __restrict__ twN) {
-    extern __shared__ float2 smem[];
-    constexpr int E = P::E, NT = P::NT, A2 = P::N;
-    const int c = threadIdx.x % W, t = threadIdx.x / W;
-    const int k1 = blockIdx.y;
-    float2* base = data + (int64_t)k1 * A2 * pitch + blockIdx.x * W + c;
-    float2 v[E];
-#pragma unroll
-    for (int s = 0; s < E; ++s) v[s] = base[(int64_t)(t + NT * s) * pitch];
-    transform<P, INV, W, 0>(v, t, smem + c, tw);
-#pragma unroll
-    for (int s = 0; s < E; ++s) {
-        float2 x = v[s];
-        if (INV) x = cmul_conj(x, __ldg(twN + ((k1 * (t + NT * s)) & (n_az - 1))));
-        base[(int64_t)(t + NT * s) * pitch] = x;
-    }
-}
-
-// Persistent, TMA-fed variant: each CTA walks tiles tile = x + n_col_tiles * k1; while tile i is transformed the
+// A2-point transforms down W adjacent columns of the row block [k1*A2, (k1+1)*A2); lanes <-> columns, so every
+// shared-memory access of the transform is a contiguous W*8-byte row piece (bank-conflict free).
+// Persistent and TMA-fed: each CTA walks tiles tile = x + n_col_tiles * k1; while tile i is transformed the
 // [A2 x W] box of tile i+1 is already in flight into the other shared buffer (cp.async.bulk.tensor.2d, completion
 // on an mbarrier).  The tile buffer doubles as the exchange buffer of the transform, so global loads never stall a
 // warp and stores leave straight from registers.
 template <class P, bool INV, int W>
 __global__ void __launch_bounds__(P::NT* W) k_az_inner_tma(const __grid_constant__ CUtensorMap map,
-                                                           float2* __restrict__ data, int64_t pitch, int n_az,
-                                                           int n_col_tiles, int n_tiles, const float2* __restrict__ tw,
-                                                           const float2* __restrict__ twN) {
+                                                           float2* __restrict__ data, int64_t pitch,
+                                                           int n_col_tiles, int n_tiles, const float2* __restrict__ tw) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ uint64_t full[2];
     constexpr int E = P::E, NT = P::NT, A2 = P::N;
@@ -168,9 +153,7 @@ __global__ void __launch_bounds__(P::NT* W) k_az_inner_tma(const __grid_constant
         float2* base = data + (int64_t)k1 * A2 * pitch + x * W + c;
 #pragma unroll
         for (int s = 0; s < E; ++s) {
-            float2 xo = v[s];
-            if (INV) xo = cmul_conj(xo, __ldg(twN + ((k1 * (t + NT * s)) & (n_az - 1))));
-            base[(int64_t)(t + NT * s) * pitch] = xo;
+            base[(int64_t)(t + NT * s) * pitch] = v[s];
         }
         tma::fence_proxy_async();   // this thread's exchange writes are ordered before the TMA refill of buf
         __syncthreads();
@@ -324,7 +307,7 @@ int launch_outer_inv(nis_csa_plan* pl, float2* slc, float* max_sq, cudaStream_t 
     dim3 grid(pl->n_rg / 16, pl->A2 / TA);
     const float scale = (float)(1.0 / ((double)pl->n_az * (double)pl->n_rg));
     k_az_outer_inv<A1, TA><<<grid, 256, smem, st>>>(pl->work, pl->n_rg, slc, pl->n_rg, pl->A2, pl->n_az, scale,
-                                                    max_sq);
+                                                    max_sq, pl->tw_full);
     NIS_LAUNCH_CHECK(pl->ctx);
     return NIS_OK;
 }
@@ -347,11 +330,11 @@ int launch_inner(nis_csa_plan* pl, bool inv, cudaStream_t st) {
     int grid = pl->ctx->num_sms * per_sm;
     if (grid > n_tiles) grid = n_tiles;
     if (inv)
-        k_az_inner_tma<P, true, W><<<grid, P::NT * W, smem, st>>>(pl->tile_map, pl->work, pl->n_rg, pl->n_az,
-                                                                  n_col_tiles, n_tiles, pl->tw_inner, pl->tw_full);
+        k_az_inner_tma<P, true, W><<<grid, P::NT * W, smem, st>>>(pl->tile_map, pl->work, pl->n_rg, n_col_tiles, n_tiles,
+                                                                  pl->tw_inner);
     else
-        k_az_inner_tma<P, false, W><<<grid, P::NT * W, smem, st>>>(pl->tile_map, pl->work, pl->n_rg, pl->n_az,
-                                                                   n_col_tiles, n_tiles, pl->tw_inner, pl->tw_full);
+        k_az_inner_tma<P, false, W><<<grid, P::NT * W, smem, st>>>(pl->tile_map, pl->work, pl->n_rg, n_col_tiles, n_tiles,
+                                                                   pl->tw_inner);
     NIS_LAUNCH_CHECK(pl->ctx);
     return NIS_OK;
 }
@@ -535,9 +518,9 @@ extern "C" int nis_csa_plan_create(nis_ctx* ctx, int32_t n_az, int32_t n_rg, con
     switch (pl->A1) {
         case 4: pl->outer_fwd = launch_outer_fwd<4>; pl->outer_inv = launch_outer_inv<4, 16>; break;
         case 8: pl->outer_fwd = launch_outer_fwd<8>;
-                pl->outer_inv = (pl->A2 >= 32) ? launch_outer_inv<8, 32> : launch_outer_inv<8, 16>; break;
+                pl->outer_inv = launch_outer_inv<8, 16>; break;
         default: pl->outer_fwd = launch_outer_fwd<16>;
-                 pl->outer_inv = (pl->A2 >= 32) ? launch_outer_inv<16, 32> : launch_outer_inv<16, 16>; break;
+                 pl->outer_inv = launch_outer_inv<16, 16>; break;
     }
     switch (pl->A2) {
         case 16: pl->inner_w = 32; pl->inner = launch_inner<P16, 32>; FAIL_IF(upload_twiddles<P16>(&pl->tw_inner)); break;

@@ -7,6 +7,7 @@ from . import targets, scenes  # noqa: F401
 
 _LAZY = {"run_bistatic_physics_gpu", "sar_focus_csa", "run_physics_engine", "run_moving_physics",
          "run_custom_physics", "gmti_products", "dpca_coregister", "install", "set_default_params",
+         "save_ati_dpca_npz",
          "set_default_device"}
 
 

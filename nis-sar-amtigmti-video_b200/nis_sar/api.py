@@ -169,6 +169,13 @@ def dpca_coregister(raw_rx1, raw_rx2):
     return raw_rx1[1:, :], raw_rx2[:-1, :]
 
 
+def save_ati_dpca_npz(fname, slc1, slc2, range_axis, cross_range):
+    """The hand-off file of the reference (sar_ati_dcpa_sim_csa.py:457-461): keys slc1, slc2 ([N_rg, N_az]
+    complex128), range_axis, cross_range -- what sar_ati_dcpa_viewer_csa.py:24-29 loads and transposes back."""
+    np.savez(fname, slc1=np.asarray(slc1, dtype=np.complex128), slc2=np.asarray(slc2, dtype=np.complex128),
+             range_axis=np.asarray(range_axis, dtype=np.float64), cross_range=np.asarray(cross_range, dtype=np.float64))
+
+
 # --------------------------------------------------------------------------------------- install
 _ENTRY_POINTS = ("run_bistatic_physics_gpu", "sar_focus_csa", "run_physics_engine", "run_moving_physics",
                  "run_custom_physics")

@@ -56,7 +56,7 @@ def chunk_hint(pos0_d, ptx_d, t_fast, t_p, c, prx_d=None) -> int:
     lo = np.clip(tau, t_fast[0], t_fast[-1])
     hi = np.clip(tau + t_p, t_fast[0], t_fast[-1])
     frac = float(np.mean(hi - lo) / max(t_fast[-1] - t_fast[0], 1e-30))
-    return 8 if frac < 0.6 else 0
+    return 0   # measured on B200: the narrow chunk never wins (setup per sample doubles); kept as an ABI knob
 
 
 def echo_accumulate(pos0, vel, rcs, pos_tx, pos_rx, t_slow, *, c, fc, k_rate, t_p, t_start, fs, n_samples,

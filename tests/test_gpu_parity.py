@@ -354,3 +354,27 @@ def test_csa_default_scene_shape(api, dev):
     e_in = float(torch.linalg.vector_norm(x)) ** 2
     e_out = float(torch.linalg.vector_norm(fx)) ** 2
     assert abs(e_out / e_in - 1.0) < 1e-4
+
+
+def test_npz_contract_and_viewer_products(api, tmp_path):
+    """The viewer's input file (sar_ati_dcpa_sim_csa.py:457-461) and its derived products
+    (SARData.compute_all, sar_ati_dcpa_viewer_csa.py:42-52) from GPU-focused channels."""
+    prm = params.spaceborne_preset()
+    rng = np.random.default_rng(11)
+    a = (rng.standard_normal((128, 256)) + 1j * rng.standard_normal((128, 256))).astype(np.complex64)
+    b = (a * np.exp(1j * 0.2)).astype(np.complex64)
+    args = (prm.Lambda, prm.T_p, prm.k_rate, prm.FS, prm.PRF, prm.V_eff, prm.R0, prm.t_start_fast)
+    s1, rax, cax = api.sar_focus_csa(a, *args)
+    s2, _, _ = api.sar_focus_csa(b, *args)
+    f = tmp_path / "sar_ati_dpca_data_csa.npz"
+    api.save_ati_dpca_npz(f, s1, s2, rax, cax)
+    d = np.load(f)
+    assert set(d.files) == {"slc1", "slc2", "range_axis", "cross_range"}
+    v1, v2 = d["slc1"].T, d["slc2"].T                       # the viewer transposes back (:26-27)
+    assert v1.shape == (128, 256) and d["range_axis"].shape == (256,) and d["cross_range"].shape == (128,)
+    cal = orc.balance_phase(v1, v2)                          # viewer auto-balance (:249-250)
+    out = api.gmti_products(d["slc1"], d["slc2"], 0.05, cal)
+    ref = orc.gmti_products(d["slc1"], d["slc2"], 0.05, cal)
+    assert np.array_equal(out["det_idx"], ref["det_idx"])
+    assert _rel(out["dpca_diff"], ref["dpca_diff"]) < 1e-3   # the difference is a 1e-3 residual after balancing
+    assert abs(cal - 0.2) < 1e-3 or abs(cal + 0.2) < 1e-3

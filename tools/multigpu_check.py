@@ -1,0 +1,94 @@
+#!/usr/bin/env python
+"""Multi-GPU correctness + timing of the sharded drivers in nis_sar.dist (NCCL over NVLink).
+
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port 29511 \
+        tools/multigpu_check.py
+
+Checks, with N ranks against a one-GPU computation on rank 0:
+  1. scatterer-sharded echo + sum all-reduce (config 3 style)        -> rel-L2 vs unsharded
+  2. pulse-block echo + all-gather                                    -> bit-equal vs unsharded
+  3. frame-parallel CSA (config 4 style)                              -> frames identical to a local recompute
+  4. one receive channel per rank, ring exchange, DPCA/ATI per pair   -> indices equal to a local recompute
+Prints one JSON line on rank 0."""
+import json
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "nis-sar-amtigmti-video_b200"))
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from nis_sar import device as dev, dist as nd, params, scenes
+
+
+def main():
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    device = torch.device("cuda", local)
+    dist.init_process_group("nccl", device_id=device)
+    out = {"world": world}
+
+    # ---- 1/2: echo sharding on the airborne dense-vehicle geometry
+    sc = scenes.vehicle_scene(seed=3, num_pulses=512, num_scatterers=4096)
+    prm = sc["prm"]
+    t0 = (2 * prm.R0 / prm.C) - (2048 / 360e6) / 2
+    kw = dict(c=prm.C, fc=prm.FC, k_rate=prm.k_rate, t_p=prm.T_p, t_start=t0, fs=360e6, n_samples=2048, device=device)
+    full = dev.echo_accumulate(sc["pos"], np.zeros(3), sc["rcs"], sc["pos_sat"], None, sc["t_vec"], **kw)
+
+    def shard(a, b):
+        return dev.echo_accumulate(sc["pos"][a:b], np.zeros(3), sc["rcs"][a:b], sc["pos_sat"], None, sc["t_vec"], **kw)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    dist.barrier()
+    ev0.record()
+    summed = nd.echo_scatterer_shards(shard, len(sc["rcs"]))
+    ev1.record()
+    torch.cuda.synchronize()
+    out["scatterer_shards_rel_l2"] = float(torch.linalg.vector_norm(summed - full) / torch.linalg.vector_norm(full))
+    out["scatterer_shards_ms"] = nd.max_over_ranks(ev0.elapsed_time(ev1), device)
+
+    raw = torch.zeros_like(full)
+
+    def fill(p0, p1, buf):
+        dev.echo_accumulate(sc["pos"], np.zeros(3), sc["rcs"], sc["pos_sat"], None, sc["t_vec"], out=buf,
+                            pulse_range=(p0, p1), **kw)
+    nd.echo_pulse_blocks(fill, raw, gather=True)
+    out["pulse_blocks_equal"] = bool(torch.equal(raw, full))
+
+    # ---- 3: frame-parallel CSA
+    sp = params.spaceborne_preset()
+    n = 1024
+    plan = dev.cached_plan(n, n, lam=sp.Lambda, kr=sp.k_rate, fs=sp.FS, prf=sp.PRF, vr=sp.V_eff, r_ref=sp.R0,
+                           t_start=sp.t_start_fast, device=device)
+
+    def frame(f):
+        g = torch.Generator(device=device).manual_seed(1000 + f)
+        return torch.view_as_complex(torch.randn((n, n, 2), generator=g, device=device))
+    mine = nd.focus_frames(lambda f: plan.focus(frame(f)).clone(), 8)
+    out["frames_owned"] = sorted(mine)
+    chk = all(torch.equal(v, plan.focus(frame(f))) for f, v in mine.items())
+    flag = torch.tensor([1 if chk else 0], device=device)
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    out["frames_ok"] = bool(flag.item())
+
+    # ---- 4: one receive channel per rank, neighbour exchange, fused DPCA/ATI per adjacent pair
+    chan = plan.focus(frame(100 + rank)).clone()
+    pair = nd.pair_products(chan, lambda a, b: dev.gmti_fused(a, b, want=("ati_phase_masked",)))
+    ok = 1
+    if rank < world - 1:
+        ref = dev.gmti_fused(chan, plan.focus(frame(100 + rank + 1)).clone(), want=("ati_phase_masked",))
+        ok = int(torch.equal(pair["det_idx"], ref["det_idx"]) and pair["peak_idx"] == ref["peak_idx"])
+    flag = torch.tensor([ok], device=device)
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    out["channel_pairs_ok"] = bool(flag.item())
+    if rank == 0:
+        print(json.dumps(out))
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
