@@ -41,22 +41,10 @@ def fast_time_axis(t_start: float, n_samples: int, fs: float) -> np.ndarray:
     return t_start + np.linspace(0.0, n_samples / fs, n_samples)
 
 
-def chunk_hint(pos0_d, ptx_d, t_fast, t_p, c, prx_d=None) -> int:
-    """Pick the CTA chunk width of K1: when the chirps of a scene cover well under the whole receive window
-    (estimated from a few scatterers at the mid-aperture pulse), narrow chunks keep more warps busy."""
-    T, P = pos0_d.shape[0], ptx_d.shape[0]
-    if T == 0 or P == 0:
-        return 0
-    idx = torch.linspace(0, T - 1, min(T, 16)).long().to(pos0_d.device)
-    p = pos0_d[idx]
-    tx = ptx_d[P // 2]
-    d = torch.linalg.vector_norm(p - tx, dim=1)
-    d2 = d if prx_d is None else torch.linalg.vector_norm(p - prx_d[P // 2], dim=1)
-    tau = ((d + d2) / c).cpu().numpy()
-    lo = np.clip(tau, t_fast[0], t_fast[-1])
-    hi = np.clip(tau + t_p, t_fast[0], t_fast[-1])
-    frac = float(np.mean(hi - lo) / max(t_fast[-1] - t_fast[0], 1e-30))
-    return 0   # measured on B200: the narrow chunk never wins (setup per sample doubles); kept as an ABI knob
+def chunk_hint(*_args, **_kw) -> int:
+    """CTA chunk width of K1 (nis_echo_params.samples_per_thread): 0 lets the library choose.  Measured on
+    B200 the narrow chunk (8) never wins -- the per-sample setup doubles -- so it stays an ABI knob only."""
+    return 0
 
 
 def echo_accumulate(pos0, vel, rcs, pos_tx, pos_rx, t_slow, *, c, fc, k_rate, t_p, t_start, fs, n_samples,
