@@ -5,11 +5,9 @@
 // (sar_satellite_moving_sim.py:129-156) and run_custom_physics (sar_vehicle_sim.py:102-123):
 //   raw[i][n] = sum_b amp_b exp(j 2 pi (-fc tau_bi + (k/2) (t_n - tau_bi - T_p/2)^2)) [|t_n - tau_bi - T_p/2| <= T_p/2]
 //
-// Work split: a pre-pass (k_echo_union) finds, per pulse, the sample range that any chirp of the scene can
-// touch; one CTA = one pulse x one chunk of CH = 128*SPT consecutive samples counted from the start of that
-// range (so CTAs are spent only where there is signal; everything else is zero-filled).  Each thread owns
+// Work split: one CTA = one pulse x one chunk of CH = 256*SPT consecutive samples; each thread owns
 // SPT consecutive samples in registers and loops over every scatterer (no cross-thread reduction).
-//  * Prologue (fp64, once per scatterer per CTA, 128 scatterers at a time into shared memory): exact
+//  * Prologue (fp64, once per scatterer per CTA, 256 scatterers at a time into shared memory): exact
 //    two-way range -> delay tau, the phase polynomial about the chunk centre reduced mod 1 and stored
 //    as 32-bit fixed-point turns, and the closed-interval chirp support [lo, hi) evaluated with the
 //    reference's own fp64 expression on the caller's sample-time table (boundary samples bit-exact).
@@ -48,91 +46,20 @@ __device__ __forceinline__ bool gate(const double* __restrict__ t_fast, int n, d
     return fabs(__dsub_rn(__dsub_rn(t_fast[n], tau), half)) <= half;
 }
 
-constexpr int kEchoThreads = 128;
-
-__device__ __forceinline__ double two_way_delay(const EchoConst& k, const double* __restrict__ pos0,
-                                                const double* __restrict__ vel, int b, double ti, double tx0, double tx1,
-                                                double tx2, double rx0, double rx1, double rx2) {
-    const double* vb = k.per_target_velocity ? vel + 3 * b : vel;
-    // p = p0 + v t with separate roundings, as numpy / torch evaluate it (:151)
-    const double px = __dadd_rn(pos0[3 * b], __dmul_rn(vb[0], ti)), py = __dadd_rn(pos0[3 * b + 1], __dmul_rn(vb[1], ti)),
-                 pz = __dadd_rn(pos0[3 * b + 2], __dmul_rn(vb[2], ti));
-    double dx = px - tx0, dy = py - tx1, dz = pz - tx2;
-    const double d_tx = sqrt(__dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz)));
-    if (k.bistatic) {
-        dx = px - rx0; dy = py - rx1; dz = pz - rx2;
-        const double d_rx = sqrt(__dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz)));
-        return __ddiv_rn(__dadd_rn(d_tx, d_rx), k.c);
-    }
-    return __ddiv_rn(__dmul_rn(2.0, d_tx), k.c);
-}
-
-// Per pulse: conservative sample range [lo, hi) outside of which no scatterer of the call contributes.
-__global__ void __launch_bounds__(kEchoThreads) k_echo_union(EchoConst k, const double* __restrict__ pos0,
-                                                             const double* __restrict__ vel,
-                                                             const double* __restrict__ pos_tx,
-                                                             const double* __restrict__ pos_rx,
-                                                             const double* __restrict__ t_slow, int2* __restrict__ span) {
-    const int pulse = k.P0 + blockIdx.x;
-    const double ti = t_slow[pulse];
-    const double tx0 = pos_tx[3 * pulse], tx1 = pos_tx[3 * pulse + 1], tx2 = pos_tx[3 * pulse + 2];
-    double rx0 = tx0, rx1 = tx1, rx2 = tx2;
-    if (k.bistatic) { rx0 = pos_rx[3 * pulse]; rx1 = pos_rx[3 * pulse + 1]; rx2 = pos_rx[3 * pulse + 2]; }
-    double tmin = 1e300, tmax = -1e300;
-    for (int b = threadIdx.x; b < k.T; b += blockDim.x) {
-        const double tau = two_way_delay(k, pos0, vel, b, ti, tx0, tx1, tx2, rx0, rx1, rx2);
-        tmin = fmin(tmin, tau);
-        tmax = fmax(tmax, tau);
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        tmin = fmin(tmin, __shfl_xor_sync(0xffffffffu, tmin, o));
-        tmax = fmax(tmax, __shfl_xor_sync(0xffffffffu, tmax, o));
-    }
-    __shared__ double smin[kEchoThreads / 32], smax[kEchoThreads / 32];
-    if ((threadIdx.x & 31) == 0) { smin[threadIdx.x >> 5] = tmin; smax[threadIdx.x >> 5] = tmax; }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        for (int w = 1; w < kEchoThreads / 32; ++w) { tmin = fmin(tmin, smin[w]); tmax = fmax(tmax, smax[w]); }
-        int lo = 0, hi = 0;
-        if (k.T > 0 && tmax >= tmin) {
-            const double flo = floor((tmin - k.t_start) / k.dt_fast) - 2.0;
-            const double fhi = ceil((tmax + k.t_p - k.t_start) / k.dt_fast) + 3.0;
-            lo = (int)fmin(fmax(flo, 0.0), (double)k.S);
-            hi = (int)fmin(fmax(fhi, 0.0), (double)k.S);
-        }
-        span[blockIdx.x] = make_int2(lo & ~1, hi);   // even start keeps the 16-byte alignment of the stores
-    }
-}
-
 template <int SPT>
-__global__ void __launch_bounds__(kEchoThreads) k_echo(EchoConst k, EchoTail<SPT> tail, const double* __restrict__ pos0,
-                                                       const double* __restrict__ vel, const double* __restrict__ amp,
-                                                       const double* __restrict__ pos_tx,
-                                                       const double* __restrict__ pos_rx,
-                                                       const double* __restrict__ t_slow,
-                                                       const double* __restrict__ t_fast, const int2* __restrict__ span,
-                                                       float2* __restrict__ raw) {
-    constexpr int NTH = kEchoThreads;
-    constexpr int CH = NTH * SPT;
+__global__ void __launch_bounds__(256) k_echo(EchoConst k, EchoTail<SPT> tail, const double* __restrict__ pos0,
+                                              const double* __restrict__ vel, const double* __restrict__ amp,
+                                              const double* __restrict__ pos_tx, const double* __restrict__ pos_rx,
+                                              const double* __restrict__ t_slow, const double* __restrict__ t_fast,
+                                              float2* __restrict__ raw) {
+    constexpr int CH = 256 * SPT;
     constexpr int HALF = SPT / 2;
-    __shared__ uint4 rec[NTH];
-    __shared__ int warp_cnt[NTH / 32];
+    __shared__ uint4 rec[256];
+    __shared__ int warp_cnt[8];
 
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int pulse = k.P0 + blockIdx.y;
-    const int2 sp = span[blockIdx.y];
-    const int n_used = sp.y > sp.x ? (sp.y - sp.x + CH - 1) / CH : 0;   // chunks that can hold signal
-    const int cov_hi = min(k.S, sp.x + n_used * CH);                    // computed region is [sp.x, cov_hi)
-    if (!k.accumulate) {
-        // zero-fill this CTA's share of the row outside the computed region
-        float2* row = raw + (int64_t)pulse * k.S;
-        const int z0 = blockIdx.x * CH, z1 = min(k.S, z0 + CH);
-        for (int n = z0 + tid; n < z1; n += NTH)
-            if (n < sp.x || n >= cov_hi) row[n] = make_float2(0.f, 0.f);
-    }
-    if ((int)blockIdx.x >= n_used) return;
-    const int n0 = sp.x + blockIdx.x * CH;          // first sample of the chunk
+    const int n0 = blockIdx.x * CH;                 // first sample of the chunk
     const int nc = n0 + CH / 2;                     // chunk centre: phase polynomial is expanded about it
     const int mt = tid * SPT + HALF - CH / 2;       // this thread's centre sample relative to nc (signed)
     const int t_lo = tid * SPT, t_hi = t_lo + SPT;  // this thread's samples relative to n0
@@ -152,13 +79,27 @@ __global__ void __launch_bounds__(kEchoThreads) k_echo(EchoConst k, EchoTail<SPT
 #pragma unroll
     for (int j = 0; j < SPT; ++j) acc[j] = make_float2(0.f, 0.f);
 
-    for (int b0 = 0; b0 < k.T; b0 += NTH) {
+    for (int b0 = 0; b0 < k.T; b0 += 256) {
         // ------------------------------------------------ prologue: one scatterer per thread, fp64
         const int b = b0 + tid;
         bool keep = false;
         uint4 r = make_uint4(0, 0, 0, 0);
         if (b < k.T) {
-            const double tau = two_way_delay(k, pos0, vel, b, ti, tx0, tx1, tx2, rx0, rx1, rx2);
+            const double* vb = k.per_target_velocity ? vel + 3 * b : vel;
+            // p = p0 + v t with separate roundings, as numpy / torch evaluate it (:151)
+            const double px = __dadd_rn(pos0[3 * b], __dmul_rn(vb[0], ti)),
+                         py = __dadd_rn(pos0[3 * b + 1], __dmul_rn(vb[1], ti)),
+                         pz = __dadd_rn(pos0[3 * b + 2], __dmul_rn(vb[2], ti));
+            double dx = px - tx0, dy = py - tx1, dz = pz - tx2;
+            const double d_tx = sqrt(__dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz)));
+            double tau;
+            if (k.bistatic) {
+                dx = px - rx0; dy = py - rx1; dz = pz - rx2;
+                const double d_rx = sqrt(__dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz)));
+                tau = __ddiv_rn(__dadd_rn(d_tx, d_rx), k.c);
+            } else {
+                tau = __ddiv_rn(__dmul_rn(2.0, d_tx), k.c);
+            }
             // support [lo, hi) in absolute sample indices
             int lo = (int)ceil((tau - k.t_start) / k.dt_fast);
             int hi = (int)floor((tau + k.t_p - k.t_start) / k.dt_fast) + 1;
@@ -191,7 +132,7 @@ __global__ void __launch_bounds__(kEchoThreads) k_echo(EchoConst k, EchoTail<SPT
         int off = __popc(ball & ((1u << lane) - 1u));
         int total = 0;
 #pragma unroll
-        for (int w = 0; w < NTH / 32; ++w) {
+        for (int w = 0; w < 8; ++w) {
             const int cw = warp_cnt[w];
             if (w < wid) off += cw;
             total += cw;
@@ -272,14 +213,9 @@ int launch_echo(nis_ctx* ctx, const EchoConst& k, const double* pos0, const doub
         ph -= floor(ph);
         tail.e[j] = make_float2((float)cos(two_pi * ph), (float)sin(two_pi * ph));
     }
-    int rc = ctx->ensure_scratch((size_t)n_pulses * sizeof(int2));
-    if (rc != NIS_OK) return rc;
-    int2* span = reinterpret_cast<int2*>(ctx->scratch);
-    k_echo_union<<<n_pulses, kEchoThreads, 0, st>>>(k, pos0, vel, pos_tx, pos_rx, t_slow, span);
-    NIS_LAUNCH_CHECK(ctx);
-    constexpr int CH = kEchoThreads * SPT;
+    constexpr int CH = 256 * SPT;
     dim3 grid((k.S + CH - 1) / CH, n_pulses);
-    k_echo<SPT><<<grid, kEchoThreads, 0, st>>>(k, tail, pos0, vel, amp, pos_tx, pos_rx, t_slow, t_fast, span, raw);
+    k_echo<SPT><<<grid, 256, 0, st>>>(k, tail, pos0, vel, amp, pos_tx, pos_rx, t_slow, t_fast, raw);
     NIS_LAUNCH_CHECK(ctx);
     return NIS_OK;
 }
@@ -305,9 +241,10 @@ extern "C" int nis_echo_accumulate(nis_ctx* ctx, const nis_echo_params* prm, con
     k.T = T; k.P0 = P0; k.S = S; k.per_target_velocity = prm->per_target_velocity;
     k.accumulate = accumulate; k.bistatic = pos_rx != nullptr;
     float2* r = reinterpret_cast<float2*>(raw);
-    // chunk = 128*SPT samples per CTA; 16 samples per thread halves the per-sample setup cost and is the
-    // default, 8 is available through the samples_per_thread knob
-    const bool wide = prm->samples_per_thread != 8;
+    // chunk = 256*SPT samples: take the wider chunk unless it wastes > 12 % of its threads past S, or the
+    // caller knows that the chirps cover only part of the window (samples_per_thread hint)
+    const int waste16 = ((S + 4095) / 4096) * 4096 - S;
+    const bool wide = prm->samples_per_thread == 16 || (prm->samples_per_thread != 8 && waste16 * 8 <= S);
     if (wide)
         return launch_echo<16>(ctx, k, tgt_pos0, tgt_vel, tgt_amp, pos_tx, pos_rx, t_slow, t_fast, r, P1 - P0, st);
     return launch_echo<8>(ctx, k, tgt_pos0, tgt_vel, tgt_amp, pos_tx, pos_rx, t_slow, t_fast, r, P1 - P0, st);
