@@ -122,9 +122,10 @@ NIS_API int nis_csa_size_class(int32_t n_az, int32_t n_rg);
 NIS_API int nis_csa_axes(const nis_csa_plan* plan, double* range_axis, double* cross_range);
 /* phist: dev [n_az][pitch] complex64, pitch in elements (>= n_rg).  The DPCA co-registration of
  * :402-403 (rx1[1:], rx2[:-1]) is a pointer offset of one row by the caller.
- * slc: dev [n_rg][n_az].  max_sq (optional, dev, 1 float): max |slc|^2, accumulated with max. */
+ * slc: dev [n_rg][n_az].  max_sq (optional, dev, 1 double, zeroed by the caller): max |slc|^2 evaluated in
+ * fp64 on the stored fp32 samples, accumulated with max -- hand it to nis_gmti_fused to skip its first pass. */
 NIS_API int nis_csa_focus(nis_csa_plan* plan, const nis_c32* phist, int64_t pitch, nis_c32* slc,
-                  float* max_sq, nis_stream stream);
+                  double* max_sq, nis_stream stream);
 
 /* Per-kernel timing for bench.py's roofline: when enabled every nis_csa_focus call records CUDA
  * events between its five kernels (az-outer-fwd, az-inner-fwd, range, az-inner-inv, az-outer-inv)
@@ -153,6 +154,7 @@ NIS_API int nis_gmti_fused(nis_ctx* ctx, const nis_c32* slc1, const nis_c32* slc
                    nis_c32* ati_interf, float* ati_phase, nis_c32* dpca_diff, float* dpca_mag,
                    float* slc1_mag, uint8_t* mag_mask, float* ati_phase_masked,
                    uint32_t* det_idx, uint32_t det_cap,
+                   const double* max_mag_sq_in /* dev, optional: max |slc1|^2 from nis_csa_focus */,
                    nis_gmti_result* result /* dev */, nis_stream stream);
 /* viewer auto-balance (sar_ati_dcpa_viewer_csa.py:249-250): sum slc1 conj(slc2) in fp64;
  * out: dev [2] doubles (re, im) of the SUM (angle of the mean == angle of the sum) */

@@ -105,6 +105,22 @@ __device__ __forceinline__ float2 cis_u32_pre(uint32_t u) {
 }
 __device__ __forceinline__ float2 cis_u64(uint64_t u) { return cis_u32((uint32_t)(u >> 32)); }
 
+// |s|^2 in fp64: both products are exact for fp32 inputs, one rounding in the sum
+__device__ __forceinline__ double sq_mag_f64(float2 s) {
+    const double re = (double)s.x, im = (double)s.y;
+    return fma(re, re, im * im);
+}
+__device__ __forceinline__ double warp_max_f64(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+// lane 0 of each warp publishes; non-negative doubles order like their bit patterns
+__device__ __forceinline__ void atomic_max_f64(double* dst, double v) {
+    if ((threadIdx.x & 31) == 0 && v > 0.0)
+        atomicMax(reinterpret_cast<unsigned long long*>(dst), (unsigned long long)__double_as_longlong(v));
+}
+
 __device__ __forceinline__ float warp_max(float v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));

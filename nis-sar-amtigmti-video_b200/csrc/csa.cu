@@ -64,7 +64,7 @@ __global__ void __launch_bounds__(256) k_az_outer_fwd(const float2* __restrict__
 template <int A1, int TA>
 __global__ void __launch_bounds__(256) k_az_outer_inv(const float2* __restrict__ in, int64_t pitch,
                                                       float2* __restrict__ slc, int n_rg, int A2, int n_az,
-                                                      float scale, float* __restrict__ max_sq,
+                                                      float scale, double* __restrict__ max_sq,
                                                       const float2* __restrict__ twN) {
     constexpr int TN = 16;
     extern __shared__ float2 tile[];  // [A1][TN][TA+1]
@@ -89,7 +89,7 @@ __global__ void __launch_bounds__(256) k_az_outer_inv(const float2* __restrict__
         }
     }
     __syncthreads();
-    float m = 0.f;
+    double m = 0.0;
     constexpr int LPR = TA;                 // lanes per (a1, n) row piece
     constexpr int RPI = 256 / LPR;          // row pieces per iteration
     const int l = threadIdx.x % LPR, g = threadIdx.x / LPR;
@@ -97,12 +97,9 @@ __global__ void __launch_bounds__(256) k_az_outer_inv(const float2* __restrict__
         const int a1 = p / TN, nn = p % TN;
         float2 x = tile[(a1 * TN + nn) * (TA + 1) + l];
         slc[(int64_t)(n0 + nn) * n_az + a1 * A2 + a20 + l] = x;
-        m = fmaxf(m, fmaf(x.x, x.x, x.y * x.y));
+        if (max_sq != nullptr) m = fmax(m, sq_mag_f64(x));
     }
-    if (max_sq != nullptr) {
-        m = warp_max(m);
-        if ((threadIdx.x & 31) == 0) atomicMax(reinterpret_cast<unsigned int*>(max_sq), __float_as_uint(m));
-    }
+    if (max_sq != nullptr) atomic_max_f64(max_sq, warp_max_f64(m));
 }
 
 // ------------------------------------------------------------------------------ azimuth, inner
@@ -296,7 +293,7 @@ int launch_outer_fwd(nis_csa_plan* pl, const float2* in, int64_t in_pitch, cudaS
 }
 
 template <int A1, int TA>
-int launch_outer_inv(nis_csa_plan* pl, float2* slc, float* max_sq, cudaStream_t st) {
+int launch_outer_inv(nis_csa_plan* pl, float2* slc, double* max_sq, cudaStream_t st) {
     const size_t smem = (size_t)A1 * 16 * (TA + 1) * sizeof(float2);
     static bool attr_done = false;
     if (!attr_done) {
@@ -564,7 +561,7 @@ extern "C" int nis_csa_axes(const nis_csa_plan* pl, double* range_axis, double* 
     return NIS_OK;
 }
 
-extern "C" int nis_csa_focus(nis_csa_plan* pl, const nis_c32* phist, int64_t pitch, nis_c32* slc, float* max_sq,
+extern "C" int nis_csa_focus(nis_csa_plan* pl, const nis_c32* phist, int64_t pitch, nis_c32* slc, double* max_sq,
                              nis_stream stream) {
     NIS_REQUIRE(pl && phist && slc, "nis_csa_focus: null argument");
     NIS_REQUIRE(pitch >= pl->n_rg, "nis_csa_focus: pitch %lld < n_rg %d", (long long)pitch, pl->n_rg);

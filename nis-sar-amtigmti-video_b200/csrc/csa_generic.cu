@@ -149,11 +149,11 @@ __device__ float2* mixed_dft(const GenDev& g, float2* a, float2* b) {
 
 template <int MODE>
 __global__ void k_row_mixed(GenDev g, float2* __restrict__ data, int64_t pitch, int n_rows,
-                            const RowCoef* __restrict__ coef, float scale, float* __restrict__ max_sq) {
+                            const RowCoef* __restrict__ coef, float scale, double* __restrict__ max_sq) {
     extern __shared__ float2 sm[];
     float2* b0 = sm;
     float2* b1 = sm + g.N;
-    float mx = 0.f;
+    double mx = 0.0;
     for (int row = blockIdx.x; row < n_rows; row += gridDim.x) {
         float2* p = data + (int64_t)row * pitch;
         RowCoef rc{};
@@ -178,17 +178,14 @@ __global__ void k_row_mixed(GenDev g, float2* __restrict__ data, int64_t pitch, 
                 float2 x = cur[n];
                 if (MODE == AZ_INV) {
                     x.x *= scale; x.y *= scale;
-                    mx = fmaxf(mx, fmaf(x.x, x.x, x.y * x.y));
+                    if (max_sq != nullptr) mx = fmax(mx, sq_mag_f64(x));
                 }
                 p[n] = x;
             }
         }
         __syncthreads();
     }
-    if (MODE == AZ_INV && max_sq != nullptr) {
-        mx = warp_max(mx);
-        if ((threadIdx.x & 31) == 0) atomicMax(reinterpret_cast<unsigned int*>(max_sq), __float_as_uint(mx));
-    }
+    if (MODE == AZ_INV && max_sq != nullptr) atomic_max_f64(max_sq, warp_max_f64(mx));
 }
 
 // ------------------------------------------------------------------------------- Bluestein engine
@@ -219,11 +216,11 @@ __device__ __forceinline__ void bluestein_core(float2* v, int t, float2* sm, con
 template <int MODE, class P, int PAD>
 __global__ void __launch_bounds__(P::NT) k_row_blue(GenDev g, float2* __restrict__ data, int64_t pitch, int n_rows,
                                                     const RowCoef* __restrict__ coef, float scale,
-                                                    float* __restrict__ max_sq) {
+                                                    double* __restrict__ max_sq) {
     extern __shared__ float2 sm[];
     constexpr int E = P::E, NT = P::NT;
     const int t = threadIdx.x;
-    float mx = 0.f;
+    double mx = 0.0;
     for (int row = blockIdx.x; row < n_rows; row += gridDim.x) {
         float2* p = data + (int64_t)row * pitch;
         RowCoef rc{};
@@ -264,16 +261,13 @@ __global__ void __launch_bounds__(P::NT) k_row_blue(GenDev g, float2* __restrict
                 if (MODE == RANGE) x = cmul(x, cis_u64(quad_phase(rc.a3, rc.b3, rc.c3, (uint32_t)idx)));
                 if (MODE == AZ_INV) {
                     x.x *= scale; x.y *= scale;
-                    mx = fmaxf(mx, fmaf(x.x, x.x, x.y * x.y));
+                    if (max_sq != nullptr) mx = fmax(mx, sq_mag_f64(x));
                 }
                 p[idx] = x;
             }
         }
     }
-    if (MODE == AZ_INV && max_sq != nullptr) {
-        mx = warp_max(mx);
-        if ((threadIdx.x & 31) == 0) atomicMax(reinterpret_cast<unsigned int*>(max_sq), __float_as_uint(mx));
-    }
+    if (MODE == AZ_INV && max_sq != nullptr) atomic_max_f64(max_sq, warp_max_f64(mx));
 }
 
 // --------------------------------------------------------------------------------------- host side
@@ -360,7 +354,7 @@ int build_length(int n, GenLen* g) {
 
 template <int MODE, class P, int PAD>
 int launch_blue(nis_ctx* ctx, const GenLen& g, float2* data, int64_t pitch, int n_rows, const RowCoef* coef,
-                float scale, float* max_sq, cudaStream_t st) {
+                float scale, double* max_sq, cudaStream_t st) {
     constexpr int SMROW = P::N + (PAD ? (P::N >> PAD) : 0);
     const size_t smem = (size_t)SMROW * sizeof(float2);
     static bool attr_done = false;
@@ -379,7 +373,7 @@ int launch_blue(nis_ctx* ctx, const GenLen& g, float2* data, int64_t pitch, int 
 
 template <int MODE>
 int launch_row(nis_ctx* ctx, const GenLen& g, float2* data, int64_t pitch, int n_rows, const RowCoef* coef,
-               float scale, float* max_sq, cudaStream_t st) {
+               float scale, double* max_sq, cudaStream_t st) {
     if (g.kind == 1) {
         switch (g.M) {
             case 64: return launch_blue<MODE, P64, 3>(ctx, g, data, pitch, n_rows, coef, scale, max_sq, st);
@@ -434,7 +428,7 @@ void generic_destroy(nis_csa_plan* pl) {
     pl->generic = nullptr;
 }
 
-int generic_focus(nis_csa_plan* pl, const float2* phist, int64_t pitch, float2* slc, float* max_sq, cudaStream_t st) {
+int generic_focus(nis_csa_plan* pl, const float2* phist, int64_t pitch, float2* slc, double* max_sq, cudaStream_t st) {
     nis_ctx* ctx = pl->ctx;
     const int n_az = pl->n_az, n_rg = pl->n_rg;
     const float scale = (float)(1.0 / ((double)n_az * (double)n_rg));

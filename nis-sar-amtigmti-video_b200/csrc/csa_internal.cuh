@@ -48,13 +48,13 @@ struct GenericState;   // csa_generic.cu
 int generic_supported(int n_az, int n_rg);
 int generic_create(nis_csa_plan* pl);
 void generic_destroy(nis_csa_plan* pl);
-int generic_focus(nis_csa_plan* pl, const float2* phist, int64_t pitch, float2* slc, float* max_sq, cudaStream_t st);
+int generic_focus(nis_csa_plan* pl, const float2* phist, int64_t pitch, float2* slc, double* max_sq, cudaStream_t st);
 
 }  // namespace csa
 }  // namespace nis
 
 typedef int (*nis_az_outer_fwd_fn)(nis_csa_plan*, const float2*, int64_t, cudaStream_t);
-typedef int (*nis_az_outer_inv_fn)(nis_csa_plan*, float2*, float*, cudaStream_t);
+typedef int (*nis_az_outer_inv_fn)(nis_csa_plan*, float2*, double*, cudaStream_t);
 typedef int (*nis_az_inner_fn)(nis_csa_plan*, bool, cudaStream_t);
 typedef int (*nis_range_fn)(nis_csa_plan*, cudaStream_t);
 

@@ -53,7 +53,7 @@ SIGNATURES = {
     "nis_csa_plan_set_profiling": (C.c_int, [_P, C.c_int32]),
     "nis_csa_stage_times": (C.c_int, [_P, C.c_int32, _P]),
     "nis_gmti_fused": (C.c_int, [_P, _P, _P, C.c_uint64, C.c_double, C.c_double,
-                                 _P, _P, _P, _P, _P, _P, _P, _P, C.c_uint32, _P, _P]),
+                                 _P, _P, _P, _P, _P, _P, _P, _P, C.c_uint32, _P, _P, _P]),
     "nis_gmti_balance_sum": (C.c_int, [_P, _P, _P, C.c_uint64, _P, _P]),
     "nis_narrow_c128_to_c32": (C.c_int, [_P, _P, _P, C.c_uint64, _P]),
     "nis_widen_c32_to_c128": (C.c_int, [_P, _P, _P, C.c_uint64, _P]),

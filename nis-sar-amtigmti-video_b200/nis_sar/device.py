@@ -126,7 +126,8 @@ class CsaPlan:
 
     def focus(self, phist, out=None, max_sq=None):
         """phist: complex64 CUDA tensor [n_az, n_rg] (rows may be strided: a ``raw[1:]`` view is fine).
-        Returns slc [n_rg, n_az] complex64 -- the array the reference returns as ``img.T``."""
+        Returns slc [n_rg, n_az] complex64 -- the array the reference returns as ``img.T``.  ``max_sq``: optional
+        1-element float64 CUDA tensor, zeroed here, that receives max |slc|^2 (exact, for ``gmti_fused``)."""
         if phist.dtype != torch.complex64 or phist.dim() != 2 or phist.stride(1) != 1:
             raise NisError("CsaPlan.focus: phist must be a complex64 [n_az, n_rg] tensor with unit column stride")
         if tuple(phist.shape) != (self.n_az, self.n_rg):
@@ -134,6 +135,10 @@ class CsaPlan:
         if out is None:
             out = torch.empty((self.n_rg, self.n_az), dtype=torch.complex64, device=phist.device)
         with torch.cuda.device(self.di):
+            if max_sq is not None:
+                if max_sq.dtype != torch.float64 or max_sq.numel() != 1:
+                    raise NisError("CsaPlan.focus: max_sq must be a 1-element float64 tensor")
+                max_sq.zero_()
             rc = _lib.load().nis_csa_focus(self._h, _ptr(phist), phist.stride(0), _ptr(out), _ptr(max_sq),
                                            C.c_void_p(_stream_ptr(self.di)))
         _lib.check(rc, "nis_csa_focus")
@@ -182,10 +187,13 @@ def cached_plan(n_az, n_rg, **kw) -> CsaPlan:
 GMTI_PRODUCTS = ("ati_interf", "ati_phase", "dpca_diff", "dpca_mag", "slc1_mag", "mag_mask", "ati_phase_masked")
 
 
-def gmti_fused(slc1, slc2, thresh_frac=0.05, cal_phase=0.0, want=GMTI_PRODUCTS, det_cap=None):
+def gmti_fused(slc1, slc2, thresh_frac=0.05, cal_phase=0.0, want=GMTI_PRODUCTS, det_cap=None, max_sq=None,
+               lazy=False):
     """K3.  slc1/slc2: complex64 CUDA tensors of one shape.  Returns a dict with the requested
-    product tensors plus ``det_idx`` (uint32 -> int64 tensor of flat indices, ascending),
-    ``det_count``, ``peak_idx``, ``max_mag`` (python scalars; reading them synchronises)."""
+    product tensors (``max_sq``: optional 1-element float64 CUDA tensor filled by ``CsaPlan.focus(..., max_sq=)``
+    for slc1 -- skips the max pass) plus ``det_idx`` (uint32 -> int64 tensor of flat indices, ascending),
+    ``det_count``, ``peak_idx``, ``max_mag`` (python scalars; reading them synchronises).  ``lazy=True`` skips
+    that read-back and returns the raw device buffers (``det_idx_raw``, ``result_dev``) instead."""
     if slc1.dtype != torch.complex64 or slc2.dtype != torch.complex64 or slc1.shape != slc2.shape:
         raise NisError("gmti_fused: slc1 and slc2 must be complex64 tensors of the same shape")
     if not (slc1.is_contiguous() and slc2.is_contiguous()):
@@ -213,9 +221,15 @@ def gmti_fused(slc1, slc2, thresh_frac=0.05, cal_phase=0.0, want=GMTI_PRODUCTS, 
         res = torch.zeros((16,), dtype=torch.uint8, device=dev)
         rc = _lib.load().nis_gmti_fused(_lib.context(di), _ptr(slc1), _ptr(slc2), n, float(thresh_frac),
                                         float(cal_phase), _ptr(interf), _ptr(phase), _ptr(diff), _ptr(dmag),
-                                        _ptr(mag1), _ptr(mask), _ptr(pmask), _ptr(det), cap, _ptr(res),
+                                        _ptr(mag1), _ptr(mask), _ptr(pmask), _ptr(det), cap, _ptr(max_sq), _ptr(res),
                                         C.c_void_p(_stream_ptr(di)))
         _lib.check(rc, "nis_gmti_fused")
+        if lazy:            # no host synchronisation: the caller reads the 16-byte record / index list later
+            if "mag_mask" in outs:
+                outs["mag_mask"] = outs["mag_mask"].view(torch.bool)
+            outs["det_idx_raw"] = det
+            outs["result_dev"] = res
+            return outs
         raw = res.cpu().numpy().tobytes()          # synchronises: the 16-byte result record
     r = _lib.GmtiResult.from_buffer_copy(raw)
     k = min(int(r.det_count), cap)

@@ -230,6 +230,31 @@ def test_gmti_products_vs_oracle(api, shape):
         assert abs(out["max_mag"] - np.abs(s1.astype(np.complex128)).max()) < 1e-12 * out["max_mag"]
 
 
+def test_gmti_with_max_from_csa(api, dev):
+    """nis_csa_focus can hand max|slc1|^2 (fp64, exact) to nis_gmti_fused, which then skips its first pass:
+    identical detections and peak."""
+    prm = params.spaceborne_preset()
+    gen = torch.Generator(device="cuda").manual_seed(9)
+    x = torch.view_as_complex(torch.randn((257, 512, 2), generator=gen, device="cuda"))
+    x[100, 200] += 50.0
+    plan = dev.cached_plan(256, 512, lam=prm.Lambda, kr=prm.k_rate, fs=prm.FS, prf=prm.PRF, vr=prm.V_eff, r_ref=prm.R0,
+                           t_start=prm.t_start_fast, device="cuda")
+    mx = torch.zeros(1, dtype=torch.float64, device="cuda")
+    s1 = plan.focus(x[1:], max_sq=mx).clone()
+    s2 = plan.focus(x[:-1]).clone()
+    a = dev.gmti_fused(s1, s2, max_sq=mx)
+    b = dev.gmti_fused(s1, s2)
+    assert a["peak_idx"] == b["peak_idx"] and a["det_count"] == b["det_count"] and a["max_mag"] == b["max_mag"]
+    assert torch.equal(a["det_idx"], b["det_idx"])
+    assert abs(float(mx) - float((s1.abs().double() ** 2).max())) <= 1e-6 * float(mx)
+    # general-size path too
+    plan2 = dev.cached_plan(255, 500, lam=prm.Lambda, kr=prm.k_rate, fs=prm.FS, prf=prm.PRF, vr=prm.V_eff, r_ref=prm.R0,
+                            t_start=prm.t_start_fast, device="cuda")
+    y = x[:255, :500].contiguous()
+    s3 = plan2.focus(y, max_sq=mx).clone()
+    assert dev.gmti_fused(s3, s3, max_sq=mx)["peak_idx"] == dev.gmti_fused(s3, s3)["peak_idx"]
+
+
 def test_gmti_edge_cases(api, dev):
     # strict '>' at the threshold, ties for the peak resolve to the first index, all-equal image
     s = np.full((4, 8), 2.0 + 0j, dtype=np.complex64)
