@@ -325,19 +325,33 @@ def run_gpu_arm(args):
         for _ in range(5):
             frame()
         torch.cuda.synchronize(device)
+        # the frame is 17 short kernels: replay it from a CUDA graph so that host launch latency is not measured
+        graph_note = "cuda graph replay"
+        try:
+            gph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(gph):
+                out4 = frame()
+            run_frame = gph.replay
+        except Exception as e:   # capture not possible: time eager launches and say so
+            graph_note = f"eager launches (graph capture failed: {str(e)[:80]})"
+            run_frame = frame
+        for _ in range(3):
+            run_frame()
+        torch.cuda.synchronize(device)
         ea, eb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        nfr = 30
-        ea.record(stream)
+        nfr = 50
+        cur = torch.cuda.current_stream(device)
+        ea.record(cur)
         for _ in range(nfr):
-            out4 = frame()
-        eb.record(stream)
+            run_frame()
+        eb.record(cur)
         torch.cuda.synchronize(device)
         fr_ms = ea.elapsed_time(eb) / nfr
         fr_bytes = (2 * CSA_ALGO_BYTES_PER_PIXEL + 49.0) * n4 * n4
         ati = {"workload": "4096x4096 two-channel frame: CSA x2 + fused DPCA/ATI/threshold/compaction (all products)",
+               "launch": graph_note,
                "ms_per_frame": fr_ms, "frames_per_s": 1e3 / fr_ms, "algorithmic_bytes_per_frame": fr_bytes,
                "achieved_GBps": fr_bytes / (fr_ms * 1e-3) / 1e9}
-        del out4
         p4.close()
 
     # ------------------------------------------------ reduce over ranks (max time)
