@@ -70,8 +70,36 @@ __host__ __device__ __forceinline__ float2 cmul(float2 a, float2 b) {
 __host__ __device__ __forceinline__ float2 cmul_conj(float2 a, float2 b) {  // a * conj(b)
     return make_float2(fmaf(a.x, b.x, a.y * b.y), fmaf(a.y, b.x, -a.x * b.y));
 }
+// Complex add / subtract as ONE packed instruction on sm_100 (add.f32x2 -> FADD2): same FP32 pipe time as two
+// FADDs (measured, csrc/pipebench.cu) but half the issue slots, which is what the FFT kernels are short of.
 __host__ __device__ __forceinline__ float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
 __host__ __device__ __forceinline__ float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
+__host__ __device__ __forceinline__ float2 cadd_pk(float2 a, float2 b) {
+#ifdef __CUDA_ARCH__
+    unsigned long long ra, rb;
+    float2 c;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(ra) : "f"(a.x), "f"(a.y));
+    asm("mov.b64 %0, {%1, %2};" : "=l"(rb) : "f"(b.x), "f"(b.y));
+    asm("add.rn.f32x2 %0, %0, %1;" : "+l"(ra) : "l"(rb));
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(c.x), "=f"(c.y) : "l"(ra));
+    return c;
+#else
+    return make_float2(a.x + b.x, a.y + b.y);
+#endif
+}
+__host__ __device__ __forceinline__ float2 csub_pk(float2 a, float2 b) {
+#ifdef __CUDA_ARCH__
+    unsigned long long ra, rb;
+    float2 c;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(ra) : "f"(a.x), "f"(a.y));
+    asm("mov.b64 %0, {%1, %2};" : "=l"(rb) : "f"(b.x), "f"(b.y));
+    asm("sub.rn.f32x2 %0, %0, %1;" : "+l"(ra) : "l"(rb));
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(c.x), "=f"(c.y) : "l"(ra));
+    return c;
+#else
+    return make_float2(a.x - b.x, a.y - b.y);
+#endif
+}
 
 // Phase arithmetic in "turns" held as unsigned fixed point: value = u / 2^64 (or / 2^32).
 // Integer wrap-around IS the mod-1 reduction, so quadratic phases of 1e4..1e8 rad keep full

@@ -24,6 +24,8 @@
 
 #include <vector>
 
+#include <stdlib.h>
+
 #include <type_traits>
 
 #include "csa_internal.cuh"
@@ -48,7 +50,7 @@ __global__ void __launch_bounds__(256) k_az_outer_fwd(const float2* __restrict__
     float2 v[A1];
 #pragma unroll
     for (int a1 = 0; a1 < A1; ++a1) v[a1] = in[(int64_t)(a1 * A2 + a2) * in_pitch + n];
-    fft_dif<A1, false, 1>(v);
+    fft_dif<A1, false, 1, true>(v);
     constexpr int L = ilog2(A1);
 #pragma unroll
     for (int k1 = 0; k1 < A1; ++k1) {
@@ -59,21 +61,22 @@ __global__ void __launch_bounds__(256) k_az_outer_fwd(const float2* __restrict__
 }
 
 // Inverse + corner turn: slc[n][a1*A2 + a2] = scale * sum_k1 Z[k1*A2 + a2][n] w_A1^-(k1 a1)
-// Tile: TN = 16 range columns x TA azimuth offsets; transposed through shared memory so that both
-// the reads (128 B row pieces) and the writes (TA*8 B pieces of an slc row) are coalesced.
-template <int A1, int TA>
+// Tile: TN range columns x TA azimuth offsets; transposed through shared memory so that both the reads
+// (TN*8-byte row pieces) and the writes (TA*8-byte pieces of an slc row) are coalesced.
+template <int A1, int TN, int TA>
 __global__ void __launch_bounds__(256) k_az_outer_inv(const float2* __restrict__ in, int64_t pitch,
                                                       float2* __restrict__ slc, int n_rg, int A2, int n_az,
                                                       float scale, double* __restrict__ max_sq,
                                                       const float2* __restrict__ twN) {
-    constexpr int TN = 16;
     extern __shared__ float2 tile[];  // [A1][TN][TA+1]
+    constexpr int AROWS = 256 / TN;   // azimuth offsets covered per iteration
+    static_assert(TA % AROWS == 0, "tile height must be a multiple of 256 / TN");
     const int n0 = blockIdx.x * TN, a20 = blockIdx.y * TA;
-    const int n_off = threadIdx.x & 15, a_off = threadIdx.x >> 4;  // 16 x 16
+    const int n_off = threadIdx.x % TN, a_off = threadIdx.x / TN;
     constexpr int L = ilog2(A1);
 #pragma unroll
-    for (int it = 0; it < TA / 16; ++it) {
-        const int a2 = a20 + a_off + 16 * it;
+    for (int it = 0; it < TA / AROWS; ++it) {
+        const int a2 = a20 + a_off + AROWS * it;
         float2 v[A1];
 #pragma unroll
         for (int k1 = 0; k1 < A1; ++k1) {
@@ -81,11 +84,11 @@ __global__ void __launch_bounds__(256) k_az_outer_inv(const float2* __restrict__
             if (k1 > 0) x = cmul_conj(x, __ldg(twN + ((k1 * a2) & (n_az - 1))));   // four-step twiddle w_N^-(k1 a2)
             v[k1] = x;
         }
-        fft_dif<A1, true, 1>(v);
+        fft_dif<A1, true, 1, true>(v);
 #pragma unroll
         for (int a1 = 0; a1 < A1; ++a1) {
             float2 x = v[brev(a1, L)];
-            tile[(a1 * TN + n_off) * (TA + 1) + a_off + 16 * it] = make_float2(x.x * scale, x.y * scale);
+            tile[(a1 * TN + n_off) * (TA + 1) + a_off + AROWS * it] = make_float2(x.x * scale, x.y * scale);
         }
     }
     __syncthreads();
@@ -145,7 +148,7 @@ __global__ void __launch_bounds__(P::NT* W) k_az_inner_tma(const __grid_constant
 #pragma unroll
         for (int s = 0; s < E; ++s) v[s] = buf[(t + NT * s) * W + c];
         __syncthreads();   // every element is in registers before the exchange overwrites the tile
-        transform<P, INV, W, 0>(v, t, buf + c, tw);
+        transform<P, INV, W, 0, CtaBarrier, true>(v, t, buf + c, tw);
         const int x = tile % n_col_tiles, k1 = tile / n_col_tiles;
         float2* base = data + (int64_t)k1 * A2 * pitch + x * W + c;
 #pragma unroll
@@ -292,19 +295,19 @@ int launch_outer_fwd(nis_csa_plan* pl, const float2* in, int64_t in_pitch, cudaS
     return NIS_OK;
 }
 
-template <int A1, int TA>
+template <int A1, int TN, int TA>
 int launch_outer_inv(nis_csa_plan* pl, float2* slc, double* max_sq, cudaStream_t st) {
-    const size_t smem = (size_t)A1 * 16 * (TA + 1) * sizeof(float2);
+    const size_t smem = (size_t)A1 * TN * (TA + 1) * sizeof(float2);
     static bool attr_done = false;
     if (!attr_done) {
-        NIS_CUDA_TRY(cudaFuncSetAttribute(k_az_outer_inv<A1, TA>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        NIS_CUDA_TRY(cudaFuncSetAttribute(k_az_outer_inv<A1, TN, TA>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                           (int)smem));
         attr_done = true;
     }
-    dim3 grid(pl->n_rg / 16, pl->A2 / TA);
+    dim3 grid(pl->n_rg / TN, pl->A2 / TA);
     const float scale = (float)(1.0 / ((double)pl->n_az * (double)pl->n_rg));
-    k_az_outer_inv<A1, TA><<<grid, 256, smem, st>>>(pl->work, pl->n_rg, slc, pl->n_rg, pl->A2, pl->n_az, scale,
-                                                    max_sq, pl->tw_full);
+    k_az_outer_inv<A1, TN, TA><<<grid, 256, smem, st>>>(pl->work, pl->n_rg, slc, pl->n_rg, pl->A2, pl->n_az, scale,
+                                                        max_sq, pl->tw_full);
     NIS_LAUNCH_CHECK(pl->ctx);
     return NIS_OK;
 }
@@ -513,11 +516,20 @@ extern "C" int nis_csa_plan_create(nis_ctx* ctx, int32_t n_az, int32_t n_rg, con
 
     // ---- kernel selection (power-of-two path)
     switch (pl->A1) {
-        case 4: pl->outer_fwd = launch_outer_fwd<4>; pl->outer_inv = launch_outer_inv<4, 16>; break;
+        case 4: pl->outer_fwd = launch_outer_fwd<4>; pl->outer_inv = launch_outer_inv<4, 16, 16>; break;
         case 8: pl->outer_fwd = launch_outer_fwd<8>;
-                pl->outer_inv = launch_outer_inv<8, 16>; break;
+                pl->outer_inv = launch_outer_inv<8, 16, 16>; break;
         default: pl->outer_fwd = launch_outer_fwd<16>;
-                 pl->outer_inv = launch_outer_inv<16, 16>; break;
+                 pl->outer_inv = launch_outer_inv<16, 16, 16>;
+                 if (const char* v = getenv("NIS_OUTER_INV")) {   // tuning knob (development only)
+                     if (pl->A2 >= 32 && n_rg >= 32) {
+                         if (v[0] == '1') pl->outer_inv = launch_outer_inv<16, 32, 8>;
+                         if (v[0] == '2') pl->outer_inv = launch_outer_inv<16, 32, 16>;
+                         if (v[0] == '3') pl->outer_inv = launch_outer_inv<16, 16, 32>;
+                         if (v[0] == '4') pl->outer_inv = launch_outer_inv<16, 8, 32>;
+                     }
+                 }
+                 break;
     }
     switch (pl->A2) {
         case 16: pl->inner_w = 32; pl->inner = launch_inner<P16, 32>; FAIL_IF(upload_twiddles<P16>(&pl->tw_inner)); break;

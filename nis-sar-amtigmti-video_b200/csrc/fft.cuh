@@ -61,25 +61,26 @@ __host__ __device__ __forceinline__ float2 twmul(float2 d) {
     }
 }
 
-template <int N, bool INV, int STRIDE, int I>
+// PK selects the packed fp32x2 add/sub (one FADD2 per complex add): fewer issue slots, same pipe time.
+template <int N, bool INV, int STRIDE, int I, bool PK>
 __host__ __device__ __forceinline__ void dif_bfly(float2* v) {
     constexpr int H = N / 2;
     float2 a = v[I * STRIDE], b = v[(I + H) * STRIDE];
-    v[I * STRIDE] = cadd(a, b);
-    v[(I + H) * STRIDE] = twmul<N, INV, I>(csub(a, b));
+    v[I * STRIDE] = PK ? cadd_pk(a, b) : cadd(a, b);
+    v[(I + H) * STRIDE] = twmul<N, INV, I>(PK ? csub_pk(a, b) : csub(a, b));
 }
-template <int N, bool INV, int STRIDE, int... I>
+template <int N, bool INV, int STRIDE, bool PK, int... I>
 __host__ __device__ __forceinline__ void dif_level(float2* v, std::integer_sequence<int, I...>) {
-    (dif_bfly<N, INV, STRIDE, I>(v), ...);
+    (dif_bfly<N, INV, STRIDE, I, PK>(v), ...);
 }
 // In-register decimation-in-frequency FFT over v[0], v[STRIDE], ..., v[(N-1) STRIDE].
 // Result X[k] is left at position brev(k).
-template <int N, bool INV, int STRIDE>
+template <int N, bool INV, int STRIDE, bool PK = false>
 __host__ __device__ __forceinline__ void fft_dif(float2* v) {
     if constexpr (N > 1) {
-        dif_level<N, INV, STRIDE>(v, std::make_integer_sequence<int, N / 2>{});
-        fft_dif<N / 2, INV, STRIDE>(v);
-        fft_dif<N / 2, INV, STRIDE>(v + (N / 2) * STRIDE);
+        dif_level<N, INV, STRIDE, PK>(v, std::make_integer_sequence<int, N / 2>{});
+        fft_dif<N / 2, INV, STRIDE, PK>(v);
+        fft_dif<N / 2, INV, STRIDE, PK>(v + (N / 2) * STRIDE);
     }
 }
 
@@ -107,7 +108,7 @@ __host__ __device__ __forceinline__ int padidx(int i) {
 }
 
 // One pass: twiddle, butterflies.  v slots: element t + NT*s.  Ns = product of earlier radices.
-template <int E, int NT, int R, int Ns, bool INV>
+template <int E, int NT, int R, int Ns, bool INV, bool PK = false>
 __host__ __device__ __forceinline__ void pass_compute(float2* v, int t, const float2* __restrict__ tw) {
     constexpr int B = E / R;  // butterflies per thread
 #pragma unroll
@@ -120,7 +121,7 @@ __host__ __device__ __forceinline__ void pass_compute(float2* v, int t, const fl
                 v[b + r * B] = INV ? cmul_conj(v[b + r * B], w) : cmul(v[b + r * B], w);
             }
         }
-        fft_dif<R, INV, B>(v + b);
+        fft_dif<R, INV, B, PK>(v + b);
     }
 }
 
@@ -188,17 +189,17 @@ struct NamedBarrier {  // a sub-group of the CTA (e.g. one row of a multi-row bl
     __device__ __forceinline__ void operator()() const { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
 };
 
-template <class P, bool INV, int SMS, int PADSHIFT, class Bar = CtaBarrier>
+template <class P, bool INV, int SMS, int PADSHIFT, class Bar = CtaBarrier, bool PK = false>
 __device__ __forceinline__ void transform(float2* v, int t, float2* sm, const float2* __restrict__ tw, Bar bar = Bar()) {
     constexpr int E = P::E, NT = P::NT;
-    pass_compute<E, NT, P::R0, 1, INV>(v, t, tw);
+    pass_compute<E, NT, P::R0, 1, INV, PK>(v, t, tw);
     if constexpr (P::passes == 1) {
         pass_unpermute<E, P::R0>(v);
     } else {
         pass_scatter<E, NT, P::R0, 1, SMS, PADSHIFT>(v, t, sm);
         bar();
         gather_slots<E, NT, SMS, PADSHIFT>(v, t, sm);
-        pass_compute<E, NT, P::R1, P::R0, INV>(v, t, tw + P::tw_off1);
+        pass_compute<E, NT, P::R1, P::R0, INV, PK>(v, t, tw + P::tw_off1);
         if constexpr (P::passes == 2) {
             pass_unpermute<E, P::R1>(v);
         } else {
@@ -206,7 +207,7 @@ __device__ __forceinline__ void transform(float2* v, int t, float2* sm, const fl
             pass_scatter<E, NT, P::R1, P::R0, SMS, PADSHIFT>(v, t, sm);
             bar();
             gather_slots<E, NT, SMS, PADSHIFT>(v, t, sm);
-            pass_compute<E, NT, P::R2, P::R0 * P::R1, INV>(v, t, tw + P::tw_off2);
+            pass_compute<E, NT, P::R2, P::R0 * P::R1, INV, PK>(v, t, tw + P::tw_off2);
             if constexpr (P::passes == 3) {
                 pass_unpermute<E, P::R2>(v);
             } else {
@@ -214,7 +215,7 @@ __device__ __forceinline__ void transform(float2* v, int t, float2* sm, const fl
                 pass_scatter<E, NT, P::R2, P::R0 * P::R1, SMS, PADSHIFT>(v, t, sm);
                 bar();
                 gather_slots<E, NT, SMS, PADSHIFT>(v, t, sm);
-                pass_compute<E, NT, P::R3, P::R0 * P::R1 * P::R2, INV>(v, t, tw + P::tw_off3);
+                pass_compute<E, NT, P::R3, P::R0 * P::R1 * P::R2, INV, PK>(v, t, tw + P::tw_off3);
                 pass_unpermute<E, P::R3>(v);
             }
         }
