@@ -70,34 +70,70 @@ __host__ __device__ __forceinline__ float2 cmul(float2 a, float2 b) {
 __host__ __device__ __forceinline__ float2 cmul_conj(float2 a, float2 b) {  // a * conj(b)
     return make_float2(fmaf(a.x, b.x, a.y * b.y), fmaf(a.y, b.x, -a.x * b.y));
 }
-// Complex add / subtract as ONE packed instruction on sm_100 (add.f32x2 -> FADD2): same FP32 pipe time as two
-// FADDs (measured, csrc/pipebench.cu) but half the issue slots, which is what the FFT kernels are short of.
+// Packed fp32x2 complex arithmetic (sm_100: FADD2 / FMUL2 / FFMA2).  A complex number already sits in an aligned
+// register pair, and the SASS forms take per-operand half swaps (.LO_HI), lane sign patterns (.NP) and scalar
+// broadcasts (.F32), so ptxas folds the mov.b64 shuffles below into the arithmetic: a complex add is ONE instruction and
+// a complex multiply TWO (scalar code: 2 and 4).  Same FP32 pipe time (measured, csrc/pipebench.cu), half the issue slots --
+// which is what the FFT kernels are short of.
 __host__ __device__ __forceinline__ float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
 __host__ __device__ __forceinline__ float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
+#ifdef __CUDA_ARCH__
+__device__ __forceinline__ unsigned long long pk2(float a, float b) {
+    unsigned long long r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
+    return r;
+}
+__device__ __forceinline__ float2 upk2(unsigned long long r) {
+    float2 c;
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(c.x), "=f"(c.y) : "l"(r));
+    return c;
+}
+#endif
 __host__ __device__ __forceinline__ float2 cadd_pk(float2 a, float2 b) {
 #ifdef __CUDA_ARCH__
-    unsigned long long ra, rb;
-    float2 c;
-    asm("mov.b64 %0, {%1, %2};" : "=l"(ra) : "f"(a.x), "f"(a.y));
-    asm("mov.b64 %0, {%1, %2};" : "=l"(rb) : "f"(b.x), "f"(b.y));
-    asm("add.rn.f32x2 %0, %0, %1;" : "+l"(ra) : "l"(rb));
-    asm("mov.b64 {%0, %1}, %2;" : "=f"(c.x), "=f"(c.y) : "l"(ra));
-    return c;
+    unsigned long long r;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(pk2(a.x, a.y)), "l"(pk2(b.x, b.y)));
+    return upk2(r);
 #else
     return make_float2(a.x + b.x, a.y + b.y);
 #endif
 }
 __host__ __device__ __forceinline__ float2 csub_pk(float2 a, float2 b) {
 #ifdef __CUDA_ARCH__
-    unsigned long long ra, rb;
-    float2 c;
-    asm("mov.b64 %0, {%1, %2};" : "=l"(ra) : "f"(a.x), "f"(a.y));
-    asm("mov.b64 %0, {%1, %2};" : "=l"(rb) : "f"(b.x), "f"(b.y));
-    asm("sub.rn.f32x2 %0, %0, %1;" : "+l"(ra) : "l"(rb));
-    asm("mov.b64 {%0, %1}, %2;" : "=f"(c.x), "=f"(c.y) : "l"(ra));
-    return c;
+    unsigned long long r;
+    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(pk2(a.x, a.y)), "l"(pk2(b.x, b.y)));
+    return upk2(r);
 #else
     return make_float2(a.x - b.x, a.y - b.y);
+#endif
+}
+__host__ __device__ __forceinline__ float2 cmul_pk(float2 a, float2 b) {   // a * b
+#ifdef __CUDA_ARCH__
+    unsigned long long t, r;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(t) : "l"(pk2(a.x, a.y)), "l"(pk2(b.x, b.x)));
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(pk2(a.y, a.x)), "l"(pk2(-b.y, b.y)), "l"(t));
+    return upk2(r);
+#else
+    return cmul(a, b);
+#endif
+}
+__host__ __device__ __forceinline__ float2 cmul_conj_pk(float2 a, float2 b) {   // a * conj(b)
+#ifdef __CUDA_ARCH__
+    unsigned long long t, r;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(t) : "l"(pk2(a.x, a.y)), "l"(pk2(b.x, b.x)));
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(pk2(a.y, a.x)), "l"(pk2(b.y, -b.y)), "l"(t));
+    return upk2(r);
+#else
+    return cmul_conj(a, b);
+#endif
+}
+__host__ __device__ __forceinline__ float2 cscale_pk(float2 a, float s) {   // a * real s
+#ifdef __CUDA_ARCH__
+    unsigned long long r;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(pk2(a.x, a.y)), "l"(pk2(s, s)));
+    return upk2(r);
+#else
+    return make_float2(a.x * s, a.y * s);
 #endif
 }
 

@@ -55,7 +55,7 @@ __global__ void __launch_bounds__(256) k_az_outer_fwd(const float2* __restrict__
 #pragma unroll
     for (int k1 = 0; k1 < A1; ++k1) {
         float2 x = v[brev(k1, L)];
-        if (k1 > 0) x = cmul(x, __ldg(twN + ((a2 * k1) & (n_az - 1))));
+        if (k1 > 0) x = cmul_pk(x, __ldg(twN + ((a2 * k1) & (n_az - 1))));
         out[(int64_t)(k1 * A2 + a2) * out_pitch + n] = x;
     }
 }
@@ -81,7 +81,7 @@ __global__ void __launch_bounds__(256) k_az_outer_inv(const float2* __restrict__
 #pragma unroll
         for (int k1 = 0; k1 < A1; ++k1) {
             float2 x = in[(int64_t)(k1 * A2 + a2) * pitch + n0 + n_off];
-            if (k1 > 0) x = cmul_conj(x, __ldg(twN + ((k1 * a2) & (n_az - 1))));   // four-step twiddle w_N^-(k1 a2)
+            if (k1 > 0) x = cmul_conj_pk(x, __ldg(twN + ((k1 * a2) & (n_az - 1))));   // four-step twiddle w_N^-(k1 a2)
             v[k1] = x;
         }
         fft_dif<A1, true, 1, true>(v);
@@ -115,7 +115,8 @@ __global__ void __launch_bounds__(256) k_az_outer_inv(const float2* __restrict__
 template <class P, bool INV, int W>
 __global__ void __launch_bounds__(P::NT* W) k_az_inner_tma(const __grid_constant__ CUtensorMap map,
                                                            float2* __restrict__ data, int64_t pitch,
-                                                           int n_col_tiles, int n_tiles, const float2* __restrict__ tw) {
+                                                           int n_col_tiles, int n_tiles, int x0, int k10,
+                                                           const float2* __restrict__ tw) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ uint64_t full[2];
     constexpr int E = P::E, NT = P::NT, A2 = P::N;
@@ -131,7 +132,7 @@ __global__ void __launch_bounds__(P::NT* W) k_az_inner_tma(const __grid_constant
     }
     __syncthreads();
     auto issue = [&](int tile, int b) {
-        const int x = tile % n_col_tiles, k1 = tile / n_col_tiles;
+        const int x = x0 + tile % n_col_tiles, k1 = k10 + tile / n_col_tiles;
         tma::mbar_arrive_expect_tx(&full[b], TILE_BYTES);
 #pragma unroll
         for (int i = 0; i < NBOX; ++i)
@@ -149,7 +150,7 @@ __global__ void __launch_bounds__(P::NT* W) k_az_inner_tma(const __grid_constant
         for (int s = 0; s < E; ++s) v[s] = buf[(t + NT * s) * W + c];
         __syncthreads();   // every element is in registers before the exchange overwrites the tile
         transform<P, INV, W, 0, CtaBarrier, true>(v, t, buf + c, tw);
-        const int x = tile % n_col_tiles, k1 = tile / n_col_tiles;
+        const int x = x0 + tile % n_col_tiles, k1 = k10 + tile / n_col_tiles;
         float2* base = data + (int64_t)k1 * A2 * pitch + x * W + c;
 #pragma unroll
         for (int s = 0; s < E; ++s) {
@@ -158,6 +159,110 @@ __global__ void __launch_bounds__(P::NT* W) k_az_inner_tma(const __grid_constant
         tma::fence_proxy_async();   // this thread's exchange writes are ordered before the TMA refill of buf
         __syncthreads();
     }
+}
+
+
+// ------------------------------------------------------------------------------ azimuth, whole columns per cluster
+// One cluster of C CTAs transforms all n_az = C*M samples of W adjacent columns in ONE pass over HBM (the two-kernel
+// four-step above moves every sample twice).  Decimation in time across the cluster:
+//     X[k2 + M k1] = sum_n1 w_C^(n1 k1) * ( w_N^(n1 k2) * sum_n2 x[n1 + C n2] w_M^(n2 k2) )
+// CTA n1 pulls rows n1, n1 + C, ... of the column tile with one strided TMA box sequence (3-D tensor map), runs the
+// M-point transforms in registers / its own shared memory, applies the four-step twiddle and leaves Z'_n1[k2] in shared
+// memory.  After a cluster barrier CTA r gathers, for its slice k2 in [r M/C, (r+1) M/C), the C partial spectra through
+// distributed shared memory (each value crosses the SM-to-SM network once), finishes with radix-C butterflies in
+// registers and stores rows k2 + M k1 (natural Doppler order) straight to HBM -- or, for the inverse transform, the
+// scaled, corner-turned image slc[column][azimuth] with azimuth-contiguous 256-byte stores, plus max |slc|^2.
+// Several CTAs of different clusters share an SM, so one cluster's load / barrier latency hides behind another's math.
+template <class P, int C, int W, bool INV, bool TOUT>
+__global__ void __launch_bounds__(P::NT* W, 1024 / (P::NT * W)) k_az_cluster(const __grid_constant__ CUtensorMap map,
+                                                         float2* __restrict__ out, int64_t out_pitch, int n_col_tiles,
+                                                         float scale, double* __restrict__ max_sq,
+                                                         const float2* __restrict__ tw, const float2* __restrict__ twN) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    __shared__ uint64_t full;
+    constexpr int E = P::E, NT = P::NT, M = P::N, NTH = NT * W;
+    constexpr int SLICE = M / C;              // k2 values finished by one CTA
+    constexpr int JN = SLICE * W / NTH;       // (k2, column) pairs per thread
+    static_assert(SLICE * W % NTH == 0 && JN >= 1, "slice must tile the CTA");
+    constexpr int ZP = M + 2;                 // padded column length of the corner-turned layout
+    constexpr uint32_t TILE_BYTES = M * W * sizeof(float2);
+    constexpr int BOX_ROWS = M < 256 ? M : 256, NBOX = M / BOX_ROWS;
+    float2* const buf = reinterpret_cast<float2*>(smem_raw);
+    const int tid = threadIdx.x, c = tid % W, t = tid / W;
+    const uint32_t rank = tma::cluster_ctarank();
+    const int cluster_id = blockIdx.x / C, n_clusters = gridDim.x / C;
+    if (tid == 0) {
+        tma::mbar_init(&full, 1);
+        tma::fence_barrier_init();
+    }
+    __syncthreads();
+    double mx = 0.0;
+    uint32_t phase = 0;
+    bool pending = false;   // a "my reads of the other CTAs' tiles are done" arrival not yet waited for
+    for (int x = cluster_id; x < n_col_tiles; x += n_clusters) {
+        if (pending) tma::cluster_wait();   // every CTA of the cluster has finished reading this CTA's buffer
+        if (tid == 0) {
+            tma::mbar_arrive_expect_tx(&full, TILE_BYTES);
+#pragma unroll
+            for (int i = 0; i < NBOX; ++i)
+                tma::tile_load_3d(buf + i * BOX_ROWS * W, &map, x * W, (int)rank, i * BOX_ROWS, &full);
+        }
+        tma::mbar_wait(&full, phase);
+        phase ^= 1;
+        float2 v[E];
+#pragma unroll
+        for (int s = 0; s < E; ++s) v[s] = buf[(t + NT * s) * W + c];
+        __syncthreads();   // the tile is in registers: the buffer becomes the exchange buffer
+        transform<P, INV, W, 0, CtaBarrier, true>(v, t, buf + c, tw);
+        if (rank != 0) {
+#pragma unroll
+            for (int s = 0; s < E; ++s) {
+                const float2 w = __ldg(twN + rank * (uint32_t)(t + NT * s));   // n1 k2 < N
+                v[s] = INV ? cmul_conj_pk(v[s], w) : cmul_pk(v[s], w);
+            }
+        }
+        __syncthreads();   // last exchange read by everyone
+#pragma unroll
+        for (int s = 0; s < E; ++s) {
+            const int k2 = t + NT * s;
+            buf[TOUT ? c * ZP + k2 : k2 * W + c] = v[s];
+        }
+        tma::cluster_arrive();   // release: this CTA's partial spectrum is visible to the cluster
+        tma::cluster_wait();     // all C partial spectra are in place
+        constexpr int L = ilog2(C);
+#pragma unroll
+        for (int j = 0; j < JN; ++j) {
+            const int q = tid + NTH * j;
+            int k2, cc;
+            if constexpr (TOUT) { k2 = rank * SLICE + q % SLICE; cc = q / SLICE; }
+            else { k2 = rank * SLICE + q / W; cc = q % W; }
+            const uint32_t local = tma::smem_u32(buf + (TOUT ? cc * ZP + k2 : k2 * W + cc));
+            float2 u[C];
+#pragma unroll
+            for (int n1 = 0; n1 < C; ++n1) u[n1] = tma::ld_cluster_f2(tma::map_to_rank(local, (uint32_t)n1));
+            fft_dif<C, INV, 1, true>(u);
+            if constexpr (TOUT) {
+                float2* o = out + (int64_t)(x * W + cc) * out_pitch + k2;
+#pragma unroll
+                for (int a1 = 0; a1 < C; ++a1) {
+                    const float2 r = make_float2(u[brev(a1, L)].x * scale, u[brev(a1, L)].y * scale);
+                    o[a1 * M] = r;
+                    if (max_sq != nullptr) mx = fmax(mx, sq_mag_f64(r));
+                }
+            } else {
+                float2* o = out + (int64_t)k2 * out_pitch + x * W + cc;
+#pragma unroll
+                for (int k1 = 0; k1 < C; ++k1) o[(int64_t)(k1 * M) * out_pitch] = u[brev(k1, L)];
+            }
+        }
+        tma::fence_proxy_async();   // generic-proxy traffic on the buffers is ordered before the next TMA refill
+        // "my reads of your buffers are done": nothing to publish, so no release fence -- a releasing arrive would also
+        // wait for the global stores just issued (MEMBAR.GPU), 7 % of the kernel when measured
+        tma::cluster_arrive_relaxed();
+        pending = true;
+    }
+    if (pending) tma::cluster_wait();   // nobody may exit while a neighbour still reads its shared memory
+    if (TOUT && max_sq != nullptr) atomic_max_f64(max_sq, warp_max_f64(mx));
 }
 
 // ------------------------------------------------------------------------------ range
@@ -190,7 +295,7 @@ struct PhaseStepper {
 // One Doppler row per group of NT threads: x Phi1 -> FFT -> x Phi2 -> IFFT -> x Phi3, one HBM round
 // trip.  RPB independent row groups share a CTA (named barriers, so groups drift apart and overlap
 // each other's load / exchange / store phases).
-template <class P, int PAD, int RPB, int MINB>
+template <class P, int PAD, int RPB, int MINB, bool PK>
 __global__ void __launch_bounds__(P::NT* RPB, MINB) k_range(float2* __restrict__ data, int64_t pitch, int n_rows,
                                                             const RowCoef* __restrict__ coef,
                                                             const float2* __restrict__ tw) {
@@ -202,7 +307,7 @@ __global__ void __launch_bounds__(P::NT* RPB, MINB) k_range(float2* __restrict__
     // bar.sync counts whole warps: row groups narrower than a warp (or a single group) use the CTA barrier
     constexpr bool kNamed = (NT >= 32) && (RPB > 1);
     // the next row is prefetched into shared memory by a 1-D bulk copy (TMA) while this one is transformed
-    constexpr bool kPrefetch = (NT >= 32);
+    constexpr bool kPrefetch = (NT >= 32) && (N <= 8192);   // a 16384-sample row leaves no room for the prefetch buffer
     constexpr int GROUP_ELEMS = SMROW + (kPrefetch ? N : 0);
     const int t = threadIdx.x;
     float2* sm = reinterpret_cast<float2*>(smem_raw) + threadIdx.y * GROUP_ELEMS;
@@ -253,27 +358,27 @@ __global__ void __launch_bounds__(P::NT* RPB, MINB) k_range(float2* __restrict__
             PhaseStepper ps;
             ps.init(__ldg(&rc->a1), __ldg(&rc->b1), __ldg(&rc->c1), (uint32_t)t, NT);
 #pragma unroll
-            for (int s = 0; s < E; ++s) v[s] = cmul(v[s], ps.next());
+            for (int s = 0; s < E; ++s) v[s] = PK ? cmul_pk(v[s], ps.next()) : cmul(v[s], ps.next());
         }
-        transform<P, false, 1, PAD>(v, t, sm, tw, bar);
+        transform<P, false, 1, PAD, Bar, PK>(v, t, sm, tw, bar);
         {
             const uint64_t a2 = __ldg(&rc->a2), b2 = __ldg(&rc->b2);
             PhaseStepper ps;
             ps.init(a2, b2, 0ull, (uint32_t)t, NT);
 #pragma unroll
-            for (int s = 0; s < E / 2; ++s) v[s] = cmul(v[s], ps.next());
+            for (int s = 0; s < E / 2; ++s) v[s] = PK ? cmul_pk(v[s], ps.next()) : cmul(v[s], ps.next());
             ps.init_mirror(a2, b2, __ldg(&rc->bn2), (uint32_t)(N / 2 - t), (uint32_t)(N / 2 + t), NT);
 #pragma unroll
-            for (int s = E / 2; s < E; ++s) v[s] = cmul(v[s], ps.next());
+            for (int s = E / 2; s < E; ++s) v[s] = PK ? cmul_pk(v[s], ps.next()) : cmul(v[s], ps.next());
         }
         bar();
-        transform<P, true, 1, PAD>(v, t, sm, tw, bar);
+        transform<P, true, 1, PAD, Bar, PK>(v, t, sm, tw, bar);
         {
             PhaseStepper ps;
             ps.init(__ldg(&rc->a3), __ldg(&rc->b3), __ldg(&rc->c3), (uint32_t)t, NT);
 #pragma unroll
             for (int s = 0; s < E; ++s) {
-                const float2 x = cmul(v[s], ps.next());
+                const float2 x = PK ? cmul_pk(v[s], ps.next()) : cmul(v[s], ps.next());
                 if (live) p[t + NT * s] = x;
             }
         }
@@ -287,16 +392,16 @@ __global__ void __launch_bounds__(P::NT* RPB, MINB) k_range(float2* __restrict__
 namespace {
 
 template <int A1>
-int launch_outer_fwd(nis_csa_plan* pl, const float2* in, int64_t in_pitch, cudaStream_t st) {
-    dim3 grid((pl->n_rg + 31) / 32, (pl->A2 + 7) / 8);
-    k_az_outer_fwd<A1><<<grid, 256, 0, st>>>(in, in_pitch, pl->work, pl->n_rg, pl->n_rg, pl->A2, pl->n_az,
+int launch_outer_fwd(nis_csa_plan* pl, const float2* in, int64_t in_pitch, int col0, int ncols, cudaStream_t st) {
+    dim3 grid((ncols + 31) / 32, (pl->A2 + 7) / 8);
+    k_az_outer_fwd<A1><<<grid, 256, 0, st>>>(in + col0, in_pitch, pl->work + col0, pl->n_rg, ncols, pl->A2, pl->n_az,
                                               pl->tw_full);
     NIS_LAUNCH_CHECK(pl->ctx);
     return NIS_OK;
 }
 
 template <int A1, int TN, int TA>
-int launch_outer_inv(nis_csa_plan* pl, float2* slc, double* max_sq, cudaStream_t st) {
+int launch_outer_inv(nis_csa_plan* pl, float2* slc, double* max_sq, int col0, int ncols, cudaStream_t st) {
     const size_t smem = (size_t)A1 * TN * (TA + 1) * sizeof(float2);
     static bool attr_done = false;
     if (!attr_done) {
@@ -304,16 +409,16 @@ int launch_outer_inv(nis_csa_plan* pl, float2* slc, double* max_sq, cudaStream_t
                                           (int)smem));
         attr_done = true;
     }
-    dim3 grid(pl->n_rg / TN, pl->A2 / TA);
+    dim3 grid(ncols / TN, pl->A2 / TA);
     const float scale = (float)(1.0 / ((double)pl->n_az * (double)pl->n_rg));
-    k_az_outer_inv<A1, TN, TA><<<grid, 256, smem, st>>>(pl->work, pl->n_rg, slc, pl->n_rg, pl->A2, pl->n_az, scale,
-                                                        max_sq, pl->tw_full);
+    k_az_outer_inv<A1, TN, TA><<<grid, 256, smem, st>>>(pl->work + col0, pl->n_rg, slc + (int64_t)col0 * pl->n_az,
+                                                        pl->n_rg, pl->A2, pl->n_az, scale, max_sq, pl->tw_full);
     NIS_LAUNCH_CHECK(pl->ctx);
     return NIS_OK;
 }
 
 template <class P, int W>
-int launch_inner(nis_csa_plan* pl, bool inv, cudaStream_t st) {
+int launch_inner(nis_csa_plan* pl, bool inv, int col0, int ncols, int k10, int nk1, cudaStream_t st) {
     const size_t smem = 2 * (size_t)P::N * W * sizeof(float2);   // double-buffered tile
     static bool attr_done = false;
     if (!attr_done) {
@@ -326,36 +431,39 @@ int launch_inner(nis_csa_plan* pl, bool inv, cudaStream_t st) {
     int per_sm = 1;
     NIS_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_az_inner_tma<P, false, W>, P::NT * W, smem));
     if (per_sm < 1) per_sm = 1;
-    const int n_col_tiles = pl->n_rg / W, n_tiles = n_col_tiles * pl->A1;
+    const int n_col_tiles = ncols / W, n_tiles = n_col_tiles * nk1;
     int grid = pl->ctx->num_sms * per_sm;
     if (grid > n_tiles) grid = n_tiles;
     if (inv)
         k_az_inner_tma<P, true, W><<<grid, P::NT * W, smem, st>>>(pl->tile_map, pl->work, pl->n_rg, n_col_tiles, n_tiles,
-                                                                  pl->tw_inner);
+                                                                  col0 / W, k10, pl->tw_inner);
     else
         k_az_inner_tma<P, false, W><<<grid, P::NT * W, smem, st>>>(pl->tile_map, pl->work, pl->n_rg, n_col_tiles, n_tiles,
-                                                                   pl->tw_inner);
+                                                                   col0 / W, k10, pl->tw_inner);
     NIS_LAUNCH_CHECK(pl->ctx);
     return NIS_OK;
 }
 
-template <class P, int PAD, int RPB, int MINB>
-int launch_range(nis_csa_plan* pl, cudaStream_t st) {
+// PK = false: the packed forms cut this kernel's instruction count by a third but not its time (it is bound by the
+// FMA pipe and the MIO/shared-memory pipe back to back, not by issue slots; measured 0.466 vs 0.456 ms at 8192^2)
+template <class P, int PAD, int RPB, int MINB, bool PK = false>
+int launch_range(nis_csa_plan* pl, int row0, int nrows, cudaStream_t st) {
     constexpr int SMROW = P::N + (PAD ? (P::N >> PAD) : 0);
-    constexpr int GROUP_ELEMS = SMROW + (P::NT >= 32 ? P::N : 0);   // exchange buffer + prefetch buffer
+    constexpr int GROUP_ELEMS = SMROW + ((P::NT >= 32 && P::N <= 8192) ? P::N : 0);   // exchange buffer + prefetch buffer
     const size_t smem = (size_t)GROUP_ELEMS * RPB * sizeof(float2);
     static bool attr_done = false;
     if (!attr_done) {
-        NIS_CUDA_TRY(cudaFuncSetAttribute(k_range<P, PAD, RPB, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        NIS_CUDA_TRY(cudaFuncSetAttribute(k_range<P, PAD, RPB, MINB, PK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr_done = true;
     }
     int per_sm = 1;
-    NIS_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_range<P, PAD, RPB, MINB>, P::NT * RPB, smem));
+    NIS_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_range<P, PAD, RPB, MINB, PK>, P::NT * RPB, smem));
     if (per_sm < 1) per_sm = 1;
-    const int blocks_needed = (pl->n_az + RPB - 1) / RPB;
+    const int blocks_needed = (nrows + RPB - 1) / RPB;
     int grid = pl->ctx->num_sms * per_sm;
     if (grid > blocks_needed) grid = blocks_needed;
-    k_range<P, PAD, RPB, MINB><<<grid, dim3(P::NT, RPB), smem, st>>>(pl->work, pl->n_rg, pl->n_az, pl->coef, pl->tw_rg);
+    k_range<P, PAD, RPB, MINB, PK><<<grid, dim3(P::NT, RPB), smem, st>>>(pl->work + (int64_t)row0 * pl->n_rg, pl->n_rg, nrows,
+                                                                     pl->coef + row0, pl->tw_rg);
     NIS_LAUNCH_CHECK(pl->ctx);
     return NIS_OK;
 }
@@ -381,9 +489,88 @@ int upload_twiddles(float2** dev) {
     return NIS_OK;
 }
 
+
+// cluster azimuth transforms: forward (raw -> W, natural Doppler row order) and inverse (W -> slc, corner-turned)
+template <class P, int C, int W, bool INV>
+int launch_az_cluster(nis_csa_plan* pl, const CUtensorMap& map, float2* out, int64_t out_pitch, double* max_sq,
+                      cudaStream_t st) {
+    auto kern = k_az_cluster<P, C, W, INV, INV>;
+    const size_t smem = INV ? (size_t)W * (P::N + 2) * sizeof(float2) : (size_t)P::N * W * sizeof(float2);
+    static int n_clusters = 0;
+    cudaLaunchConfig_t cfg = {};
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = C;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.blockDim = dim3(P::NT * W);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    if (!n_clusters) {
+        NIS_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        if (C > 8) NIS_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+        cfg.gridDim = dim3(C * pl->ctx->num_sms);
+        int n = 0;
+        NIS_CUDA_TRY(cudaOccupancyMaxActiveClusters(&n, kern, &cfg));
+        if (n < 1) {
+            set_error("azimuth cluster kernel: no cluster of %d CTAs x %zu bytes fits this device", C, smem);
+            return NIS_ERR_UNSUPPORTED;
+        }
+        if (const char* v = getenv("NIS_AZ_CLUSTERS")) { const int lim = atoi(v); if (lim > 0 && lim < n) n = lim; }
+        n_clusters = n;
+        if (getenv("NIS_DEBUG")) fprintf(stderr, "[nis] az cluster C=%d M=%d W=%d inv=%d: %d clusters resident, %zu B smem\n", C, P::N, W, (int)INV, n, smem);
+    }
+    const int n_col_tiles = pl->n_rg / W;
+    const int nc = n_clusters < n_col_tiles ? n_clusters : n_col_tiles;
+    cfg.gridDim = dim3(C * nc);
+    const float scale = (float)(1.0 / ((double)pl->n_az * (double)pl->n_rg));
+    NIS_CUDA_TRY(cudaLaunchKernelEx(&cfg, kern, map, out, out_pitch, n_col_tiles, scale, max_sq,
+                                    (const float2*)pl->tw_inner, (const float2*)pl->tw_full));
+    NIS_LAUNCH_CHECK(pl->ctx);
+    return NIS_OK;
+}
+template <class P, int C, int W>
+int az_cluster_fwd(nis_csa_plan* pl, const float2* in, int64_t pitch, cudaStream_t st) {
+    if (pl->in_map_base != in || pl->in_map_pitch != pitch) {
+        int rc = tma::make_tile_map_3d(&pl->in_map, in, pl->n_rg, C, P::N, pitch, P::N < 256 ? P::N : 256, W);
+        if (rc != NIS_OK) return rc;
+        pl->in_map_base = in;
+        pl->in_map_pitch = pitch;
+    }
+    return launch_az_cluster<P, C, W, false>(pl, pl->in_map, pl->work, pl->n_rg, nullptr, st);
+}
+template <class P, int C, int W>
+int az_cluster_inv(nis_csa_plan* pl, float2* slc, double* max_sq, cudaStream_t st) {
+    return launch_az_cluster<P, C, W, true>(pl, pl->work_map3, slc, pl->n_az, max_sq, st);
+}
+template <class P, int C, int W>
+int az_cluster_setup(nis_csa_plan* pl) {
+    pl->az_cluster = true;
+    pl->A1 = 1;            // rows of W hold Doppler bins in natural order
+    pl->A2 = pl->n_az;
+    pl->az_fwd = az_cluster_fwd<P, C, W>;
+    pl->az_inv = az_cluster_inv<P, C, W>;
+    int rc = upload_twiddles<P>(&pl->tw_inner);
+    if (rc != NIS_OK) return rc;
+    return tma::make_tile_map_3d(&pl->work_map3, pl->work, pl->n_rg, C, P::N, pl->n_rg, P::N < 256 ? P::N : 256, W);
+}
+
 struct AzSplit { int n, a1, a2; };
 const AzSplit kAzSplits[] = {{64, 4, 16},     {128, 8, 16},    {256, 16, 16},   {512, 8, 64},    {1024, 16, 64},
                              {2048, 8, 256},  {4096, 16, 256}, {8192, 16, 512}, {16384, 16, 1024}};
+
+struct AzClusterCfg { int n_az, id; int (*setup)(nis_csa_plan*); };
+const AzClusterCfg kAzCluster[] = {
+    {16384, 1, az_cluster_setup<P1024, 16, 8>},
+    {8192, 1, az_cluster_setup<P1024, 8, 8>}, {8192, 2, az_cluster_setup<P512, 16, 8>},
+    {8192, 3, az_cluster_setup<P512, 16, 16>},
+    {4096, 1, az_cluster_setup<P512, 8, 8>},  {4096, 2, az_cluster_setup<P1024, 4, 8>},
+    {4096, 3, az_cluster_setup<P256, 16, 8>}, {4096, 4, az_cluster_setup<P256, 16, 16>},
+    {2048, 1, az_cluster_setup<P256, 8, 8>},  {2048, 2, az_cluster_setup<P512, 4, 8>},
+    {1024, 1, az_cluster_setup<P256, 4, 8>},
+};
 
 bool range_supported(int n) { return n >= 64 && n <= 16384 && (n & (n - 1)) == 0; }
 bool az_supported(int n) {
@@ -502,6 +689,12 @@ extern "C" int nis_csa_plan_create(nis_ctx* ctx, int32_t n_az, int32_t n_rg, con
     } else {
         for (const auto& s : kAzSplits)
             if (s.n == n_az) { pl->A1 = s.a1; pl->A2 = s.a2; }
+        // default: whole-column cluster transforms where they measured faster than the two-kernel four-step
+        // (n_az = 4096: 0.187 vs 0.204 ms per frame on a B200); NIS_CSA_AZ = 0 / k overrides (development knob)
+        int az_id = (n_az == 4096) ? 1 : 0;
+        if (const char* v = getenv("NIS_CSA_AZ")) az_id = atoi(v);
+        for (const auto& c : kAzCluster)
+            if (c.n_az == n_az && c.id == az_id && n_rg % 16 == 0) FAIL_IF(c.setup(pl));
     }
     {
         std::vector<RowCoef> h = build_row_coefs(n_az, n_rg, *prm, pl->A1, pl->A2);
@@ -515,6 +708,7 @@ extern "C" int nis_csa_plan_create(nis_ctx* ctx, int32_t n_az, int32_t n_rg, con
     }
 
     // ---- kernel selection (power-of-two path)
+    if (!pl->az_cluster) {
     switch (pl->A1) {
         case 4: pl->outer_fwd = launch_outer_fwd<4>; pl->outer_inv = launch_outer_inv<4, 16, 16>; break;
         case 8: pl->outer_fwd = launch_outer_fwd<8>;
@@ -536,7 +730,8 @@ extern "C" int nis_csa_plan_create(nis_ctx* ctx, int32_t n_az, int32_t n_rg, con
         case 64: pl->inner_w = 32; pl->inner = launch_inner<P64, 32>; FAIL_IF(upload_twiddles<P64>(&pl->tw_inner)); break;
         case 256: pl->inner_w = 16; pl->inner = launch_inner<P256, 16>; FAIL_IF(upload_twiddles<P256>(&pl->tw_inner)); break;
         case 512: pl->inner_w = 8; pl->inner = launch_inner<P512, 8>; FAIL_IF(upload_twiddles<P512>(&pl->tw_inner)); break;
-        default: pl->inner_w = 16; pl->inner = launch_inner<P1024, 16>; FAIL_IF(upload_twiddles<P1024>(&pl->tw_inner)); break;
+        default: pl->inner_w = 8; pl->inner = launch_inner<P1024, 8>; FAIL_IF(upload_twiddles<P1024>(&pl->tw_inner)); break;
+    }
     }
     switch (n_rg) {
         case 64: pl->range = launch_range<P64, 3, 8, 1>; FAIL_IF(upload_twiddles<P64>(&pl->tw_rg)); break;
@@ -549,7 +744,8 @@ extern "C" int nis_csa_plan_create(nis_ctx* ctx, int32_t n_az, int32_t n_rg, con
         case 8192: pl->range = launch_range<P8192, 4, 1, 1>; FAIL_IF(upload_twiddles<P8192>(&pl->tw_rg)); break;
         default: pl->range = launch_range<P16384, 4, 1, 1>; FAIL_IF(upload_twiddles<P16384>(&pl->tw_rg)); break;
     }
-    FAIL_IF(tma::make_tile_map(&pl->tile_map, pl->work, n_az, n_rg, n_rg, pl->A2 < 256 ? pl->A2 : 256, pl->inner_w));
+    if (!pl->az_cluster)
+        FAIL_IF(tma::make_tile_map(&pl->tile_map, pl->work, n_az, n_rg, n_rg, pl->A2 < 256 ? pl->A2 : 256, pl->inner_w));
     // ---- full-length azimuth twiddles w_N^m
     {
         std::vector<float2> h(n_az);
@@ -583,17 +779,34 @@ extern "C" int nis_csa_focus(nis_csa_plan* pl, const nis_c32* phist, int64_t pit
     cudaEvent_t* ev = pl->profiling ? pl->prof_ev[pl->prof_calls % nis_csa_plan::kProfRing] : nullptr;
 #define STAGE_MARK(i) do { if (ev) NIS_CUDA_TRY(cudaEventRecord(ev[i], st)); } while (0)
     int rc;
-    STAGE_MARK(0);
-    if ((rc = pl->outer_fwd(pl, reinterpret_cast<const float2*>(phist), pitch, st)) != NIS_OK) return rc;
-    STAGE_MARK(1);
-    if ((rc = pl->inner(pl, false, st)) != NIS_OK) return rc;
-    STAGE_MARK(2);
-    if ((rc = pl->range(pl, st)) != NIS_OK) return rc;
-    STAGE_MARK(3);
-    if ((rc = pl->inner(pl, true, st)) != NIS_OK) return rc;
-    STAGE_MARK(4);
-    if ((rc = pl->outer_inv(pl, reinterpret_cast<float2*>(slc), max_sq, st)) != NIS_OK) return rc;
-    STAGE_MARK(5);
+    const int n_az = pl->n_az, n_rg = pl->n_rg, A1 = pl->A1;
+    const float2* in = reinterpret_cast<const float2*>(phist);
+    float2* out = reinterpret_cast<float2*>(slc);
+#define RUN(x) do { if ((rc = (x)) != NIS_OK) return rc; } while (0)
+    if (pl->az_cluster) {
+        STAGE_MARK(0);
+        RUN(pl->az_fwd(pl, in, pitch, st));
+        STAGE_MARK(1);
+        STAGE_MARK(2);
+        RUN(pl->range(pl, 0, n_az, st));
+        STAGE_MARK(3);
+        STAGE_MARK(4);
+        RUN(pl->az_inv(pl, out, max_sq, st));
+        STAGE_MARK(5);
+    } else {
+        STAGE_MARK(0);
+        RUN(pl->outer_fwd(pl, in, pitch, 0, n_rg, st));
+        STAGE_MARK(1);
+        RUN(pl->inner(pl, false, 0, n_rg, 0, A1, st));
+        STAGE_MARK(2);
+        RUN(pl->range(pl, 0, n_az, st));
+        STAGE_MARK(3);
+        RUN(pl->inner(pl, true, 0, n_rg, 0, A1, st));
+        STAGE_MARK(4);
+        RUN(pl->outer_inv(pl, out, max_sq, 0, n_rg, st));
+        STAGE_MARK(5);
+    }
+#undef RUN
 #undef STAGE_MARK
     if (ev) pl->prof_calls++;
     return NIS_OK;

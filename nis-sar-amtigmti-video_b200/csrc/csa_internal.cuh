@@ -53,10 +53,11 @@ int generic_focus(nis_csa_plan* pl, const float2* phist, int64_t pitch, float2* 
 }  // namespace csa
 }  // namespace nis
 
-typedef int (*nis_az_outer_fwd_fn)(nis_csa_plan*, const float2*, int64_t, cudaStream_t);
-typedef int (*nis_az_outer_inv_fn)(nis_csa_plan*, float2*, double*, cudaStream_t);
-typedef int (*nis_az_inner_fn)(nis_csa_plan*, bool, cudaStream_t);
-typedef int (*nis_range_fn)(nis_csa_plan*, cudaStream_t);
+// every stage takes the window it works on: columns [col0, col0 + ncols), row blocks [k10, k10 + nk1), rows
+typedef int (*nis_az_outer_fwd_fn)(nis_csa_plan*, const float2*, int64_t, int col0, int ncols, cudaStream_t);
+typedef int (*nis_az_outer_inv_fn)(nis_csa_plan*, float2*, double*, int col0, int ncols, cudaStream_t);
+typedef int (*nis_az_inner_fn)(nis_csa_plan*, bool, int col0, int ncols, int k10, int nk1, cudaStream_t);
+typedef int (*nis_range_fn)(nis_csa_plan*, int row0, int nrows, cudaStream_t);
 
 struct nis_csa_plan {
     nis_ctx* ctx = nullptr;
@@ -80,5 +81,12 @@ struct nis_csa_plan {
     nis_az_outer_inv_fn outer_inv = nullptr;
     nis_az_inner_fn inner = nullptr;
     nis_range_fn range = nullptr;
+    // whole-column azimuth transforms by thread-block clusters (one HBM pass each)
+    bool az_cluster = false;
+    int (*az_fwd)(nis_csa_plan*, const float2*, int64_t, cudaStream_t) = nullptr;
+    int (*az_inv)(nis_csa_plan*, float2*, double*, cudaStream_t) = nullptr;
+    CUtensorMap work_map3{}, in_map{};
+    const void* in_map_base = nullptr;
+    int64_t in_map_pitch = 0;
     nis::csa::GenericState* generic = nullptr;
 };

@@ -41,8 +41,8 @@ __host__ __device__ constexpr int brev(int k, int bits) {
     return r;
 }
 
-// d * exp(-+ 2 pi i I / N)  (forward: minus), with the trivial cases folded at compile time
-template <int N, bool INV, int I>
+// d * exp(-+ 2 pi i I / N)  (forward: minus), with the trivial cases folded at compile time.  PK: packed fp32x2 forms.
+template <int N, bool INV, int I, bool PK = false>
 __host__ __device__ __forceinline__ float2 twmul(float2 d) {
     constexpr int q = I * (32 / N);  // 0 <= q < 16
     constexpr float h = 0.70710678118654757f;
@@ -50,6 +50,13 @@ __host__ __device__ __forceinline__ float2 twmul(float2 d) {
         return d;
     } else if constexpr (q == 8) {
         return INV ? make_float2(-d.y, d.x) : make_float2(d.y, -d.x);
+    } else if constexpr (PK && q == 4) {     // h (1 -+ i) d = h (d + (-+i) d)
+        return cscale_pk(cadd_pk(d, INV ? make_float2(-d.y, d.x) : make_float2(d.y, -d.x)), h);
+    } else if constexpr (PK && q == 12) {    // h (-1 -+ i) d = h ((-+i) d - d)
+        return cscale_pk(csub_pk(INV ? make_float2(-d.y, d.x) : make_float2(d.y, -d.x), d), h);
+    } else if constexpr (PK) {
+        constexpr float c = cos32(q), s = sin32(q);   // w = c - i s (forward)
+        return INV ? cmul_pk(d, make_float2(c, s)) : cmul_conj_pk(d, make_float2(c, s));
     } else if constexpr (q == 4) {
         return INV ? make_float2((d.x - d.y) * h, (d.x + d.y) * h) : make_float2((d.x + d.y) * h, (d.y - d.x) * h);
     } else if constexpr (q == 12) {
@@ -67,7 +74,7 @@ __host__ __device__ __forceinline__ void dif_bfly(float2* v) {
     constexpr int H = N / 2;
     float2 a = v[I * STRIDE], b = v[(I + H) * STRIDE];
     v[I * STRIDE] = PK ? cadd_pk(a, b) : cadd(a, b);
-    v[(I + H) * STRIDE] = twmul<N, INV, I>(PK ? csub_pk(a, b) : csub(a, b));
+    v[(I + H) * STRIDE] = twmul<N, INV, I, PK>(PK ? csub_pk(a, b) : csub(a, b));
 }
 template <int N, bool INV, int STRIDE, bool PK, int... I>
 __host__ __device__ __forceinline__ void dif_level(float2* v, std::integer_sequence<int, I...>) {
@@ -118,7 +125,8 @@ __host__ __device__ __forceinline__ void pass_compute(float2* v, int t, const fl
 #pragma unroll
             for (int r = 1; r < R; ++r) {
                 float2 w = NIS_LDG(tw + (r - 1) * Ns + k);
-                v[b + r * B] = INV ? cmul_conj(v[b + r * B], w) : cmul(v[b + r * B], w);
+                if constexpr (PK) v[b + r * B] = INV ? cmul_conj_pk(v[b + r * B], w) : cmul_pk(v[b + r * B], w);
+                else v[b + r * B] = INV ? cmul_conj(v[b + r * B], w) : cmul(v[b + r * B], w);
             }
         }
         fft_dif<R, INV, B, PK>(v + b);

@@ -55,8 +55,78 @@ __device__ __forceinline__ void tile_load_2d(void* dst_smem, const CUtensorMap* 
         : "memory");
 }
 
+// 3-D tile load: box at (c0 = column, c1, c2) of a matrix viewed as [c2][c1][column]
+__device__ __forceinline__ void tile_load_3d(void* dst_smem, const CUtensorMap* map, int c0, int c1, int c2, uint64_t* bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(
+            smem_u32(dst_smem)),
+        "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(smem_u32(bar))
+        : "memory");
+}
+
+// ---- thread-block clusters: rank, split barrier, distributed shared memory loads
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_arrive() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
+__device__ __forceinline__ void cluster_arrive_relaxed() { asm volatile("barrier.cluster.arrive.relaxed.aligned;" ::: "memory"); }
+__device__ __forceinline__ void cluster_wait() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
+// address of the same shared-memory location in CTA `rank` of this cluster
+__device__ __forceinline__ uint32_t map_to_rank(uint32_t smem_addr, uint32_t rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_addr), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ float2 ld_cluster_f2(uint32_t addr) {
+    float2 v;
+    asm volatile("ld.shared::cluster.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(addr) : "memory");
+    return v;
+}
+
 // Host: tensor map of a row-major [rows][pitch] matrix of 8-byte elements (complex64), box = box_rows x box_cols.
 // The driver entry point is resolved at run time so that the library does not link against libcuda.
+typedef CUresult (*encode_fn_t)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+inline encode_fn_t encode_entry() {
+    static encode_fn_t fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres);
+        if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess || !p) {
+            set_error("cuTensorMapEncodeTiled entry point unavailable (%s)", cudaGetErrorString(e));
+            return nullptr;
+        }
+        fn = (encode_fn_t)p;
+    }
+    return fn;
+}
+
+// Host: a row-major [n1 * n2 rows][pitch] matrix of complex64 viewed as [n2][n1][cols] (row = j1 + n1 * j2), box =
+// box_rows (along j2) x 1 x box_cols: one CTA of a cluster pulls every n1-th row of a column tile.
+inline int make_tile_map_3d(CUtensorMap* out, const void* base, uint64_t cols, uint64_t n1, uint64_t n2,
+                            uint64_t pitch_elems, uint32_t box_rows, uint32_t box_cols) {
+    encode_fn_t fn = encode_entry();
+    if (!fn) return NIS_ERR_CUDA;
+    const cuuint64_t dims[3] = {cols, n1, n2};
+    const cuuint64_t strides[2] = {pitch_elems * 8, pitch_elems * 8 * n1};
+    const cuuint32_t box[3] = {box_cols, 1, box_rows};
+    const cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_UINT64, 3, const_cast<void*>(base), dims, strides, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_error("cuTensorMapEncodeTiled (3-D) failed with CUresult %d (cols %llu n1 %llu n2 %llu pitch %llu box %u x %u)",
+                  (int)r, (unsigned long long)cols, (unsigned long long)n1, (unsigned long long)n2,
+                  (unsigned long long)pitch_elems, box_rows, box_cols);
+        return NIS_ERR_CUDA;
+    }
+    return NIS_OK;
+}
+
 inline int make_tile_map(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t pitch_elems,
                          uint32_t box_rows, uint32_t box_cols) {
     typedef CUresult (*encode_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,

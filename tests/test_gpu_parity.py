@@ -139,7 +139,8 @@ def test_echo_many_scatterers_and_edge_cases(api, dev):
 
 
 # ------------------------------------------------------------------------------------------ K2
-CSA_SIZES = [(64, 64), (64, 128), (128, 256), (256, 64), (512, 512), (1024, 2048), (2048, 1024), (4096, 4096)]
+CSA_SIZES = [(64, 64), (64, 128), (128, 256), (256, 64), (512, 512), (1024, 2048), (2048, 1024), (4096, 4096),
+             (4096, 64), (8192, 128), (128, 8192), (16384, 64), (64, 16384)]
 
 
 @pytest.mark.parametrize("n_az,n_rg", CSA_SIZES)
@@ -157,6 +158,35 @@ def test_csa_random_input_vs_oracle(api, n_az, n_rg):
     assert err < TOL_L2
     assert np.array_equal(rax, rrax)
     assert np.allclose(cax, rcax, rtol=1e-13, atol=1e-9)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("n_az,az_cfg", [(1024, 1), (2048, 1), (2048, 2), (4096, 0), (4096, 1), (4096, 2), (4096, 3),
+                                         (4096, 4), (8192, 1), (8192, 2), (8192, 3), (16384, 1)])
+def test_csa_azimuth_engines_vs_oracle(api, dev, n_az, az_cfg, monkeypatch):
+    """Every azimuth engine of the power-of-two path -- the two-kernel four-step (0) and each thread-block-cluster
+    configuration (cluster size x per-CTA transform length x tile width) -- against the oracle, selected with the
+    development knob NIS_CSA_AZ (read at plan creation)."""
+    monkeypatch.setenv("NIS_CSA_AZ", str(az_cfg))
+    for pl in dev._plan_cache.values():
+        pl.close()
+    dev._plan_cache.clear()
+    n_rg = 128
+    prm = params.spaceborne_preset()
+    rng = np.random.default_rng(n_az + az_cfg)
+    x = (rng.standard_normal((n_az, n_rg)) + 1j * rng.standard_normal((n_az, n_rg))).astype(np.complex64)
+    try:
+        img, _, _ = api.sar_focus_csa(x, prm.Lambda, prm.T_p, prm.k_rate, prm.FS, prm.PRF, prm.V_eff, prm.R0,
+                                      prm.t_start_fast)
+    finally:
+        for pl in dev._plan_cache.values():
+            pl.close()
+        dev._plan_cache.clear()
+    ref, _, _ = orc.focus_csa(x.astype(np.complex128), prm.Lambda, prm.k_rate, prm.FS, prm.PRF, prm.V_eff, prm.R0,
+                              prm.t_start_fast)
+    err = _rel(img, ref)
+    print(f"CSA az engine {az_cfg} at {n_az}x{n_rg}: rel-L2 {err:.3e}")
+    assert err < TOL_L2
 
 
 def test_csa_golden_reference_vector(api):
