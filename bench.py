@@ -400,7 +400,7 @@ def run_gpu_arm(args):
     if os.path.isfile(tpath):
         traffic = json.load(open(tpath)).get(dom)
 
-    cpu_v, e_rate, c_rate, cpu_dt = cpu_step_throughput(1, pulses=4, n_csa=2048) if world == 1 else (None, 0, 0, 0)
+    cpu_v, e_rate, c_rate, cpu_dt = cpu_step_throughput(1, pulses=128, n_csa=4096) if world == 1 else (None, 0, 0, 0)
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -432,8 +432,8 @@ def run_gpu_arm(args):
     if cpu_v is not None:
         line["cpu_baseline"] = {
             "value": cpu_v, "unit": UNIT, "cores": 1, "kind": "port",
-            "sample": f"numpy port of run_physics_engine on 4 of {N_AZ} pulses ({e_rate:.3g} scatterer-samples/s) + "
-                      f"sar_focus_csa port on a 2048x2048 frame ({c_rate / 1e6:.3g} Mpixel/s); per-pixel costs added; "
+            "sample": f"numpy port of run_physics_engine on 128 of {N_AZ} pulses ({e_rate:.3g} scatterer-samples/s) + "
+                      f"sar_focus_csa port on a 4096x4096 frame ({c_rate / 1e6:.3g} Mpixel/s); per-pixel costs added; "
                       f"{cpu_dt:.1f} s of CPU work"}
     print(json.dumps(line))
     if world > 1:

@@ -153,6 +153,35 @@ def golden_chain():
         f_contiguous=bool(slc1.flags.f_contiguous))
 
 
+def golden_rda():
+    """sar_focus_rda of the three simulators on seeded random phase histories: a power-of-two case, a
+    smooth non-power-of-two case and an odd x odd case (exercises the (n-1)/2 axis branches)."""
+    prm = params.spaceborne_preset(fs=60e6, bw=50e6).replace(T_p=1e-6)
+    fns = ref_extract.rda_functions()
+    rng = np.random.default_rng(77)
+    out = {"t_p": prm.T_p, "kr": prm.k_rate, "fs": prm.FS, "prf": prm.PRF, "vr": prm.V_eff, "r0": prm.R0, "lam": prm.Lambda}
+    for tag, (nr, npul) in {"p2": (256, 128), "smooth": (200, 96), "odd": (131, 45)}.items():
+        x = (rng.standard_normal((nr, npul)) + 1j * rng.standard_normal((nr, npul))).astype(np.complex64)
+        args = (x.astype(np.complex128), prm.Lambda, prm.T_p, prm.k_rate, prm.FS, prm.PRF, prm.V_eff, prm.R0)
+        img, rax, cax, rc, rd, rcmc, filt, dop = fns["vehicle"](*args)
+        img7 = fns["satellite"](*args)
+        img3 = fns["moving"](*args)
+        assert len(img7) == 7 and len(img3) == 3
+        assert np.array_equal(img7[0], img) and np.array_equal(img3[0], img) and np.array_equal(img7[5], rcmc)
+        out[f"{tag}_in"] = x
+        out[f"{tag}_img"] = img
+        out[f"{tag}_rax"] = rax
+        out[f"{tag}_cax"] = cax
+        # intermediates: every 3rd range sample x every 2nd pulse (the odd case in full)
+        sl = (slice(None), slice(None)) if tag == "odd" else (slice(None, None, 3), slice(None, None, 2))
+        out[f"{tag}_rc"] = rc[sl].astype(np.complex64)
+        out[f"{tag}_rd"] = rd[sl].astype(np.complex64)
+        out[f"{tag}_rcmc"] = rcmc[sl].astype(np.complex64)
+        out[f"{tag}_filt"] = filt[sl].astype(np.complex64)
+        out[f"{tag}_dop"] = dop
+    np.savez_compressed(os.path.join(OUT, "rda_random.npz"), **out)
+
+
 if __name__ == "__main__":
     if not ref_extract.reference_available():
         sys.exit("reference tree not found: fixtures can only be regenerated in the build container")
@@ -161,5 +190,6 @@ if __name__ == "__main__":
     golden_echo()
     golden_csa()
     golden_chain()
+    golden_rda()
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))

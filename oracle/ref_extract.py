@@ -108,3 +108,18 @@ def vehicle_target_generators():
     spec.loader.exec_module(mod)
     return {n: getattr(mod, n) for n in
             ("generate_car", "generate_tank", "generate_fighter_jet", "generate_f35", "generate_destroyer")}
+
+
+def rda_functions():
+    """``sar_focus_rda`` of the three simulators that define it (sar_satellite_sim.py:356-448 -> 7-tuple,
+    sar_vehicle_sim.py:182-274 -> 8-tuple, sar_satellite_moving_sim.py:208-285 -> 3-tuple).  They read no module
+    globals; scipy supplies interp1d / convolve / hamming as in the scripts' imports."""
+    from scipy.interpolate import interp1d
+    from scipy.signal import convolve
+    from scipy.signal.windows import hamming
+    out = {}
+    for key, fname in (("satellite", "sar_satellite_sim.py"), ("vehicle", "sar_vehicle_sim.py"),
+                       ("moving", "sar_satellite_moving_sim.py")):
+        ns = {"np": np, "interp1d": interp1d, "convolve": convolve, "hamming": hamming}
+        out[key] = _quiet(_extract(fname, ("sar_focus_rda",), ns)["sar_focus_rda"])
+    return out

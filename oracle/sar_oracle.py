@@ -198,3 +198,88 @@ def threshold_margin(slc1, thresh_frac=0.05):
     mag = np.abs(np.asarray(slc1)).ravel()
     thr = mag.max() * thresh_frac
     return float(np.min(np.abs(mag - thr)) / thr)
+
+
+# ---------------------------------------------------------------------------- RDA
+def hamming_sym(m: int) -> np.ndarray:
+    """scipy.signal.windows.hamming(m) (symmetric): 0.54 - 0.46 cos(2 pi n / (m - 1))."""
+    if m == 1:
+        return np.ones(1)
+    return 0.54 - 0.46 * np.cos(2.0 * np.pi * np.arange(m) / (m - 1))
+
+
+def rda_axes(num_ranges, num_pulses, fs, prf, range_grp_m):
+    """Axes of ``sar_focus_rda`` (sar_satellite_sim.py:363-375, :400-406): slow time and fast time centred
+    on sample n/2 (even) or (n-1)/2 (odd), Doppler axis k PRF / P in fftshift order, range = c t / 2."""
+    c = 299792458
+    if num_pulses % 2 == 0:
+        slow = (np.arange(num_pulses) - num_pulses / 2) / prf
+        dop = np.arange(-num_pulses / 2, num_pulses / 2) * (prf / num_pulses)
+    else:
+        slow = (np.arange(num_pulses) - (num_pulses - 1) / 2) / prf
+        dop = np.arange(-(num_pulses - 1) / 2, (num_pulses - 1) / 2 + 1) * (prf / num_pulses)
+    t_grp = 2 * range_grp_m / c
+    if num_ranges % 2 == 0:
+        fast = (np.arange(num_ranges) - num_ranges / 2) / fs + t_grp
+    else:
+        fast = (np.arange(num_ranges) - (num_ranges - 1) / 2) / fs + t_grp
+    return slow, fast, dop, fast * c / 2
+
+
+def rda_matched_filter(t_p, kr, fs):
+    """Hamming-weighted, unit-norm matched filter (sar_satellite_sim.py:379-386):
+    L = floor(T_p / (1/fs)) + 1 taps on linspace(-T_p/2, T_p/2, L)."""
+    step = 1 / fs
+    n_mf = int(np.floor(t_p / step)) + 1
+    t = np.linspace(-t_p / 2, t_p / 2, n_mf)
+    mf = np.conj(np.exp(1j * np.pi * kr * t ** 2)) * hamming_sym(n_mf)
+    return mf / np.linalg.norm(mf)
+
+
+def convolve_same(x, h):
+    """scipy.signal.convolve(x, h, mode='same') along axis 0 of x ([N, P]): the N samples of the full linear
+    convolution starting at (len(h) - 1) // 2, here through zero-padded FFTs (exact to fp64 rounding)."""
+    n, l = x.shape[0], len(h)
+    m = 1
+    while m < n + l - 1:
+        m *= 2
+    y = np.fft.ifft(np.fft.fft(x, m, axis=0) * np.fft.fft(h, m)[:, None], axis=0)
+    s = (l - 1) // 2
+    return y[s:s + n]
+
+
+def interp_linear_zero(x, y, xn):
+    """scipy.interpolate.interp1d(x, y, kind='linear', fill_value=0, bounds_error=False)(xn) for increasing x:
+    neighbours from searchsorted (left), clipped to [1, n-1]; zero outside [x[0], x[-1]]."""
+    idx = np.clip(np.searchsorted(x, xn), 1, len(x) - 1)
+    lo, hi = idx - 1, idx
+    slope = (y[hi] - y[lo]) / (x[hi] - x[lo])
+    out = slope * (xn - x[lo]) + y[lo]
+    out[(xn < x[0]) | (xn > x[-1])] = 0
+    return out
+
+
+def focus_rda(phist, lam, t_p, kr, fs, prf, vr, range_grp_m):
+    """Range-Doppler focusing, ``sar_focus_rda`` (sar_satellite_sim.py:356-448; the copies at
+    sar_vehicle_sim.py:182-274 and sar_satellite_moving_sim.py:208-285 differ only in what they return).
+    phist is [num_ranges, num_pulses].  matched-filter range compression (:377-392) -> azimuth Hamming, shifted
+    FFT (:396-398) -> RCMC: per Doppler column, linear interpolation from the axis r (1 - fd^2 lam^2 / 8 Vr^2)
+    back onto r, zero outside (:408-427) -> x exp(-j pi fd^2 / Ka), Ka = 2 Vr^2 / (lam r) (:431-435) -> shifted
+    azimuth IFFT (:438).  Returns a dict of every array any of the three variants returns."""
+    phist = np.asarray(phist)
+    num_ranges, num_pulses = phist.shape
+    slow, fast, dop, rax = rda_axes(num_ranges, num_pulses, fs, prf, range_grp_m)
+    rc = convolve_same(phist.astype(complex), rda_matched_filter(t_p, kr, fs))
+    rd = np.fft.fftshift(np.fft.fft(np.fft.fftshift(rc * hamming_sym(num_pulses), axes=1), axis=1), axes=1)
+    c = 299792458
+    lambd = c / (c / lam)
+    rcmc = np.zeros_like(rd)
+    for k in range(num_pulses):
+        d_r = rax * (dop[k] ** 2) * lambd ** 2 / (8 * vr ** 2)
+        rcmc[:, k] = interp_linear_zero(rax - d_r, rd[:, k], rax) if num_ranges > 1 else rd[:, k]
+    inv_ka = 1.0 / ((2 * vr ** 2) / (lambd * rax))
+    filt = rcmc * np.exp(-1j * np.pi * (inv_ka[:, None] * dop[None, :] ** 2))
+    img = np.fft.ifftshift(np.fft.ifft(np.fft.ifftshift(filt, axes=1), axis=1), axes=1)
+    return {"image_mag_T": np.abs(img).T, "range_axis_centered": rax - np.mean(rax), "cross_range": vr * slow,
+            "phist_compressed": rc, "range_doppler": rd, "range_doppler_rcmc": rcmc, "range_doppler_filtered": filt,
+            "doppler_freq": dop}

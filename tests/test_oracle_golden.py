@@ -154,3 +154,24 @@ def test_gmti_definitions_small():
     s1b = np.array([[2.0 + 0j, 1.0 + 0j, 0.5 + 0j]])
     pb = orc.gmti_products(s1b, s1b, thresh_frac=0.5)
     assert list(pb["det_idx"]) == [0]
+
+
+# ------------------------------------------------------------------------------------------ RDA (N1)
+@pytest.mark.parametrize("tag", ["p2", "smooth", "odd"])
+def test_rda_matches_reference(tag):
+    """oracle.focus_rda against sar_focus_rda of the three simulators run in the build container
+    (oracle/make_golden.py:golden_rda): image magnitude, axes, and the intermediates the viewers read."""
+    g = np.load(os.path.join(GOLDEN, "rda_random.npz"))
+    o = orc.focus_rda(g[f"{tag}_in"].astype(np.complex128), float(g["lam"]), float(g["t_p"]), float(g["kr"]),
+                      float(g["fs"]), float(g["prf"]), float(g["vr"]), float(g["r0"]))
+    rel = lambda a, b: np.linalg.norm(a - b) / np.linalg.norm(b)
+    assert o["image_mag_T"].shape == g[f"{tag}_img"].shape
+    assert rel(o["image_mag_T"], g[f"{tag}_img"]) < 1e-12
+    assert np.array_equal(o["range_axis_centered"], g[f"{tag}_rax"])
+    assert np.array_equal(o["cross_range"], g[f"{tag}_cax"])
+    assert np.array_equal(o["doppler_freq"], g[f"{tag}_dop"])
+    sl = (slice(None), slice(None)) if tag == "odd" else (slice(None, None, 3), slice(None, None, 2))
+    for key, name in (("phist_compressed", "rc"), ("range_doppler", "rd"), ("range_doppler_rcmc", "rcmc"),
+                      ("range_doppler_filtered", "filt")):
+        assert rel(o[key][sl], g[f"{tag}_{name}"]) < 1e-6          # stored as complex64
+        assert np.array_equal(o[key][sl] == 0, g[f"{tag}_{name}"] == 0)   # same zero fill outside the shifted axis
