@@ -44,6 +44,7 @@ enum {
 
 typedef struct nis_ctx nis_ctx;
 typedef struct nis_csa_plan nis_csa_plan;
+typedef struct nis_rda_plan nis_rda_plan;
 typedef struct { float re, im; } nis_c32;
 typedef void* nis_stream; /* cudaStream_t */
 
@@ -133,6 +134,37 @@ NIS_API int nis_csa_focus(nis_csa_plan* plan, const nis_c32* phist, int64_t pitc
  * recent, ring of 64) and returns the five durations in milliseconds (host buffer). */
 NIS_API int nis_csa_plan_set_profiling(nis_csa_plan* plan, int32_t enable);
 NIS_API int nis_csa_stage_times(nis_csa_plan* plan, int32_t calls_back, float* ms5);
+
+/* ------------------------------------------------------------------ K2b: Range-Doppler focusing
+ * Replaces sar_focus_rda (sar_satellite_sim.py:356-448, sar_vehicle_sim.py:182-274,
+ * sar_satellite_moving_sim.py:208-285): Hamming-weighted matched-filter range compression (the 'same' window of the
+ * linear convolution), Hamming-weighted azimuth DFT, per-Doppler linear-interpolation RCMC with zero fill, range-dependent
+ * azimuth compression, inverse azimuth DFT, magnitude.  All arrays are PULSE-MAJOR [n_pulses][n_ranges] -- the layout of
+ * the echo engines and of the `.T` the reference returns; its [num_ranges, num_pulses] arrays are the transposed views.
+ */
+typedef struct {
+    double c;          /* 299792458 in the reference (:359) */
+    double lambda;     /* center_wavelength_m */
+    double t_p;        /* pulse_width_sec */
+    double kr;         /* chirp_rate_hzpsec */
+    double fs;         /* sample_rate_hz */
+    double prf;        /* prf_hz */
+    double vr;         /* platform_speed_mps */
+    double range_grp;  /* range_grp_m */
+} nis_rda_params;
+
+/* 1 if an (n_pulses, n_ranges) frame with this matched-filter length can be focused */
+NIS_API int nis_rda_supported(int32_t n_pulses, int32_t n_ranges, const nis_rda_params* prm);
+NIS_API int nis_rda_plan_create(nis_ctx* ctx, int32_t n_pulses, int32_t n_ranges, const nis_rda_params* prm,
+                        nis_rda_plan** out);
+NIS_API int nis_rda_plan_destroy(nis_rda_plan* plan);
+/* host buffers: range_axis_centered[n_ranges] (:443-444), cross_range[n_pulses] (:441), doppler_freq[n_pulses] (:400-404) */
+NIS_API int nis_rda_axes(const nis_rda_plan* plan, double* range_axis_centered, double* cross_range, double* doppler_freq);
+/* phist: dev [n_pulses][pitch] complex64.  image_mag: dev [n_pulses][n_ranges] float (= the reference's
+ * sar_image_mag.T).  Optional exports, each dev [n_pulses][n_ranges] complex64 or NULL: rc = phist_compressed.T,
+ * rd = range_doppler.T, rcmc = range_doppler_rcmc.T, filt = range_doppler_filtered.T (Doppler rows in fftshift order). */
+NIS_API int nis_rda_focus(nis_rda_plan* plan, const nis_c32* phist, int64_t pitch, float* image_mag, nis_c32* rc,
+                  nis_c32* rd, nis_c32* rcmc, nis_c32* filt, nis_stream stream);
 
 /* ------------------------------------------------------------------ K3: DPCA + ATI + detection
  * Replaces the inline numpy passes sar_ati_dcpa_sim_csa.py:414-419, :447-449 and

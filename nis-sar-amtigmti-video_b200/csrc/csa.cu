@@ -105,6 +105,32 @@ __global__ void __launch_bounds__(256) k_az_outer_inv(const float2* __restrict__
     if (max_sq != nullptr) atomic_max_f64(max_sq, warp_max_f64(m));
 }
 
+
+// Inverse radix-A1 stage WITHOUT the corner turn, magnitude out (RDA image, sar_satellite_sim.py:438-439):
+// mag[a1*A2 + a2][n] = scale * | sum_k1 w_N^-(k1 a2) Z[k1*A2 + a2][n] w_A1^-(k1 a1) |
+template <int A1>
+__global__ void __launch_bounds__(256) k_az_outer_inv_mag(const float2* __restrict__ in, int64_t pitch,
+                                                          float* __restrict__ mag, int64_t mag_pitch, int n_rg, int A2,
+                                                          int n_az, float scale, const float2* __restrict__ twN) {
+    const int n = blockIdx.x * 32 + (threadIdx.x & 31);
+    const int a2 = blockIdx.y * 8 + (threadIdx.x >> 5);
+    if (n >= n_rg || a2 >= A2) return;
+    float2 v[A1];
+#pragma unroll
+    for (int k1 = 0; k1 < A1; ++k1) {
+        float2 x = in[(int64_t)(k1 * A2 + a2) * pitch + n];
+        if (k1 > 0) x = cmul_conj_pk(x, __ldg(twN + ((k1 * a2) & (n_az - 1))));
+        v[k1] = x;
+    }
+    fft_dif<A1, true, 1, true>(v);
+    constexpr int L = ilog2(A1);
+#pragma unroll
+    for (int a1 = 0; a1 < A1; ++a1) {
+        const float2 x = v[brev(a1, L)];
+        mag[(int64_t)(a1 * A2 + a2) * mag_pitch + n] = scale * sqrtf(fmaf(x.x, x.x, x.y * x.y));
+    }
+}
+
 // ------------------------------------------------------------------------------ azimuth, inner
 // A2-point transforms down W adjacent columns of the row block [k1*A2, (k1+1)*A2); lanes <-> columns, so every
 // shared-memory access of the transform is a contiguous W*8-byte row piece (bank-conflict free).
@@ -579,6 +605,66 @@ bool az_supported(int n) {
     return false;
 }
 
+
+template <int A1>
+int launch_outer_inv_mag(nis_csa_plan* pl, float* mag, float scale, cudaStream_t st) {
+    dim3 grid((pl->n_rg + 31) / 32, (pl->A2 + 7) / 8);
+    k_az_outer_inv_mag<A1><<<grid, 256, 0, st>>>(pl->work, pl->n_rg, mag, pl->n_rg, pl->n_rg, pl->A2, pl->n_az, scale,
+                                                 pl->tw_full);
+    NIS_LAUNCH_CHECK(pl->ctx);
+    return NIS_OK;
+}
+
+// two-kernel four-step azimuth engine on pl->work: launchers, inner-transform twiddles, TMA tile map
+int setup_az_four_step(nis_csa_plan* pl) {
+    const int n_az = pl->n_az, n_rg = pl->n_rg;
+    int rc;
+#define TRY_RC(x) do { rc = (x); if (rc != NIS_OK) return rc; } while (0)
+    switch (pl->A1) {
+        case 4: pl->outer_fwd = launch_outer_fwd<4>; pl->outer_inv = launch_outer_inv<4, 16, 16>;
+                pl->outer_inv_mag = launch_outer_inv_mag<4>; break;
+        case 8: pl->outer_fwd = launch_outer_fwd<8>; pl->outer_inv = launch_outer_inv<8, 16, 16>;
+                pl->outer_inv_mag = launch_outer_inv_mag<8>; break;
+        default: pl->outer_fwd = launch_outer_fwd<16>; pl->outer_inv = launch_outer_inv<16, 16, 16>;
+                 pl->outer_inv_mag = launch_outer_inv_mag<16>;
+                 if (const char* v = getenv("NIS_OUTER_INV")) {   // tuning knob (development only)
+                     if (pl->A2 >= 32 && n_rg >= 32) {
+                         if (v[0] == '1') pl->outer_inv = launch_outer_inv<16, 32, 8>;
+                         if (v[0] == '2') pl->outer_inv = launch_outer_inv<16, 32, 16>;
+                         if (v[0] == '3') pl->outer_inv = launch_outer_inv<16, 16, 32>;
+                         if (v[0] == '4') pl->outer_inv = launch_outer_inv<16, 8, 32>;
+                     }
+                 }
+                 break;
+    }
+    switch (pl->A2) {
+        case 16: pl->inner_w = 32; pl->inner = launch_inner<P16, 32>; TRY_RC(upload_twiddles<P16>(&pl->tw_inner)); break;
+        case 64: pl->inner_w = 32; pl->inner = launch_inner<P64, 32>; TRY_RC(upload_twiddles<P64>(&pl->tw_inner)); break;
+        case 256: pl->inner_w = 16; pl->inner = launch_inner<P256, 16>; TRY_RC(upload_twiddles<P256>(&pl->tw_inner)); break;
+        case 512: pl->inner_w = 8; pl->inner = launch_inner<P512, 8>; TRY_RC(upload_twiddles<P512>(&pl->tw_inner)); break;
+        default: pl->inner_w = 8; pl->inner = launch_inner<P1024, 8>; TRY_RC(upload_twiddles<P1024>(&pl->tw_inner)); break;
+    }
+#undef TRY_RC
+    if (n_rg % pl->inner_w) {
+        set_error("azimuth engine: the range length %d must be a multiple of %d", n_rg, pl->inner_w);
+        return NIS_ERR_UNSUPPORTED;
+    }
+    return tma::make_tile_map(&pl->tile_map, pl->work, n_az, n_rg, n_rg, pl->A2 < 256 ? pl->A2 : 256, pl->inner_w);
+}
+
+int upload_full_twiddles(nis_csa_plan* pl) {
+    const int n_az = pl->n_az;
+    std::vector<float2> h(n_az);
+    const double two_pi = 6.283185307179586476925286766559;
+    for (int m = 0; m < n_az; ++m) {
+        double a = -two_pi * (double)m / (double)n_az;
+        h[m] = make_float2((float)cos(a), (float)sin(a));
+    }
+    if (cudaMalloc(&pl->tw_full, n_az * sizeof(float2)) != cudaSuccess) return NIS_ERR_NOMEM;
+    NIS_CUDA_TRY(cudaMemcpy(pl->tw_full, h.data(), n_az * sizeof(float2), cudaMemcpyHostToDevice));
+    return NIS_OK;
+}
+
 }  // namespace
 
 // ---- shared builders (also used by csa_generic.cu)
@@ -632,6 +718,42 @@ std::vector<RowCoef> build_row_coefs(int n_az, int n_rg, const nis_csa_params& p
         h[rho] = r;
     }
     return h;
+}
+
+}  // namespace csa
+}  // namespace nis
+
+namespace nis {
+namespace csa {
+
+bool az_engine_supported(int n_az, int n_rg) {
+    for (const auto& s : kAzSplits)
+        if (s.n == n_az) {
+            const int w = (s.a2 <= 64) ? 32 : (s.a2 == 256 ? 16 : 8);   // tile width of the inner transform (setup_az_four_step)
+            return n_rg % w == 0;
+        }
+    return false;
+}
+
+// A plan that owns only a workspace and the four-step azimuth engine on it (used by the RDA path, rda.cu)
+int az_engine_create(nis_ctx* ctx, int n_az, int n_rg, nis_csa_plan** out) {
+    nis_csa_plan* pl = new nis_csa_plan();
+    pl->ctx = ctx;
+    pl->n_az = n_az;
+    pl->n_rg = n_rg;
+    pl->size_class = 1;
+    for (const auto& s : kAzSplits)
+        if (s.n == n_az) { pl->A1 = s.a1; pl->A2 = s.a2; }
+    int rc = NIS_OK;
+    if (cudaMalloc(&pl->work, (size_t)n_az * n_rg * sizeof(float2)) != cudaSuccess) {
+        set_error("az_engine_create: cannot allocate %zu-byte workspace", (size_t)n_az * n_rg * sizeof(float2));
+        rc = NIS_ERR_NOMEM;
+    }
+    if (rc == NIS_OK) rc = setup_az_four_step(pl);
+    if (rc == NIS_OK) rc = upload_full_twiddles(pl);
+    if (rc != NIS_OK) { nis_csa_plan_destroy(pl); return rc; }
+    *out = pl;
+    return NIS_OK;
 }
 
 }  // namespace csa
@@ -708,31 +830,7 @@ extern "C" int nis_csa_plan_create(nis_ctx* ctx, int32_t n_az, int32_t n_rg, con
     }
 
     // ---- kernel selection (power-of-two path)
-    if (!pl->az_cluster) {
-    switch (pl->A1) {
-        case 4: pl->outer_fwd = launch_outer_fwd<4>; pl->outer_inv = launch_outer_inv<4, 16, 16>; break;
-        case 8: pl->outer_fwd = launch_outer_fwd<8>;
-                pl->outer_inv = launch_outer_inv<8, 16, 16>; break;
-        default: pl->outer_fwd = launch_outer_fwd<16>;
-                 pl->outer_inv = launch_outer_inv<16, 16, 16>;
-                 if (const char* v = getenv("NIS_OUTER_INV")) {   // tuning knob (development only)
-                     if (pl->A2 >= 32 && n_rg >= 32) {
-                         if (v[0] == '1') pl->outer_inv = launch_outer_inv<16, 32, 8>;
-                         if (v[0] == '2') pl->outer_inv = launch_outer_inv<16, 32, 16>;
-                         if (v[0] == '3') pl->outer_inv = launch_outer_inv<16, 16, 32>;
-                         if (v[0] == '4') pl->outer_inv = launch_outer_inv<16, 8, 32>;
-                     }
-                 }
-                 break;
-    }
-    switch (pl->A2) {
-        case 16: pl->inner_w = 32; pl->inner = launch_inner<P16, 32>; FAIL_IF(upload_twiddles<P16>(&pl->tw_inner)); break;
-        case 64: pl->inner_w = 32; pl->inner = launch_inner<P64, 32>; FAIL_IF(upload_twiddles<P64>(&pl->tw_inner)); break;
-        case 256: pl->inner_w = 16; pl->inner = launch_inner<P256, 16>; FAIL_IF(upload_twiddles<P256>(&pl->tw_inner)); break;
-        case 512: pl->inner_w = 8; pl->inner = launch_inner<P512, 8>; FAIL_IF(upload_twiddles<P512>(&pl->tw_inner)); break;
-        default: pl->inner_w = 8; pl->inner = launch_inner<P1024, 8>; FAIL_IF(upload_twiddles<P1024>(&pl->tw_inner)); break;
-    }
-    }
+    if (!pl->az_cluster) FAIL_IF(setup_az_four_step(pl));
     switch (n_rg) {
         case 64: pl->range = launch_range<P64, 3, 8, 1>; FAIL_IF(upload_twiddles<P64>(&pl->tw_rg)); break;
         case 128: pl->range = launch_range<P128, 0, 8, 1>; FAIL_IF(upload_twiddles<P128>(&pl->tw_rg)); break;
@@ -744,19 +842,7 @@ extern "C" int nis_csa_plan_create(nis_ctx* ctx, int32_t n_az, int32_t n_rg, con
         case 8192: pl->range = launch_range<P8192, 4, 1, 1>; FAIL_IF(upload_twiddles<P8192>(&pl->tw_rg)); break;
         default: pl->range = launch_range<P16384, 4, 1, 1>; FAIL_IF(upload_twiddles<P16384>(&pl->tw_rg)); break;
     }
-    if (!pl->az_cluster)
-        FAIL_IF(tma::make_tile_map(&pl->tile_map, pl->work, n_az, n_rg, n_rg, pl->A2 < 256 ? pl->A2 : 256, pl->inner_w));
-    // ---- full-length azimuth twiddles w_N^m
-    {
-        std::vector<float2> h(n_az);
-        const double two_pi = 6.283185307179586476925286766559;
-        for (int m = 0; m < n_az; ++m) {
-            double a = -two_pi * (double)m / (double)n_az;
-            h[m] = make_float2((float)cos(a), (float)sin(a));
-        }
-        FAIL_IF(cudaMalloc(&pl->tw_full, n_az * sizeof(float2)) == cudaSuccess ? NIS_OK : NIS_ERR_NOMEM);
-        NIS_CUDA_TRY(cudaMemcpy(pl->tw_full, h.data(), n_az * sizeof(float2), cudaMemcpyHostToDevice));
-    }
+    FAIL_IF(upload_full_twiddles(pl));
 #undef FAIL_IF
     *out = pl;
     return NIS_OK;

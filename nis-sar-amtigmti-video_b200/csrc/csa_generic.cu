@@ -410,6 +410,28 @@ struct GenericState {
     GenLen az, rg;
 };
 
+struct RowDft {
+    GenLen g;
+};
+bool rowdft_supported(int n) { return length_supported(n); }
+int rowdft_create(int n, RowDft** out) {
+    RowDft* d = new RowDft();
+    int rc = build_length(n, &d->g);
+    if (rc != NIS_OK) { d->g.release(); delete d; return rc; }
+    *out = d;
+    return NIS_OK;
+}
+void rowdft_destroy(RowDft* d) {
+    if (!d) return;
+    d->g.release();
+    delete d;
+}
+int rowdft_run(nis_ctx* ctx, const RowDft* d, float2* data, int64_t pitch, int n_rows, bool inverse, float scale,
+               cudaStream_t st) {
+    if (inverse) return launch_row<AZ_INV>(ctx, d->g, data, pitch, n_rows, nullptr, scale, nullptr, st);
+    return launch_row<AZ_FWD>(ctx, d->g, data, pitch, n_rows, nullptr, 1.f, nullptr, st);
+}
+
 int generic_supported(int n_az, int n_rg) { return length_supported(n_az) && length_supported(n_rg); }
 
 int generic_create(nis_csa_plan* pl) {

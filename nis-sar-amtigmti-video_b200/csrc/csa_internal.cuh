@@ -44,6 +44,19 @@ std::vector<RowCoef> build_row_coefs(int n_az, int n_rg, const nis_csa_params& p
 void build_axes(int n_az, int n_rg, const nis_csa_params& prm, std::vector<double>& range_axis,
                 std::vector<double>& cross_range);
 
+// four-step azimuth engine as a stand-alone object (csa.cu): workspace + launchers, for other focusing algorithms
+bool az_engine_supported(int n_az, int n_rg);
+int az_engine_create(nis_ctx* ctx, int n_az, int n_rg, nis_csa_plan** out);
+
+// one-length row DFT engine of the general-size path (csa_generic.cu): mixed radix or Bluestein
+struct RowDft;
+bool rowdft_supported(int n);
+int rowdft_create(int n, RowDft** out);
+void rowdft_destroy(RowDft* d);
+// in-place DFT of n_rows rows (pitch elements apart); inverse = conjugate transform times `scale`
+int rowdft_run(nis_ctx* ctx, const RowDft* d, float2* data, int64_t pitch, int n_rows, bool inverse, float scale,
+               cudaStream_t st);
+
 struct GenericState;   // csa_generic.cu
 int generic_supported(int n_az, int n_rg);
 int generic_create(nis_csa_plan* pl);
@@ -81,6 +94,7 @@ struct nis_csa_plan {
     nis_az_outer_inv_fn outer_inv = nullptr;
     nis_az_inner_fn inner = nullptr;
     nis_range_fn range = nullptr;
+    int (*outer_inv_mag)(nis_csa_plan*, float* mag, float scale, cudaStream_t) = nullptr;   // inverse outer stage -> |.|, no corner turn
     // whole-column azimuth transforms by thread-block clusters (one HBM pass each)
     bool az_cluster = false;
     int (*az_fwd)(nis_csa_plan*, const float2*, int64_t, cudaStream_t) = nullptr;

@@ -1,0 +1,441 @@
+// rda.cu -- Range-Doppler focusing (replaces sar_focus_rda: sar_satellite_sim.py:356-448, sar_vehicle_sim.py:182-274,
+// sar_satellite_moving_sim.py:208-285).
+//
+// Everything stays in the pulse-major layout raw[P][S] of the echo engines (the reference's `phist` is the .T view of it,
+// sar_satellite_sim.py:453-454), and the image |.|.T the reference returns is again [P][S], so no corner turn is needed:
+//   k_rda_range     per pulse: zero-padded FFT_M -> x FFT_M(matched filter)/M -> IFFT_M -> the N samples of the linear
+//                   convolution that scipy's convolve(mode='same') keeps (:388-392); writes the compressed pulse
+//                   (optional export) and, times the azimuth Hamming weight of the pulse (:396-397), the workspace
+//   azimuth DFT     four-step engine of csa.cu (power-of-two P) or transpose + row-DFT engine (any other P)
+//   k_rda_rcmc      per Doppler bin: range-cell-migration correction = linear interpolation from the axis
+//                   r (1 - fd^2 lam^2 / 8 Vr^2) back onto r, zero outside it (:408-427), then x exp(-j pi fd^2 / Ka(r))
+//                   (:431-435); optional exports of the three Range-Doppler maps the viewers read
+//   inverse DFT     -> |.| / P  (:438-439)
+// The fftshift / ifftshift pairs around both transforms (:398, :438) cancel for the image (any P, even or odd): the
+// image is IFFT_k( G[r, fd(k)] . FFT_n(w . rc) ) in natural order.  Only the exported Range-Doppler maps carry them:
+// row j = (k + floor(P/2)) mod P and the factor exp(-2 pi i floor(P/2) k / P) ((-1)^k for even P).
+#include <math.h>
+#include <string.h>
+
+#include <complex>
+#include <vector>
+
+#include "csa_internal.cuh"
+#include "fft.cuh"
+
+using namespace nis;
+using namespace nis::fft;
+using namespace nis::csa;
+
+namespace {
+
+struct RdaRow {          // one per stored Doppler row
+    double beta;         // alpha / (1 - alpha), alpha = fd^2 lam^2 / (8 Vr^2): source position p = i + (i + q0) beta
+    uint64_t ph_a, ph_b; // azimuth-compression phase in fixed-point turns: ph_b + ph_a * i
+    float2 factor;       // exported maps: stored value times this
+    int32_t export_row;  // exported maps: row in fftshift order
+    int32_t pad;
+};
+static_assert(sizeof(RdaRow) == 40, "RdaRow layout");
+
+// ------------------------------------------------------------------------------ range compression
+template <class P, int PAD>
+__global__ void __launch_bounds__(P::NT) k_rda_range(const float2* __restrict__ in, int64_t in_pitch,
+                                                     float2* __restrict__ work, int64_t work_pitch,
+                                                     float2* __restrict__ rc_out, int n_rows, int N, int s0,
+                                                     const float2* __restrict__ Hf, const float* __restrict__ win,
+                                                     const float2* __restrict__ tw) {
+    extern __shared__ float2 sm[];
+    constexpr int E = P::E, NT = P::NT;
+    const int t = threadIdx.x;
+    for (int row = blockIdx.x; row < n_rows; row += gridDim.x) {
+        const float2* p = in + (int64_t)row * in_pitch;
+        float2 v[E];
+#pragma unroll
+        for (int s = 0; s < E; ++s) {
+            const int idx = t + NT * s;
+            v[s] = idx < N ? p[idx] : make_float2(0.f, 0.f);
+        }
+        transform<P, false, 1, PAD>(v, t, sm, tw);
+#pragma unroll
+        for (int s = 0; s < E; ++s) v[s] = cmul_pk(v[s], __ldg(Hf + t + NT * s));
+        __syncthreads();
+        transform<P, true, 1, PAD>(v, t, sm, tw);
+        const float w = win[row];
+#pragma unroll
+        for (int s = 0; s < E; ++s) {
+            const int o = t + NT * s - s0;
+            if (o >= 0 && o < N) {
+                if (rc_out != nullptr) rc_out[(int64_t)row * N + o] = v[s];
+                work[(int64_t)row * work_pitch + o] = make_float2(v[s].x * w, v[s].y * w);
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// ------------------------------------------------------------------------------ RCMC + azimuth compression
+__global__ void __launch_bounds__(256) k_rda_rcmc(float2* __restrict__ work, int64_t pitch, int n_rows, int N, double q0,
+                                                  const RdaRow* __restrict__ rows, float2* __restrict__ rd_out,
+                                                  float2* __restrict__ rcmc_out, float2* __restrict__ filt_out) {
+    extern __shared__ float2 line[];
+    for (int row = blockIdx.x; row < n_rows; row += gridDim.x) {
+        float2* p = work + (int64_t)row * pitch;
+        const RdaRow rr = rows[row];
+        for (int i = threadIdx.x; i < N; i += blockDim.x) line[i] = p[i];
+        __syncthreads();
+        const int64_t eo = (int64_t)rr.export_row * N;
+        for (int i = threadIdx.x; i < N; i += blockDim.x) {
+            const double pos = fma((double)i + q0, rr.beta, (double)i);   // where sample i comes from on the shifted axis
+            float2 o = make_float2(0.f, 0.f);
+            if (pos >= 0.0 && pos <= (double)(N - 1)) {
+                int lo = (int)pos;
+                if (lo > N - 2) lo = N - 2;
+                const float f = (float)(pos - (double)lo);
+                const float2 y0 = line[lo], y1 = line[lo + 1];
+                o = make_float2(fmaf(f, y1.x - y0.x, y0.x), fmaf(f, y1.y - y0.y, y0.y));
+            }
+            const float2 h = cis_u64(rr.ph_b + rr.ph_a * (uint64_t)i);
+            const float2 g = cmul(o, h);
+            if (rd_out != nullptr) rd_out[eo + i] = cmul(line[i], rr.factor);
+            if (rcmc_out != nullptr) rcmc_out[eo + i] = cmul(o, rr.factor);
+            if (filt_out != nullptr) filt_out[eo + i] = cmul(g, rr.factor);
+            p[i] = g;
+        }
+        __syncthreads();
+    }
+}
+
+// mag[c][r] = scale * |in[r][c]|  (in: rows x cols)
+__global__ void __launch_bounds__(256) k_transpose_mag(const float2* __restrict__ in, int rows, int cols,
+                                                       float* __restrict__ mag, float scale) {
+    __shared__ float tile[32][33];
+    const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    for (int k = ty; k < 32; k += 8) {
+        const int r = r0 + k, c = c0 + tx;
+        if (r < rows && c < cols) {
+            const float2 x = in[(int64_t)r * cols + c];
+            tile[k][tx] = scale * sqrtf(fmaf(x.x, x.x, x.y * x.y));
+        }
+    }
+    __syncthreads();
+    for (int k = ty; k < 32; k += 8) {
+        const int c = c0 + k, r = r0 + tx;
+        if (r < rows && c < cols) mag[(int64_t)c * rows + r] = tile[tx][k];
+    }
+}
+
+// ------------------------------------------------------------------------------ host
+using P256 = Plan<256, 16, 16, 16, 1>;
+using P1024 = Plan<1024, 16, 16, 8, 8>;
+using P2048 = Plan<2048, 16, 16, 16, 8>;
+using P4096 = Plan<4096, 16, 16, 16, 16>;
+using P8192 = Plan<8192, 16, 16, 8, 8, 8>;
+using P16384 = Plan<16384, 32, 32, 32, 16>;
+
+void host_fft_pow2(std::vector<std::complex<double>>& a) {   // in-place radix-2, forward
+    const size_t n = a.size();
+    for (size_t i = 1, j = 0; i < n; ++i) {
+        size_t bit = n >> 1;
+        for (; j & bit; bit >>= 1) j ^= bit;
+        j ^= bit;
+        if (i < j) std::swap(a[i], a[j]);
+    }
+    const double two_pi = 6.283185307179586476925286766559;
+    for (size_t len = 2; len <= n; len <<= 1)
+        for (size_t i = 0; i < n; i += len)
+            for (size_t k = 0; k < len / 2; ++k) {
+                const double ang = -two_pi * (double)k / (double)len;
+                const std::complex<double> w(cos(ang), sin(ang));
+                const std::complex<double> u = a[i + k], v = a[i + k + len / 2] * w;
+                a[i + k] = u + v;
+                a[i + k + len / 2] = u - v;
+            }
+}
+
+// scipy.signal.windows.hamming(m) (symmetric)
+std::vector<double> hamming_sym(int m) {
+    std::vector<double> w(m, 1.0);
+    const double two_pi = 6.283185307179586476925286766559;
+    if (m > 1)
+        for (int n = 0; n < m; ++n) w[n] = 0.54 - 0.46 * cos(two_pi * (double)n / (double)(m - 1));
+    return w;
+}
+
+// number of matched-filter taps, with the reference's own fp64 expression (:380-381)
+int mf_taps(const nis_rda_params& prm) {
+    const double step = 1.0 / prm.fs;
+    return (int)floor(prm.t_p / step) + 1;
+}
+
+int conv_fft_len(int n, int taps) {   // smallest supported M that keeps the 'same' window free of wrap-around
+    const int need = n + taps - 1 - (taps - 1) / 2;
+    const int ms[] = {256, 1024, 2048, 4096, 8192, 16384};
+    for (int m : ms)
+        if (m >= need && m >= taps) return m;
+    return 0;
+}
+
+}  // namespace
+
+struct nis_rda_plan {
+    nis_ctx* ctx = nullptr;
+    int P = 0, S = 0, taps = 0, M = 0, s0 = 0;
+    nis_rda_params prm{};
+    nis_csa_plan* az = nullptr;       // four-step azimuth engine + workspace [P][S] (power-of-two P)
+    RowDft* dft = nullptr;            // row-DFT engine (other P): needs the transposed buffer
+    float2 *work = nullptr, *tbuf = nullptr, *Hf = nullptr, *tw = nullptr;
+    float* win = nullptr;
+    RdaRow* rows = nullptr;
+    double q0 = 0;
+    std::vector<double> range_axis_centered, cross_range, doppler;
+    int (*range_fn)(nis_rda_plan*, const float2*, int64_t, float2*, cudaStream_t) = nullptr;
+};
+
+namespace {
+
+template <class P, int PAD>
+int launch_rda_range(nis_rda_plan* pl, const float2* in, int64_t pitch, float2* rc_out, cudaStream_t st) {
+    constexpr int SMROW = P::N + (PAD ? (P::N >> PAD) : 0);
+    const size_t smem = (size_t)SMROW * sizeof(float2);
+    static bool attr_done = false;
+    if (!attr_done) {
+        NIS_CUDA_TRY(cudaFuncSetAttribute(k_rda_range<P, PAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_done = true;
+    }
+    int per_sm = 1;
+    NIS_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_rda_range<P, PAD>, P::NT, smem));
+    int grid = pl->ctx->num_sms * (per_sm < 1 ? 1 : per_sm);
+    if (grid > pl->P) grid = pl->P;
+    k_rda_range<P, PAD><<<grid, P::NT, smem, st>>>(in, pitch, pl->work, pl->S, rc_out, pl->P, pl->S, pl->s0, pl->Hf,
+                                                    pl->win, pl->tw);
+    NIS_LAUNCH_CHECK(pl->ctx);
+    return NIS_OK;
+}
+
+template <class P>
+int upload_tw(float2** dev) {
+    std::vector<float2> h(P::tw_len + 1);
+    build_twiddles<P>(h.data());
+    NIS_CUDA_TRY(cudaMalloc(dev, h.size() * sizeof(float2)));
+    NIS_CUDA_TRY(cudaMemcpy(*dev, h.data(), h.size() * sizeof(float2), cudaMemcpyHostToDevice));
+    return NIS_OK;
+}
+
+bool rda_sizes_ok(int P, int S, const nis_rda_params& prm, int* M_out) {
+    if (P < 2 || S < 2 || S > 24576) return false;
+    const int taps = mf_taps(prm);
+    const int M = conv_fft_len(S, taps);
+    if (taps < 1 || M == 0) return false;
+    if (M_out) *M_out = M;
+    return (az_engine_supported(P, S)) || (rowdft_supported(P));
+}
+
+}  // namespace
+
+extern "C" int nis_rda_supported(int32_t n_pulses, int32_t n_ranges, const nis_rda_params* prm) {
+    if (!prm || !(prm->fs > 0) || !(prm->t_p > 0)) return 0;
+    return rda_sizes_ok(n_pulses, n_ranges, *prm, nullptr) ? 1 : 0;
+}
+
+extern "C" int nis_rda_plan_destroy(nis_rda_plan* pl) {
+    if (!pl) return NIS_OK;
+    if (pl->az) {
+        if (pl->work == pl->az->work) pl->work = nullptr;
+        nis_csa_plan_destroy(pl->az);
+    }
+    rowdft_destroy(pl->dft);
+    cudaFree(pl->work);
+    cudaFree(pl->tbuf);
+    cudaFree(pl->Hf);
+    cudaFree(pl->tw);
+    cudaFree(pl->win);
+    cudaFree(pl->rows);
+    delete pl;
+    return NIS_OK;
+}
+
+extern "C" int nis_rda_plan_create(nis_ctx* ctx, int32_t P, int32_t S, const nis_rda_params* prm, nis_rda_plan** out) {
+    NIS_REQUIRE(ctx && prm && out, "nis_rda_plan_create: null argument");
+    NIS_REQUIRE(prm->fs > 0 && prm->prf > 0 && prm->vr > 0 && prm->lambda > 0 && prm->c > 0 && prm->t_p > 0,
+                "nis_rda_plan_create: non-physical parameters");
+    int M = 0;
+    if (!rda_sizes_ok(P, S, *prm, &M)) {
+        set_error("nis_rda_plan_create: %d pulses x %d samples with a %d-tap matched filter is not supported (samples + "
+                  "taps/2 <= 16384; pulses: power of two 64..16384 with samples %% 32 == 0, or any length the row-DFT "
+                  "engine takes)", P, S, mf_taps(*prm));
+        return NIS_ERR_UNSUPPORTED;
+    }
+    NIS_CUDA_TRY(cudaSetDevice(ctx->device));
+    nis_rda_plan* pl = new nis_rda_plan();
+    pl->ctx = ctx;
+    pl->P = P;
+    pl->S = S;
+    pl->prm = *prm;
+    pl->taps = mf_taps(*prm);
+    pl->M = M;
+    pl->s0 = (pl->taps - 1) / 2;
+    int rc = NIS_OK;
+#define FAIL_IF(x) do { rc = (x); if (rc != NIS_OK) { nis_rda_plan_destroy(pl); return rc; } } while (0)
+#define CUDA_FAIL_IF(x) FAIL_IF((x) == cudaSuccess ? NIS_OK : (set_error("%s failed", #x), NIS_ERR_CUDA))
+    const double c = prm->c, lam = prm->lambda, vr = prm->vr;
+    const int h_az = P / 2;   // fftshift offset along pulses (n // 2 for even and odd n)
+
+    // ---- axes (:363-375, :400-406, :441-443)
+    pl->cross_range.resize(P);
+    pl->doppler.resize(P);
+    for (int i = 0; i < P; ++i) {
+        const double centre = (P % 2 == 0) ? (double)P / 2 : (double)(P - 1) / 2;
+        pl->cross_range[i] = vr * (((double)i - centre) / prm->prf);
+        pl->doppler[i] = ((double)i - centre) * (prm->prf / (double)P);
+    }
+    const double t_grp = 2 * prm->range_grp / c;
+    const double centre_r = (S % 2 == 0) ? (double)S / 2 : (double)(S - 1) / 2;
+    std::vector<double> rax(S);
+    long double acc = 0;
+    for (int i = 0; i < S; ++i) {
+        rax[i] = (((double)i - centre_r) / prm->fs + t_grp) * c / 2;
+        acc += rax[i];
+    }
+    const double mean = (double)(acc / S);
+    pl->range_axis_centered.resize(S);
+    for (int i = 0; i < S; ++i) pl->range_axis_centered[i] = rax[i] - mean;
+    pl->q0 = (double)((long double)t_grp * (long double)prm->fs - (long double)centre_r);
+
+    // ---- matched filter (:379-386) -> FFT_M / M
+    {
+        const int L = pl->taps;
+        std::vector<std::complex<double>> hpad(M, 0.0);
+        const std::vector<double> wh = hamming_sym(L);
+        const double start = -prm->t_p / 2, stop = prm->t_p / 2;
+        const double step = (L > 1) ? (stop - start) / (double)(L - 1) : 0.0;
+        double norm = 0;
+        for (int i = 0; i < L; ++i) {
+            double t = (double)i * step + start;    // numpy.linspace
+            if (i == L - 1 && L > 1) t = stop;
+            const double ph = M_PI * prm->kr * (t * t);
+            hpad[i] = std::conj(std::complex<double>(cos(ph), sin(ph))) * wh[i];
+            norm += std::norm(hpad[i]);
+        }
+        norm = sqrt(norm);
+        for (int i = 0; i < L; ++i) hpad[i] /= norm;
+        host_fft_pow2(hpad);
+        std::vector<float2> hf(M);
+        for (int i = 0; i < M; ++i) hf[i] = make_float2((float)(hpad[i].real() / M), (float)(hpad[i].imag() / M));
+        CUDA_FAIL_IF(cudaMalloc(&pl->Hf, M * sizeof(float2)));
+        CUDA_FAIL_IF(cudaMemcpy(pl->Hf, hf.data(), M * sizeof(float2), cudaMemcpyHostToDevice));
+    }
+    switch (M) {
+        case 256: pl->range_fn = launch_rda_range<P256, 4>; FAIL_IF(upload_tw<P256>(&pl->tw)); break;
+        case 1024: pl->range_fn = launch_rda_range<P1024, 4>; FAIL_IF(upload_tw<P1024>(&pl->tw)); break;
+        case 2048: pl->range_fn = launch_rda_range<P2048, 4>; FAIL_IF(upload_tw<P2048>(&pl->tw)); break;
+        case 4096: pl->range_fn = launch_rda_range<P4096, 4>; FAIL_IF(upload_tw<P4096>(&pl->tw)); break;
+        case 8192: pl->range_fn = launch_rda_range<P8192, 4>; FAIL_IF(upload_tw<P8192>(&pl->tw)); break;
+        default: pl->range_fn = launch_rda_range<P16384, 5>; FAIL_IF(upload_tw<P16384>(&pl->tw)); break;
+    }
+    // ---- azimuth Hamming weights (:396)
+    {
+        const std::vector<double> wa = hamming_sym(P);
+        std::vector<float> wf(P);
+        for (int i = 0; i < P; ++i) wf[i] = (float)wa[i];
+        CUDA_FAIL_IF(cudaMalloc(&pl->win, P * sizeof(float)));
+        CUDA_FAIL_IF(cudaMemcpy(pl->win, wf.data(), P * sizeof(float), cudaMemcpyHostToDevice));
+    }
+    // ---- azimuth engine
+    int A1 = 1, A2 = P;
+    if (az_engine_supported(P, S)) {
+        FAIL_IF(az_engine_create(ctx, P, S, &pl->az));
+        pl->work = pl->az->work;
+        A1 = pl->az->A1;
+        A2 = pl->az->A2;
+    } else {
+        FAIL_IF(rowdft_create(P, &pl->dft));
+        CUDA_FAIL_IF(cudaMalloc(&pl->work, (size_t)P * S * sizeof(float2)));
+        CUDA_FAIL_IF(cudaMalloc(&pl->tbuf, (size_t)P * S * sizeof(float2)));
+    }
+    // ---- per Doppler row: RCMC scale, azimuth-compression phase ramp, export placement (:408-435)
+    {
+        std::vector<RdaRow> h(P);
+        const long double dr = (long double)c / (2.0L * (long double)prm->fs);
+        const double two_pi = 6.283185307179586476925286766559;
+        for (int rho = 0; rho < P; ++rho) {
+            const int k1 = rho / A2, k2 = rho % A2;
+            const int kk = k1 + A1 * k2;                 // FFT bin held by this row
+            const int j = (kk + h_az) % P;               // its row in fftshift order
+            const double fd = pl->doppler[j];
+            const long double alpha = (long double)fd * fd * (long double)lam * lam / (8.0L * (long double)vr * vr);
+            RdaRow r{};
+            r.beta = (double)(alpha / (1.0L - alpha));
+            const long double a = -((long double)fd * fd * (long double)lam / (4.0L * (long double)vr * vr)) * dr;
+            r.ph_a = to_fix(a);
+            r.ph_b = to_fix(a * (long double)pl->q0);
+            const double ang = -two_pi * (double)(((int64_t)h_az * kk) % P) / (double)P;
+            r.factor = make_float2((float)cos(ang), (float)sin(ang));
+            r.export_row = j;
+            h[rho] = r;
+        }
+        CUDA_FAIL_IF(cudaMalloc(&pl->rows, P * sizeof(RdaRow)));
+        CUDA_FAIL_IF(cudaMemcpy(pl->rows, h.data(), P * sizeof(RdaRow), cudaMemcpyHostToDevice));
+    }
+#undef CUDA_FAIL_IF
+#undef FAIL_IF
+    *out = pl;
+    return NIS_OK;
+}
+
+extern "C" int nis_rda_axes(const nis_rda_plan* pl, double* range_axis_centered, double* cross_range, double* doppler) {
+    NIS_REQUIRE(pl, "nis_rda_axes: null plan");
+    if (range_axis_centered) memcpy(range_axis_centered, pl->range_axis_centered.data(), pl->S * sizeof(double));
+    if (cross_range) memcpy(cross_range, pl->cross_range.data(), pl->P * sizeof(double));
+    if (doppler) memcpy(doppler, pl->doppler.data(), pl->P * sizeof(double));
+    return NIS_OK;
+}
+
+extern "C" int nis_rda_focus(nis_rda_plan* pl, const nis_c32* phist, int64_t pitch, float* image_mag, nis_c32* rc_out,
+                             nis_c32* rd_out, nis_c32* rcmc_out, nis_c32* filt_out, nis_stream stream) {
+    NIS_REQUIRE(pl && phist && image_mag, "nis_rda_focus: null argument");
+    NIS_REQUIRE(pitch >= pl->S, "nis_rda_focus: pitch %lld < samples per pulse %d", (long long)pitch, pl->S);
+    cudaStream_t st = (cudaStream_t)stream;
+    nis_ctx* ctx = pl->ctx;
+    const int P = pl->P, S = pl->S;
+    int rc;
+#define RUN(x) do { if ((rc = (x)) != NIS_OK) return rc; } while (0)
+    RUN(pl->range_fn(pl, reinterpret_cast<const float2*>(phist), pitch, reinterpret_cast<float2*>(rc_out), st));
+    if (pl->az) {
+        RUN(pl->az->outer_fwd(pl->az, pl->work, S, 0, S, st));   // in place: a thread reads and writes the same 16 cells
+        RUN(pl->az->inner(pl->az, false, 0, S, 0, pl->az->A1, st));
+    } else {
+        RUN(launch_transpose(ctx, pl->work, S, pl->tbuf, P, S, st));
+        RUN(rowdft_run(ctx, pl->dft, pl->tbuf, P, S, false, 1.f, st));
+        RUN(launch_transpose(ctx, pl->tbuf, P, pl->work, S, P, st));
+    }
+    {
+        static bool attr_done = false;
+        if (!attr_done) {
+            NIS_CUDA_TRY(cudaFuncSetAttribute(k_rda_rcmc, cudaFuncAttributeMaxDynamicSharedMemorySize, 24576 * 8));
+            attr_done = true;
+        }
+        const size_t smem = (size_t)S * sizeof(float2);
+        int per_sm = 1;
+        NIS_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_rda_rcmc, 256, smem));
+        int grid = ctx->num_sms * (per_sm < 1 ? 1 : per_sm);
+        if (grid > P) grid = P;
+        k_rda_rcmc<<<grid, 256, smem, st>>>(pl->work, S, P, S, pl->q0, pl->rows, reinterpret_cast<float2*>(rd_out),
+                                            reinterpret_cast<float2*>(rcmc_out), reinterpret_cast<float2*>(filt_out));
+        NIS_LAUNCH_CHECK(ctx);
+    }
+    const float scale = (float)(1.0 / (double)P);
+    if (pl->az) {
+        RUN(pl->az->inner(pl->az, true, 0, S, 0, pl->az->A1, st));
+        RUN(pl->az->outer_inv_mag(pl->az, image_mag, scale, st));
+    } else {
+        RUN(launch_transpose(ctx, pl->work, S, pl->tbuf, P, S, st));
+        RUN(rowdft_run(ctx, pl->dft, pl->tbuf, P, S, true, 1.f, st));
+        dim3 grid((P + 31) / 32, (S + 31) / 32);
+        k_transpose_mag<<<grid, 256, 0, st>>>(pl->tbuf, S, P, image_mag, scale);
+        NIS_LAUNCH_CHECK(ctx);
+    }
+#undef RUN
+    return NIS_OK;
+}

@@ -31,6 +31,11 @@ class CsaParams(C.Structure):
                 ("prf", C.c_double), ("vr", C.c_double), ("r_ref", C.c_double), ("t_start", C.c_double)]
 
 
+class RdaParams(C.Structure):
+    _fields_ = [("c", C.c_double), ("lambda_", C.c_double), ("t_p", C.c_double), ("kr", C.c_double), ("fs", C.c_double),
+                ("prf", C.c_double), ("vr", C.c_double), ("range_grp", C.c_double)]
+
+
 class GmtiResult(C.Structure):
     _fields_ = [("det_count", C.c_uint32), ("peak_idx", C.c_uint32), ("max_mag_sq", C.c_double)]
 
@@ -52,6 +57,11 @@ SIGNATURES = {
     "nis_csa_focus": (C.c_int, [_P, _P, C.c_int64, _P, _P, _P]),
     "nis_csa_plan_set_profiling": (C.c_int, [_P, C.c_int32]),
     "nis_csa_stage_times": (C.c_int, [_P, C.c_int32, _P]),
+    "nis_rda_supported": (C.c_int, [C.c_int32, C.c_int32, C.POINTER(RdaParams)]),
+    "nis_rda_plan_create": (C.c_int, [_P, C.c_int32, C.c_int32, C.POINTER(RdaParams), C.POINTER(_P)]),
+    "nis_rda_plan_destroy": (C.c_int, [_P]),
+    "nis_rda_axes": (C.c_int, [_P, _P, _P, _P]),
+    "nis_rda_focus": (C.c_int, [_P, _P, C.c_int64, _P, _P, _P, _P, _P, _P]),
     "nis_gmti_fused": (C.c_int, [_P, _P, _P, C.c_uint64, C.c_double, C.c_double,
                                  _P, _P, _P, _P, _P, _P, _P, _P, C.c_uint32, _P, _P, _P]),
     "nis_gmti_balance_sum": (C.c_int, [_P, _P, _P, C.c_uint64, _P, _P]),

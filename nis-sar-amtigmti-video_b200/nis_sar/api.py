@@ -134,6 +134,61 @@ def sar_focus_csa(phist, center_wavelength_m, pulse_width_sec, chirp_rate_hzpsec
     return (slc if return_device else _to_host_c128(slc)), rax, cax
 
 
+# ------------------------------------------------------------------------------------------- RDA
+_RDA_RETURNS = {
+    # which of the three copies of sar_focus_rda the caller is replacing -> what it returns after the image and two axes
+    "satellite": ("phist_compressed", "range_doppler", "range_doppler_rcmc"),                              # sar_satellite_sim.py:447-448
+    "vehicle": ("phist_compressed", "range_doppler", "range_doppler_rcmc", "range_doppler_filtered"),    # sar_vehicle_sim.py:273-274
+    "moving": (),                                                                                          # sar_satellite_moving_sim.py:285
+}
+
+
+def sar_focus_rda(phist, center_wavelength_m, pulse_width_sec, chirp_rate_hzpsec, sample_rate_hz, prf_hz,
+                  platform_speed_mps, range_grp_m, *, returns="satellite", device=None, return_device=False):
+    """Range-Doppler focusing (sar_satellite_sim.py:356-448 and its copies in sar_vehicle_sim.py:182-274,
+    sar_satellite_moving_sim.py:208-285).  ``phist`` is [num_ranges, num_pulses] as in the reference -- normally the
+    ``raw_data.T`` view of the pulse-major echo array, which is consumed without a copy -- or a complex64 CUDA tensor of
+    that shape.  ``returns`` selects which copy's tuple comes back:
+      "satellite": (image_mag_T, range_axis_centered, cross_range, phist_compressed, range_doppler, range_doppler_rcmc,
+                    doppler_freq);  "vehicle": the same plus range_doppler_filtered before doppler_freq;  "moving": the
+      first three.  image_mag_T is float64 [num_pulses, num_ranges]; the complex arrays are complex128
+      [num_ranges, num_pulses] (transposed views of pulse-major buffers: same values, F-contiguous)."""
+    if returns not in _RDA_RETURNS:
+        raise dev.NisError(f"sar_focus_rda: returns must be one of {sorted(_RDA_RETURNS)}")
+    device = device or _default_device
+    if torch.is_tensor(phist):
+        xt = phist.transpose(0, 1)
+        if xt.dtype != torch.complex64:
+            xt = dev.narrow_c128(xt.to(torch.complex128).contiguous())
+        elif xt.stride(1) != 1:
+            xt = xt.contiguous()
+    else:
+        h = np.asarray(phist)
+        if h.ndim != 2:
+            raise dev.NisError("sar_focus_rda: phist must be 2-D [num_ranges, num_pulses]")
+        ht = h.T                                     # pulse-major; C-contiguous when phist is raw_data.T
+        if ht.dtype == np.complex64:
+            xt = torch.from_numpy(np.ascontiguousarray(ht)).to(device)
+        else:
+            xt = dev.narrow_c128(torch.from_numpy(np.ascontiguousarray(ht, dtype=np.complex128)).to(device))
+    n_pulses, n_ranges = xt.shape
+    plan = dev.cached_rda_plan(n_pulses, n_ranges, lam=float(center_wavelength_m), t_p=float(pulse_width_sec),
+                               kr=float(chirp_rate_hzpsec), fs=float(sample_rate_hz), prf=float(prf_hz),
+                               vr=float(platform_speed_mps), range_grp=float(range_grp_m), device=xt.device)
+    want = _RDA_RETURNS[returns]
+    out = plan.focus(xt, want=want)
+    rax, cax, dop = plan.axes()
+    if return_device:
+        img = out["image_mag"]
+        extra = [out[w].transpose(0, 1) for w in want]
+    else:
+        img = out["image_mag"].to(torch.float64).cpu().numpy()
+        extra = [_to_host_c128(out[w]).T for w in want]
+    if returns == "moving":
+        return img, rax, cax
+    return (img, rax, cax, *extra, dop)
+
+
 # ------------------------------------------------------------------------------------------ GMTI
 def gmti_products(slc1, slc2, thresh=0.05, cal_phase=0.0, *, device=None, return_device=False):
     """ATI interferogram, phase, DPCA difference, magnitudes, 5 %-of-peak mask, masked phase and the
@@ -178,7 +233,7 @@ def save_ati_dpca_npz(fname, slc1, slc2, range_axis, cross_range):
 
 # --------------------------------------------------------------------------------------- install
 _ENTRY_POINTS = ("run_bistatic_physics_gpu", "sar_focus_csa", "run_physics_engine", "run_moving_physics",
-                 "run_custom_physics")
+                 "run_custom_physics")   # sar_focus_rda: install(ns, names=("sar_focus_rda",)) with functools.partial(returns=...)
 
 
 def install(namespace: dict, names=_ENTRY_POINTS):

@@ -183,6 +183,87 @@ def cached_plan(n_az, n_rg, **kw) -> CsaPlan:
     return pl
 
 
+# -------------------------------------------------------------------------------------- RDA
+class RdaPlan:
+    """Range-Doppler focusing plan for one (n_pulses, n_ranges) and one parameter set of ``sar_focus_rda``
+    (sar_satellite_sim.py:356): matched-filter spectrum, azimuth weights, per-Doppler RCMC / azimuth-compression
+    coefficients, azimuth engine and workspace.  Arrays are pulse-major [n_pulses, n_ranges]."""
+
+    EXPORTS = ("phist_compressed", "range_doppler", "range_doppler_rcmc", "range_doppler_filtered")
+
+    def __init__(self, n_pulses, n_ranges, *, lam, t_p, kr, fs, prf, vr, range_grp, c=299792458.0, device="cuda"):
+        self.di = _dev_index(device)
+        self.n_pulses, self.n_ranges = int(n_pulses), int(n_ranges)
+        prm = _lib.RdaParams(c=c, lambda_=lam, t_p=t_p, kr=kr, fs=fs, prf=prf, vr=vr, range_grp=range_grp)
+        h = C.c_void_p()
+        with torch.cuda.device(self.di):
+            _lib.check(_lib.load().nis_rda_plan_create(_lib.context(self.di), self.n_pulses, self.n_ranges, C.byref(prm),
+                                                      C.byref(h)), "nis_rda_plan_create")
+        self._h = h
+
+    @staticmethod
+    def supported(n_pulses, n_ranges, *, lam, t_p, kr, fs, prf, vr, range_grp, c=299792458.0) -> bool:
+        prm = _lib.RdaParams(c=c, lambda_=lam, t_p=t_p, kr=kr, fs=fs, prf=prf, vr=vr, range_grp=range_grp)
+        return _lib.load().nis_rda_supported(int(n_pulses), int(n_ranges), C.byref(prm)) != 0
+
+    def axes(self):
+        """(range_axis_centered[n_ranges], cross_range[n_pulses], doppler_freq[n_pulses])"""
+        ra = np.empty(self.n_ranges, dtype=np.float64)
+        ca = np.empty(self.n_pulses, dtype=np.float64)
+        da = np.empty(self.n_pulses, dtype=np.float64)
+        _lib.check(_lib.load().nis_rda_axes(self._h, ra.ctypes.data_as(C.c_void_p), ca.ctypes.data_as(C.c_void_p),
+                                            da.ctypes.data_as(C.c_void_p)), "nis_rda_axes")
+        return ra, ca, da
+
+    def focus(self, phist, want=()):
+        """phist: complex64 CUDA tensor [n_pulses, n_ranges] (unit column stride).  Returns a dict with ``image_mag``
+        (float32 [n_pulses, n_ranges] = the reference's ``sar_image_mag.T``) and the requested exports (complex64,
+        pulse- / Doppler-major, i.e. the transposes of the reference's [num_ranges, num_pulses] arrays)."""
+        if phist.dtype != torch.complex64 or phist.dim() != 2 or phist.stride(1) != 1:
+            raise NisError("RdaPlan.focus: phist must be a complex64 [n_pulses, n_ranges] tensor with unit column stride")
+        if tuple(phist.shape) != (self.n_pulses, self.n_ranges):
+            raise NisError(f"RdaPlan.focus: plan is {self.n_pulses}x{self.n_ranges}, got {tuple(phist.shape)}")
+        for w in want:
+            if w not in self.EXPORTS:
+                raise NisError(f"RdaPlan.focus: unknown export {w!r}")
+        shape = (self.n_pulses, self.n_ranges)
+        out = {"image_mag": torch.empty(shape, dtype=torch.float32, device=phist.device)}
+        for w in want:
+            out[w] = torch.empty(shape, dtype=torch.complex64, device=phist.device)
+        with torch.cuda.device(self.di):
+            rc = _lib.load().nis_rda_focus(self._h, _ptr(phist), phist.stride(0), _ptr(out["image_mag"]),
+                                           *[_ptr(out.get(w)) for w in self.EXPORTS], C.c_void_p(_stream_ptr(self.di)))
+        _lib.check(rc, "nis_rda_focus")
+        return out
+
+    def close(self):
+        if self._h is not None:
+            _lib.load().nis_rda_plan_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+_rda_plan_cache: dict = {}
+
+
+def cached_rda_plan(n_pulses, n_ranges, **kw) -> RdaPlan:
+    di = _dev_index(kw.get("device", "cuda"))
+    key = (int(n_pulses), int(n_ranges), kw["lam"], kw["t_p"], kw["kr"], kw["fs"], kw["prf"], kw["vr"], kw["range_grp"],
+           kw.get("c", 299792458.0), di)
+    pl = _rda_plan_cache.get(key)
+    if pl is None:
+        if len(_rda_plan_cache) >= 2:
+            _rda_plan_cache.pop(next(iter(_rda_plan_cache))).close()
+        pl = RdaPlan(n_pulses, n_ranges, **kw)
+        _rda_plan_cache[key] = pl
+    return pl
+
+
 # ------------------------------------------------------------------------------------- GMTI
 GMTI_PRODUCTS = ("ati_interf", "ati_phase", "dpca_diff", "dpca_mag", "slc1_mag", "mag_mask", "ati_phase_masked")
 
