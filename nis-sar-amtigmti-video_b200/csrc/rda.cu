@@ -22,6 +22,7 @@
 
 #include "csa_internal.cuh"
 #include "fft.cuh"
+#include "tma.cuh"
 
 using namespace nis;
 using namespace nis::fft;
@@ -75,16 +76,38 @@ __global__ void __launch_bounds__(P::NT) k_rda_range(const float2* __restrict__ 
 }
 
 // ------------------------------------------------------------------------------ RCMC + azimuth compression
+// One Doppler row per CTA iteration.  The row is pulled into shared memory by ONE 1-D bulk copy (TMA) when its address and
+// length allow (16-byte multiples), so no thread waits on a chain of dependent global loads; several CTAs share an SM and
+// cover each other's copy latency.
 __global__ void __launch_bounds__(256) k_rda_rcmc(float2* __restrict__ work, int64_t pitch, int n_rows, int N, double q0,
                                                   const RdaRow* __restrict__ rows, float2* __restrict__ rd_out,
                                                   float2* __restrict__ rcmc_out, float2* __restrict__ filt_out) {
-    extern __shared__ float2 line[];
+    extern __shared__ __align__(128) float2 line[];
+    __shared__ uint64_t full;
+    const bool bulk = ((N & 1) == 0) && ((pitch & 1) == 0) && ((reinterpret_cast<uintptr_t>(work) & 15) == 0);
+    if (threadIdx.x == 0) {
+        tma::mbar_init(&full, 1);
+        tma::fence_barrier_init();
+    }
+    __syncthreads();
+    uint32_t phase = 0;
     for (int row = blockIdx.x; row < n_rows; row += gridDim.x) {
         float2* p = work + (int64_t)row * pitch;
         const RdaRow rr = rows[row];
-        for (int i = threadIdx.x; i < N; i += blockDim.x) line[i] = p[i];
-        __syncthreads();
+        if (bulk) {
+            if (threadIdx.x == 0) {
+                tma::mbar_arrive_expect_tx(&full, (uint32_t)N * sizeof(float2));
+                tma::bulk_load_1d(line, p, (uint32_t)N * sizeof(float2), &full);
+            }
+            tma::mbar_wait(&full, phase);
+            phase ^= 1;
+        } else {
+#pragma unroll 8
+            for (int i = threadIdx.x; i < N; i += blockDim.x) line[i] = p[i];
+            __syncthreads();
+        }
         const int64_t eo = (int64_t)rr.export_row * N;
+#pragma unroll 4
         for (int i = threadIdx.x; i < N; i += blockDim.x) {
             const double pos = fma((double)i + q0, rr.beta, (double)i);   // where sample i comes from on the shifted axis
             float2 o = make_float2(0.f, 0.f);
@@ -102,6 +125,7 @@ __global__ void __launch_bounds__(256) k_rda_rcmc(float2* __restrict__ work, int
             if (filt_out != nullptr) filt_out[eo + i] = cmul(g, rr.factor);
             p[i] = g;
         }
+        tma::fence_proxy_async();   // this thread's reads of the line are ordered before the next bulk copy into it
         __syncthreads();
     }
 }

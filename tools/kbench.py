@@ -55,6 +55,23 @@ def csa_stages(n_az, n_rg, iters=10):
     print(json.dumps(rec), flush=True)
 
 
+def rda(n_pulses, n_ranges, iters=10, t_p=10e-6):
+    """Range-Doppler focusing.  Algorithmic bytes per pixel: range compression 16 + azimuth DFT 16 + RCMC/azimuth
+    compression 16 + inverse DFT to magnitude 12 = 60 (image only; each exported map adds 8)."""
+    prm = params.spaceborne_preset().replace(T_p=t_p)
+    plan = dev.RdaPlan(n_pulses, n_ranges, lam=prm.Lambda, t_p=prm.T_p, kr=prm.k_rate, fs=prm.FS, prf=prm.PRF, vr=prm.V_eff,
+                       range_grp=prm.R0)
+    x = torch.view_as_complex(torch.randn((n_pulses, n_ranges, 2), device="cuda"))
+    ms = time_cuda(lambda: plan.focus(x), iters)
+    ms_all = time_cuda(lambda: plan.focus(x, want=plan.EXPORTS), iters)
+    px = n_pulses * n_ranges
+    print(json.dumps({"what": "rda", "n_pulses": n_pulses, "n_ranges": n_ranges, "taps": int(t_p * prm.FS) + 1,
+                      "ms_image_only": ms, "Mpixel_per_s": px / ms * 1e-3, "GBps_60B": 60.0 * px / ms * 1e-6,
+                      "frac": 60.0 * px / ms * 1e-6 / PEAK, "ms_with_4_exports": ms_all,
+                      "GBps_92B": 92.0 * px / ms_all * 1e-6}), flush=True)
+    plan.close()
+
+
 def gmti(n):
     a = torch.view_as_complex(torch.randn((n, n, 2), device="cuda"))
     b = torch.view_as_complex(torch.randn((n, n, 2), device="cuda"))
@@ -99,6 +116,9 @@ if __name__ == "__main__":
         if k == "csa":
             a, b = arg.split("x")
             csa_stages(int(a), int(b))
+        elif k == "rda":
+            a, b = arg.split("x")
+            rda(int(a), int(b))
         elif k == "gmti":
             gmti(int(arg))
         elif k == "echo":
