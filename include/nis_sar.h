@@ -193,6 +193,18 @@ NIS_API int nis_gmti_fused(nis_ctx* ctx, const nis_c32* slc1, const nis_c32* slc
 NIS_API int nis_gmti_balance_sum(nis_ctx* ctx, const nis_c32* slc1, const nis_c32* slc2, uint64_t n_pix,
                          double* out_sum, nis_stream stream);
 
+/* ------------------------------------------------------------------ noise and sea clutter on the device
+ * Replaces add_ocean_noise (sar_satellite_sim.py:331-344 and its copies sar_vehicle_sim.py:152-165,
+ * sar_satellite_moving_sim.py:188-206) and generate_noise_tensor (sar_batch_sim.py:65-81): complex Gaussian thermal
+ * noise at P / 10^(snr_db/10) plus K-distributed clutter (Gamma(k_nu, 1/k_nu) texture x Exp(1) speckle, uniform phase)
+ * at P / 10^(scr_db/10).  P = *power_sum_dev / n when power_sum_dev != NULL (the output of nis_power_sum: no host
+ * round trip), else ref_power.  accumulate != 0: x += noise (add_ocean_noise); 0: x = noise (generate_noise_tensor).
+ * Counter-based generator (Philox4x32-10 keyed by seed, counter = sample index): reproducible, launch-shape independent.
+ */
+NIS_API int nis_power_sum(nis_ctx* ctx, const nis_c32* x, uint64_t n, double* sum_dev /* dev, 1 double */, nis_stream stream);
+NIS_API int nis_noise_add(nis_ctx* ctx, nis_c32* x, uint64_t n, const double* power_sum_dev, double ref_power,
+                  double snr_db, double scr_db, double k_nu, uint64_t seed, int32_t accumulate, nis_stream stream);
+
 /* ------------------------------------------------------------------ buffer format helpers
  * The reference's arrays are complex128; these convert on the device so that host<->device copies
  * are the only host-side cost. */

@@ -134,6 +134,61 @@ def sar_focus_csa(phist, center_wavelength_m, pulse_width_sec, chirp_rate_hzpsec
     return (slc if return_device else _to_host_c128(slc)), rax, cax
 
 
+# ------------------------------------------------------------------------------------- noise / SNR
+K_BOLTZ = 1.380649e-23
+SNR_PRESETS = {
+    "satellite": dict(p_tx=1000.0, ant_l=3.5, ant_w=0.5, t_sys=290.0, nf_db=5.0, loss_db=3.0),   # sar_satellite_sim.py:307-313
+    "vehicle": dict(p_tx=2000.0, ant_l=1.5, ant_w=0.3, t_sys=290.0, nf_db=4.0, loss_db=3.0),     # sar_vehicle_sim.py:129-134
+}
+
+
+def calculate_snr_db(r_slant, rcs, wavelength, bandwidth, t_int, p_tx=None, ant_l=None, ant_w=None, t_sys=None,
+                     nf_db=None, loss_db=None, *, preset="satellite"):
+    """Radar-equation SNR (sar_satellite_sim.py:319-329; sar_vehicle_sim.py:140-150 with the airborne constants:
+    ``preset="vehicle"``).  Returns (snr_db, gain_db) -- host scalar arithmetic, the same expressions as the reference."""
+    d = dict(SNR_PRESETS[preset])
+    for k, v in (("p_tx", p_tx), ("ant_l", ant_l), ("ant_w", ant_w), ("t_sys", t_sys), ("nf_db", nf_db), ("loss_db", loss_db)):
+        if v is not None:
+            d[k] = v
+    ant_area = d["ant_l"] * d["ant_w"] * 0.6
+    gain = 4 * np.pi * ant_area / (wavelength ** 2)
+    gain_db = 10 * np.log10(gain)
+    nf = 10 ** (d["nf_db"] / 10)
+    loss = 10 ** (d["loss_db"] / 10)
+    numerator = d["p_tx"] * (gain ** 2) * (wavelength ** 2) * rcs * t_int
+    denominator = ((4 * np.pi) ** 3) * (r_slant ** 4) * K_BOLTZ * d["t_sys"] * bandwidth * loss * nf
+    return 10 * np.log10(numerator / denominator), gain_db
+
+
+def _draw_seed(seed):
+    # the reference draws from numpy's global generator; so does the default seed, which keeps np.random.seed() meaningful
+    return int(np.random.randint(0, 2 ** 31 - 1)) * 2654435761 + 12345 if seed is None else int(seed)
+
+
+def add_ocean_noise(raw_data, snr_db, scr_db=10.0, k_nu=1.0, *, seed=None, device=None, return_device=False):
+    """Thermal noise + K-distributed sea clutter (sar_satellite_sim.py:331-344).  A complex64 CUDA tensor is modified in
+    place and returned (the echo stays in HBM between synthesis and focusing); a numpy array comes back as a new
+    complex128 array, as in the reference.  Same distributions and powers as the reference; the draws themselves come from
+    a counter-based generator keyed by ``seed`` (default: one draw from numpy's global generator)."""
+    device = device or _default_device
+    seed = _draw_seed(seed)
+    if torch.is_tensor(raw_data):
+        x = raw_data if raw_data.dtype == torch.complex64 else dev.narrow_c128(raw_data.to(torch.complex128).contiguous())
+        return dev.add_noise(x.contiguous(), snr_db, scr_db, k_nu, seed)
+    h = np.ascontiguousarray(raw_data)
+    x = torch.from_numpy(h).to(device) if h.dtype == np.complex64 else \
+        dev.narrow_c128(torch.from_numpy(h.astype(np.complex128, copy=False)).to(device))
+    dev.add_noise(x, snr_db, scr_db, k_nu, seed)
+    return x if return_device else _to_host_c128(x)
+
+
+def generate_noise_tensor(shape, ref_power, snr_db, scr_db=10.0, k_nu=1.0, *, seed=None, device=None):
+    """Noise + clutter alone, for a given reference power (sar_batch_sim.py:65-81): a complex64 CUDA tensor."""
+    device = device or _default_device
+    x = torch.empty(tuple(shape), dtype=torch.complex64, device=device)
+    return dev.add_noise(x, snr_db, scr_db, k_nu, _draw_seed(seed), ref_power=float(ref_power), accumulate=False)
+
+
 # ------------------------------------------------------------------------------------------- RDA
 _RDA_RETURNS = {
     # which of the three copies of sar_focus_rda the caller is replacing -> what it returns after the image and two axes

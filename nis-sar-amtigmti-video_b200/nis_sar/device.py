@@ -264,6 +264,29 @@ def cached_rda_plan(n_pulses, n_ranges, **kw) -> RdaPlan:
     return pl
 
 
+# ------------------------------------------------------------------------------------ noise
+def add_noise(x, snr_db, scr_db=10.0, k_nu=1.0, seed=0, ref_power=None, accumulate=True):
+    """Thermal noise + K-distributed clutter into the complex64 CUDA tensor ``x`` in place (add_ocean_noise,
+    sar_satellite_sim.py:331-344).  ``ref_power`` None: the mean power of ``x`` itself, reduced on the device and
+    consumed there (no host synchronisation).  ``accumulate`` False overwrites ``x`` with the noise alone
+    (generate_noise_tensor, sar_batch_sim.py:65-81)."""
+    if x.dtype != torch.complex64 or not x.is_contiguous():
+        raise NisError("add_noise: x must be a contiguous complex64 CUDA tensor")
+    di = x.device.index
+    lib, ctx = _lib.load(), _lib.context(di)
+    n = x.numel()
+    with torch.cuda.device(di):
+        st = C.c_void_p(_stream_ptr(di))
+        psum = None
+        if ref_power is None:
+            psum = torch.empty(1, dtype=torch.float64, device=x.device)
+            _lib.check(lib.nis_power_sum(ctx, _ptr(x), n, _ptr(psum), st), "nis_power_sum")
+        _lib.check(lib.nis_noise_add(ctx, _ptr(x), n, _ptr(psum), float(ref_power or 0.0), float(snr_db), float(scr_db),
+                                     float(k_nu), int(seed) & 0xFFFFFFFFFFFFFFFF, 1 if accumulate else 0, st),
+                   "nis_noise_add")
+    return x
+
+
 # ------------------------------------------------------------------------------------- GMTI
 GMTI_PRODUCTS = ("ati_interf", "ati_phase", "dpca_diff", "dpca_mag", "slc1_mag", "mag_mask", "ati_phase_masked")
 

@@ -182,6 +182,24 @@ def golden_rda():
     np.savez_compressed(os.path.join(OUT, "rda_random.npz"), **out)
 
 
+def golden_noise():
+    """calculate_snr_db of the satellite and airborne scripts, and add_ocean_noise after np.random.seed (the legacy
+    global generator the reference draws from) on a small echo -- pins the oracle's draw order bit for bit."""
+    out = {}
+    rng = np.random.default_rng(3)
+    raw = (rng.standard_normal((24, 40)) + 1j * rng.standard_normal((24, 40))) * 3.0
+    for key, fname in (("satellite", "sar_satellite_sim.py"), ("vehicle", "sar_vehicle_sim.py")):
+        snr_fn, noise_fn = ref_extract.noise_functions(fname)
+        args = np.array([[6.1e5, 5.0e4, 0.031, 5.0e8, 1.2], [2.8e4, 10.0, 0.03, 3.0e8, 16.384]])
+        out[f"{key}_snr_args"] = args
+        out[f"{key}_snr"] = np.array([snr_fn(*a) for a in args])
+        for nu in (1.0, 0.5, 3.7):
+            np.random.seed(11)
+            out[f"{key}_noisy_nu{nu}"] = noise_fn(raw, 17.0, 10.0, nu)
+    out["raw"] = raw
+    np.savez_compressed(os.path.join(OUT, "noise.npz"), **out)
+
+
 if __name__ == "__main__":
     if not ref_extract.reference_available():
         sys.exit("reference tree not found: fixtures can only be regenerated in the build container")
@@ -191,5 +209,6 @@ if __name__ == "__main__":
     golden_csa()
     golden_chain()
     golden_rda()
+    golden_noise()
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))

@@ -123,3 +123,29 @@ def rda_functions():
         ns = {"np": np, "interp1d": interp1d, "convolve": convolve, "hamming": hamming}
         out[key] = _quiet(_extract(fname, ("sar_focus_rda",), ns)["sar_focus_rda"])
     return out
+
+
+def _constants(filename: str, names: tuple[str, ...]) -> dict:
+    """Literal module-level assignments (``P_TX = 1000.0``) of a reference script, by name."""
+    path = os.path.join(REFERENCE_DIR, filename)
+    with open(path, "r") as fh:
+        tree = ast.parse(fh.read(), filename=path)
+    out = {}
+    for node in tree.body:
+        if isinstance(node, ast.Assign) and len(node.targets) == 1 and isinstance(node.targets[0], ast.Name) \
+                and node.targets[0].id in names:
+            out[node.targets[0].id] = ast.literal_eval(node.value)
+    missing = set(names) - set(out)
+    if missing:
+        raise RuntimeError(f"{filename}: constants not found: {sorted(missing)}")
+    return out
+
+
+def noise_functions(fname: str = "sar_satellite_sim.py"):
+    """``calculate_snr_db`` and ``add_ocean_noise`` (sar_satellite_sim.py:319-344; identical copies in
+    sar_vehicle_sim.py:140-165 and sar_satellite_moving_sim.py:174-206 with their own radar constants)."""
+    ns = {"np": np}
+    ns.update(_constants(fname, ("P_TX", "ANT_LENGTH", "ANT_WIDTH", "T_SYS", "NF_DB", "LOSS_DB", "K_BOLTZ", "SCR_DB",
+                                 "K_NU")))
+    f = _extract(fname, ("calculate_snr_db", "add_ocean_noise"), ns)
+    return f["calculate_snr_db"], _quiet(f["add_ocean_noise"])

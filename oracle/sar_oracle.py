@@ -283,3 +283,42 @@ def focus_rda(phist, lam, t_p, kr, fs, prf, vr, range_grp_m):
     return {"image_mag_T": np.abs(img).T, "range_axis_centered": rax - np.mean(rax), "cross_range": vr * slow,
             "phist_compressed": rc, "range_doppler": rd, "range_doppler_rcmc": rcmc, "range_doppler_filtered": filt,
             "doppler_freq": dop}
+
+
+# ---------------------------------------------------------------------------- noise / clutter
+SNR_PRESETS = {
+    # module constants the three copies of calculate_snr_db take as defaults
+    "satellite": dict(p_tx=1000.0, ant_l=3.5, ant_w=0.5, t_sys=290.0, nf_db=5.0, loss_db=3.0),   # sar_satellite_sim.py:307-313
+    "vehicle": dict(p_tx=2000.0, ant_l=1.5, ant_w=0.3, t_sys=290.0, nf_db=4.0, loss_db=3.0),     # sar_vehicle_sim.py:129-134
+}
+K_BOLTZ = 1.380649e-23
+
+
+def calculate_snr_db(r_slant, rcs, wavelength, bandwidth, t_int, p_tx, ant_l, ant_w, t_sys, nf_db, loss_db):
+    """Radar-equation SNR after integration over t_int (sar_satellite_sim.py:319-329).  Returns (snr_db, gain_db)."""
+    ant_area = ant_l * ant_w * 0.6
+    gain = 4 * np.pi * ant_area / (wavelength ** 2)
+    gain_db = 10 * np.log10(gain)
+    nf = 10 ** (nf_db / 10)
+    loss = 10 ** (loss_db / 10)
+    numerator = p_tx * (gain ** 2) * (wavelength ** 2) * rcs * t_int
+    denominator = ((4 * np.pi) ** 3) * (r_slant ** 4) * K_BOLTZ * t_sys * bandwidth * loss * nf
+    return 10 * np.log10(numerator / denominator), gain_db
+
+
+def ocean_noise(raw_data, snr_db, scr_db=10.0, k_nu=1.0, rng=None):
+    """``add_ocean_noise`` (sar_satellite_sim.py:331-344): complex Gaussian thermal noise at signal_power / SNR plus
+    K-distributed sea clutter (Gamma(nu, 1/nu) texture x Exp(1) speckle, uniform phase) at signal_power / SCR.
+    ``rng``: a numpy RandomState drawn from in the reference's order (randn, randn, gamma, exponential, uniform);
+    RandomState(s) reproduces the reference after np.random.seed(s) bit for bit."""
+    rng = rng or np.random.RandomState()
+    signal_power = np.mean(np.abs(raw_data) ** 2)
+    noise_power = signal_power / (10 ** (snr_db / 10))
+    thermal = np.sqrt(noise_power / 2) * (rng.randn(*raw_data.shape) + 1j * rng.randn(*raw_data.shape))
+    clutter_power = signal_power / (10 ** (scr_db / 10))
+    texture = rng.gamma(k_nu, 1 / k_nu, raw_data.shape)
+    speckle = rng.exponential(1, raw_data.shape)
+    phase = rng.uniform(0, 2 * np.pi, raw_data.shape)
+    clutter = np.sqrt(clutter_power * texture * speckle) * np.exp(1j * phase)
+    return raw_data + thermal + clutter, {"signal_power": signal_power, "noise_power": noise_power,
+                                          "clutter_power": clutter_power}

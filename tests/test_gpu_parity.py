@@ -506,3 +506,47 @@ def test_rda_point_target_focuses_where_the_reference_puts_it(api):
     assert np.unravel_index(np.argmax(img), img.shape) == np.unravel_index(np.argmax(ref), ref.shape)
     assert abs(img.max() - ref.max()) < 1e-4 * ref.max()
     assert _rel(img, ref) < TOL_L2
+
+
+# ------------------------------------------------------------------------------------------ noise
+def test_noise_powers_and_distributions(api, dev):
+    """add_ocean_noise / generate_noise_tensor: statistical parity with the reference's numpy draws (oracle.ocean_noise)
+    -- powers, Gaussianity of the thermal part, K-distribution moments and two-sample Kolmogorov-Smirnov distances of
+    the clutter intensity for nu = 1 (fast path), 0.5 and 3.7 (Marsaglia-Tsang)."""
+    import torch
+    from scipy import stats
+    n = 1 << 20
+    # thermal part alone (clutter 300 dB down)
+    th = api.generate_noise_tensor((n,), 4.0, 6.0, scr_db=300.0, seed=5).cpu().numpy()
+    pn = 4.0 / 10 ** 0.6
+    assert abs(th.real.var() / (pn / 2) - 1) < 0.01 and abs(th.imag.var() / (pn / 2) - 1) < 0.01
+    assert abs(th.real.mean()) < 4 * np.sqrt(pn / 2 / n) and abs(np.corrcoef(th.real, th.imag)[0, 1]) < 5e-3
+    assert abs(stats.kurtosis(th.real, fisher=False) - 3) < 0.05
+    assert stats.kstest(th.real[::8] / np.sqrt(pn / 2), "norm").statistic < 0.01
+    # clutter alone (thermal 300 dB down)
+    for nu in (1.0, 0.5, 3.7):
+        cl = api.generate_noise_tensor((n,), 4.0, 300.0, scr_db=10.0, k_nu=nu, seed=9).cpu().numpy()
+        inten = np.abs(cl) ** 2
+        pc = 4.0 / 10.0
+        assert abs(inten.mean() / pc - 1) < 0.02, (nu, inten.mean())
+        m2 = (inten ** 2).mean() / inten.mean() ** 2
+        assert abs(m2 / (2 * (1 + 1 / nu)) - 1) < 0.06, (nu, m2)
+        ph = np.angle(cl)
+        assert stats.kstest((ph[::8] + np.pi) / (2 * np.pi), "uniform").statistic < 0.01
+        ref, _ = orc.ocean_noise(np.zeros(n // 4, dtype=complex) + 2.0, 300.0, 10.0, nu, np.random.RandomState(3))
+        ks = stats.ks_2samp(inten[::4], np.abs(ref - 2.0) ** 2).statistic
+        print(f"clutter nu={nu}: mean {inten.mean():.4f} (want {pc}), m2 {m2:.3f} (want {2 * (1 + 1 / nu):.3f}), KS {ks:.4f}")
+        assert ks < 0.01
+    # in-place on the device with the power taken from the echo itself; numpy in -> new complex128 out
+    rng = np.random.default_rng(0)
+    raw = (3.0 * np.exp(2j * np.pi * rng.random((512, 1024)))).astype(np.complex64)
+    out = api.add_ocean_noise(raw, 10.0, 13.0, seed=42)
+    assert out.dtype == np.complex128 and out.shape == raw.shape and np.all(np.abs(raw) - 3.0 < 1e-5)
+    added = out - raw
+    want = 9.0 / 10 + 9.0 / 10 ** 1.3
+    assert abs(np.mean(np.abs(added) ** 2) / want - 1) < 0.02
+    assert np.array_equal(out, api.add_ocean_noise(raw, 10.0, 13.0, seed=42))
+    assert not np.array_equal(out, api.add_ocean_noise(raw, 10.0, 13.0, seed=43))
+    t = torch.from_numpy(raw).cuda()
+    r = api.add_ocean_noise(t, 10.0, 13.0, seed=42)
+    assert r.data_ptr() == t.data_ptr() and np.allclose(r.cpu().numpy(), out, atol=1e-6)

@@ -175,3 +175,23 @@ def test_rda_matches_reference(tag):
                       ("range_doppler_filtered", "filt")):
         assert rel(o[key][sl], g[f"{tag}_{name}"]) < 1e-6          # stored as complex64
         assert np.array_equal(o[key][sl] == 0, g[f"{tag}_{name}"] == 0)   # same zero fill outside the shifted axis
+
+
+# ------------------------------------------------------------------------------------------ noise (N2)
+def test_noise_oracle_matches_reference_bit_for_bit():
+    """calculate_snr_db and add_ocean_noise (after np.random.seed) of the satellite and airborne scripts."""
+    g = _load("noise.npz")
+    for key in ("satellite", "vehicle"):
+        for a, r in zip(g[f"{key}_snr_args"], g[f"{key}_snr"]):
+            assert np.array_equal(np.array(orc.calculate_snr_db(*a, **orc.SNR_PRESETS[key])), r)
+        for nu in (1.0, 0.5, 3.7):
+            o, _ = orc.ocean_noise(g["raw"], 17.0, 10.0, nu, np.random.RandomState(11))
+            assert np.array_equal(o, g[f"{key}_noisy_nu{nu}"])
+
+
+def test_api_snr_matches_reference():
+    from nis_sar import api
+    g = _load("noise.npz")
+    for key in ("satellite", "vehicle"):
+        for a, r in zip(g[f"{key}_snr_args"], g[f"{key}_snr"]):
+            assert np.array_equal(np.array(api.calculate_snr_db(*a, preset=key)), r)
