@@ -193,6 +193,22 @@ NIS_API int nis_gmti_fused(nis_ctx* ctx, const nis_c32* slc1, const nis_c32* slc
 NIS_API int nis_gmti_balance_sum(nis_ctx* ctx, const nis_c32* slc1, const nis_c32* slc2, uint64_t n_pix,
                          double* out_sum, nis_stream stream);
 
+/* ------------------------------------------------------------------ viewer data layer
+ * SARData.compute_all (sar_ati_dcpa_viewer_csa.py:42-52): with s2c = slc2 * exp(j cal_phase):
+ * |slc1|, arg slc1, |s2c|, arg s2c, |slc1 - s2c|, arg(slc1 - s2c), arg(slc1 conj(s2c)); any output may be NULL. */
+NIS_API int nis_viewer_products(nis_ctx* ctx, const nis_c32* slc1, const nis_c32* slc2, uint64_t n_pix, double cal_phase,
+                        float* ch1_mag, float* ch1_phase, float* ch2_mag, float* ch2_phase, float* dpca_mag,
+                        float* dpca_phase, float* ati_phase, nis_stream stream);
+/* Statistics of the visible region (:117-139): a rows x cols rectangle of a float map whose rows are `pitch` elements
+ * apart; db_scale != 0 evaluates 20 log10(x + 1e-12) (:128).  out_dev: dev [4] doubles = sum, min, max, sum of squared
+ * deviations about the mean (mean = sum / n, std = sqrt(ssd / n) as numpy's). */
+NIS_API int nis_region_stats(nis_ctx* ctx, const float* map, int64_t pitch, int32_t rows, int32_t cols, int32_t db_scale,
+                     double* out_dev, nis_stream stream);
+/* Exact order statistics of the region by radix select (median :118,:136; 99.9th percentile :147,:178,:184):
+ * out_dev[i] = the value of 0-based rank ranks[i] (host array, 1..4 ranks) in ascending order. */
+NIS_API int nis_region_select(nis_ctx* ctx, const float* map, int64_t pitch, int32_t rows, int32_t cols,
+                      const uint64_t* ranks, int32_t n_ranks, float* out_dev, nis_stream stream);
+
 /* ------------------------------------------------------------------ noise and sea clutter on the device
  * Replaces add_ocean_noise (sar_satellite_sim.py:331-344 and its copies sar_vehicle_sim.py:152-165,
  * sar_satellite_moving_sim.py:188-206) and generate_noise_tensor (sar_batch_sim.py:65-81): complex Gaussian thermal

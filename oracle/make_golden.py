@@ -200,6 +200,24 @@ def golden_noise():
     np.savez_compressed(os.path.join(OUT, "noise.npz"), **out)
 
 
+def golden_viewer():
+    """SARData (sar_ati_dcpa_viewer_csa.py:35-55) on a small seeded channel pair, before and after a balance."""
+    cls = ref_extract.viewer_sardata_class()
+    rng = np.random.default_rng(21)
+    s1 = rng.standard_normal((20, 30)) + 1j * rng.standard_normal((20, 30))
+    s2 = s1 * np.exp(0.4j) + 0.2 * (rng.standard_normal((20, 30)) + 1j * rng.standard_normal((20, 30)))
+    sar = cls(s1, s2)
+    out = {"s1": s1, "s2": s2}
+    for m, v in sar.prods.items():
+        out["cal0_" + m] = v
+    sar.cal_phase = np.angle(np.mean(s1 * np.conj(s2)))
+    sar.compute_all()
+    out["cal_phase"] = sar.cal_phase
+    for m, v in sar.prods.items():
+        out["cal1_" + m] = v
+    np.savez_compressed(os.path.join(OUT, "viewer.npz"), **out)
+
+
 if __name__ == "__main__":
     if not ref_extract.reference_available():
         sys.exit("reference tree not found: fixtures can only be regenerated in the build container")
@@ -210,5 +228,6 @@ if __name__ == "__main__":
     golden_chain()
     golden_rda()
     golden_noise()
+    golden_viewer()
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))

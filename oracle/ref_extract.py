@@ -149,3 +149,16 @@ def noise_functions(fname: str = "sar_satellite_sim.py"):
                                  "K_NU")))
     f = _extract(fname, ("calculate_snr_db", "add_ocean_noise"), ns)
     return f["calculate_snr_db"], _quiet(f["add_ocean_noise"])
+
+
+def viewer_sardata_class():
+    """The ``SARData`` class nested in ``main()`` of sar_ati_dcpa_viewer_csa.py (:35-55)."""
+    path = os.path.join(REFERENCE_DIR, "sar_ati_dcpa_viewer_csa.py")
+    with open(path, "r") as fh:
+        tree = ast.parse(fh.read(), filename=path)
+    nodes = [n for n in ast.walk(tree) if isinstance(n, ast.ClassDef) and n.name == "SARData"]
+    if not nodes:
+        raise RuntimeError("SARData not found")
+    ns = {"np": np}
+    exec(compile(ast.Module(body=[nodes[0]], type_ignores=[]), path, "exec"), ns)
+    return ns["SARData"]

@@ -322,3 +322,35 @@ def ocean_noise(raw_data, snr_db, scr_db=10.0, k_nu=1.0, rng=None):
     clutter = np.sqrt(clutter_power * texture * speckle) * np.exp(1j * phase)
     return raw_data + thermal + clutter, {"signal_power": signal_power, "noise_power": noise_power,
                                           "clutter_power": clutter_power}
+
+
+# ---------------------------------------------------------------------------- viewer data layer
+VIEWER_MODES = ("Ch1 Magnitude", "Ch1 Phase", "Ch2 Magnitude", "Ch2 Phase", "DPCA Magnitude", "DPCA Phase", "ATI Phase")
+
+
+def viewer_products(s1, s2, cal_phase=0.0):
+    """``SARData.compute_all`` (sar_ati_dcpa_viewer_csa.py:42-52)."""
+    s2_cal = s2 * np.exp(1j * cal_phase)
+    return {"Ch1 Magnitude": np.abs(s1), "Ch1 Phase": np.angle(s1), "Ch2 Magnitude": np.abs(s2_cal),
+            "Ch2 Phase": np.angle(s2_cal), "DPCA Magnitude": np.abs(s1 - s2_cal), "DPCA Phase": np.angle(s1 - s2_cal),
+            "ATI Phase": np.angle(s1 * np.conj(s2_cal))}
+
+
+def viewer_visible_stats(prods, mode, scale, c_indices, r_indices):
+    """The numbers ``print_visible_stats`` prints (sar_ati_dcpa_viewer_csa.py:103-145) and the colour limit it sets
+    (:147-151) for the rectangle ``np.ix_(c_indices, r_indices)`` of the [N_cross, N_range] map."""
+    vis = prods[mode][np.ix_(c_indices, r_indices)]
+    if "Phase" in mode:
+        data = vis
+    else:
+        data = 20 * np.log10(vis + 1e-12) if scale == "dB" else vis
+    out = {"mean": np.mean(data), "median": np.median(data), "std": np.std(data), "min": np.min(data), "max": np.max(data)}
+    if "DPCA" in mode:
+        ref = prods["Ch1 Magnitude"][np.ix_(c_indices, r_indices)]
+        out["cancellation_ratio"] = np.mean(ref) / (np.mean(vis) + 1e-9)
+    if "Phase" in mode:
+        out["clim"] = (-np.pi, np.pi)
+    else:
+        vmax = np.percentile(data, 99.9)
+        out["clim"] = (vmax - 60 if scale == "dB" else 0, vmax)
+    return out

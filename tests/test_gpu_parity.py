@@ -550,3 +550,50 @@ def test_noise_powers_and_distributions(api, dev):
     t = torch.from_numpy(raw).cuda()
     r = api.add_ocean_noise(t, 10.0, 13.0, seed=42)
     assert r.data_ptr() == t.data_ptr() and np.allclose(r.cpu().numpy(), out, atol=1e-6)
+
+
+# ------------------------------------------------------------------------------------------ viewer
+def test_viewer_products_stats_and_clim(api, tmp_path):
+    """nis_sar.viewer.SARData against the reference's SARData (golden) and against numpy statistics of the visible
+    rectangle: mean / median / std / min / max, DPCA cancellation ratio, 99.9th-percentile colour limits -- full view and
+    a zoomed rectangle, dB and linear, before and after Auto-Balance."""
+    from nis_sar import viewer
+    g = np.load(os.path.join(GOLDEN, "viewer.npz"))
+    sar = viewer.SARData(g["s1"], g["s2"])
+    for m in viewer.MODES:
+        got = sar.get(m)
+        assert got.shape == g["s1"].shape
+        d = got - g["cal0_" + m]
+        if "Phase" in m:
+            d = np.angle(np.exp(1j * d))
+        assert np.max(np.abs(d)) < (TOL_PHASE if "Phase" in m else 1e-5), m
+    cal = sar.balance()
+    assert abs(cal - float(g["cal_phase"])) < 1e-6
+    for m in viewer.MODES:
+        d = sar.get(m) - g["cal1_" + m]
+        if "Phase" in m:
+            d = np.angle(np.exp(1j * d))
+        assert np.max(np.abs(d)) < (TOL_PHASE if "Phase" in m else 1e-5), m
+    # a larger scene through the npz hand-off, statistics on the full view and on a zoom
+    rng = np.random.default_rng(8)
+    shape = (700, 900)                                   # [N_range, N_cross] as saved by the simulator
+    s1 = (rng.standard_normal(shape) + 1j * rng.standard_normal(shape)) * np.exp(rng.standard_normal(shape))
+    s2 = s1 * np.exp(0.3j) + 0.05 * (rng.standard_normal(shape) + 1j * rng.standard_normal(shape))
+    fname = str(tmp_path / "ati_dpca_data_csa.npz")
+    api.save_ati_dpca_npz(fname, s1.astype(np.complex64), s2.astype(np.complex64), np.linspace(6e5, 6.01e5, shape[0]),
+                          np.linspace(-500, 500, shape[1]))
+    sar, rax, cax, extent = viewer.load_npz(fname)
+    d = np.load(fname)
+    prods = orc.viewer_products(d["slc1"].T, d["slc2"].T, 0.0)
+    for c_idx, r_idx in ((np.arange(shape[1]), np.arange(shape[0])), (np.arange(100, 431), np.arange(250, 577))):
+        for mode, scale in (("Ch1 Magnitude", "dB"), ("Ch1 Magnitude", "Linear"), ("DPCA Magnitude", "dB"),
+                            ("DPCA Magnitude", "Linear"), ("ATI Phase", "dB"), ("Ch2 Phase", "Linear")):
+            want = orc.viewer_visible_stats(prods, mode, scale, c_idx, r_idx)
+            got = sar.visible_stats(mode, scale, c_idx, r_idx)
+            tol = 2e-5 if "Phase" not in mode else 2e-6
+            for k in ("mean", "median", "std", "min", "max"):
+                assert abs(got[k] - want[k]) <= tol * max(1.0, abs(want[k])), (mode, scale, k, got[k], want[k])
+            if "DPCA" in mode:
+                assert abs(got["cancellation_ratio"] / want["cancellation_ratio"] - 1) < 1e-5
+            lo, hi = sar.clim(mode, scale, c_idx, r_idx)
+            assert abs(hi - want["clim"][1]) <= 2e-5 * max(1.0, abs(hi)) and abs(lo - want["clim"][0]) <= 2e-5 * max(1.0, abs(lo))

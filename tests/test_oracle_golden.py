@@ -195,3 +195,13 @@ def test_api_snr_matches_reference():
     for key in ("satellite", "vehicle"):
         for a, r in zip(g[f"{key}_snr_args"], g[f"{key}_snr"]):
             assert np.array_equal(np.array(api.calculate_snr_db(*a, preset=key)), r)
+
+
+# ------------------------------------------------------------------------------------------ viewer data layer (N3)
+def test_viewer_products_match_reference():
+    g = _load("viewer.npz")
+    for cal, tag in ((0.0, "cal0_"), (float(g["cal_phase"]), "cal1_")):
+        o = orc.viewer_products(g["s1"], g["s2"], cal)
+        for m in orc.VIEWER_MODES:
+            assert np.array_equal(o[m], g[tag + m]), m
+    assert float(g["cal_phase"]) == orc.balance_phase(g["s1"], g["s2"])
