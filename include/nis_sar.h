@@ -45,6 +45,7 @@ enum {
 typedef struct nis_ctx nis_ctx;
 typedef struct nis_csa_plan nis_csa_plan;
 typedef struct nis_rda_plan nis_rda_plan;
+typedef struct nis_tdbp_plan nis_tdbp_plan;
 typedef struct { float re, im; } nis_c32;
 typedef void* nis_stream; /* cudaStream_t */
 
@@ -82,6 +83,17 @@ typedef struct {
     int32_t samples_per_thread;  /* 0: library chooses; 8 or 16: chunk = 256 * this many samples per CTA.
                                   * 8 suits scenes whose chirps cover well under the whole window */
 } nis_echo_params;
+
+/* Spotlight engine, run_physics_spotlight (sar_batch_sim.py:83-169): start-stop corrected delay -- the receive position is
+ * pos_sat + vel_sat * 2 d_tx / c (:133-137) --, one-way sinc^2 pattern gain((pi l_ant / lambda) sin(off-boresight angle))
+ * of an aperture steered at the scene centre (:139-149), amplitude rcs * gain (not its square root), chirp CENTRED on the
+ * delay: exp(j 2 pi (-fc tau + (k_rate/2)(t_n - tau)^2)) for |t_n - tau| <= t_p/2 (:151-155).  The heading rotation of the
+ * target block (:92-100) is host geometry and arrives applied to tgt_pos0 / tgt_vel. */
+NIS_API int nis_echo_spotlight(nis_ctx* ctx, const nis_echo_params* prm, const double* tgt_pos0, const double* tgt_vel,
+                       const double* tgt_rcs /* dev [T] */, const double* pos_sat /* dev [P*3] */,
+                       const double* vel_sat /* dev [P*3] */, const double* t_slow, const double* t_fast,
+                       int32_t T, int32_t P0, int32_t P1, int32_t S, double ant_pi_l_over_lambda,
+                       nis_c32* raw, int32_t accumulate, nis_stream stream);
 
 NIS_API int nis_echo_accumulate(nis_ctx* ctx, const nis_echo_params* prm,
                         const double* tgt_pos0 /* dev [T*3] */,
@@ -165,6 +177,33 @@ NIS_API int nis_rda_axes(const nis_rda_plan* plan, double* range_axis_centered, 
  * rd = range_doppler.T, rcmc = range_doppler_rcmc.T, filt = range_doppler_filtered.T (Doppler rows in fftshift order). */
 NIS_API int nis_rda_focus(nis_rda_plan* plan, const nis_c32* phist, int64_t pitch, float* image_mag, nis_c32* rc,
                   nis_c32* rd, nis_c32* rcmc, nis_c32* filt, nis_stream stream);
+
+/* ------------------------------------------------------------------ time-domain backprojection (VideoSAR frames)
+ * Replaces tdbp_gpu (sar_batch_sim.py:171-238).  Range compression: circular correlation of each pulse with the fftshifted
+ * int(t_p fs)-tap reference chirp over the n_samples window (:177-185).  Backprojection: per pixel of the nx x ny grid
+ * linspace(-scene_size/2, scene_size/2) (x along-track, y ground range, z = 0) and per pulse, fp64 two-way delay with the
+ * start-stop correction at both ends and the pixel moving at vel_focus about the CPI centre (:207-223), range-Doppler
+ * coupling shift (:214-217), float32 two-tap interpolation of the compressed pulse exactly as torch's grid_sample
+ * (align_corners=False) evaluates it (:225-230), carrier phase exp(j 2 pi fc tau), complex128 sum over pulses (:232-235).
+ */
+typedef struct {
+    double c, fc, k_rate, t_p, fs;
+    double t_start;      /* first sample time of the receive window */
+    double scene_size;   /* m */
+    int32_t n_samples, nx, ny, reserved;
+} nis_tdbp_params;
+
+NIS_API int nis_tdbp_plan_create(nis_ctx* ctx, const nis_tdbp_params* prm, nis_tdbp_plan** out);
+NIS_API int nis_tdbp_plan_destroy(nis_tdbp_plan* plan);
+/* raw: dev [n_pulses][pitch] complex64 -> rc: dev [n_pulses][n_samples] complex64 */
+NIS_API int nis_tdbp_range_compress(nis_tdbp_plan* plan, const nis_c32* raw, int64_t pitch, int32_t n_pulses, nis_c32* rc,
+                            nis_stream stream);
+/* pos_plat / vel_plat: dev [n_pulses*3], t_pulses: dev [n_pulses] doubles; t_centre = mean(t_pulses) of the whole CPI;
+ * vel_focus: HOST [3].  Pulses [p_begin, p_end) are summed into image (dev [ny][nx] complex128 as double pairs):
+ * accumulate = 0 overwrites, 1 adds -- a CPI can be split into pulse blocks, across calls or across GPUs. */
+NIS_API int nis_tdbp_backproject(nis_tdbp_plan* plan, const nis_c32* rc, const double* pos_plat, const double* vel_plat,
+                         const double* t_pulses, int32_t n_pulses, int32_t p_begin, int32_t p_end, double t_centre,
+                         const double* vel_focus, double* image, int32_t accumulate, nis_stream stream);
 
 /* ------------------------------------------------------------------ K3: DPCA + ATI + detection
  * Replaces the inline numpy passes sar_ati_dcpa_sim_csa.py:414-419, :447-449 and

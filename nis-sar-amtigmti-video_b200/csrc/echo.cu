@@ -29,6 +29,8 @@ struct EchoConst {
     double c, fc, k_rate, t_p, t_start, dt_fast;
     double a_turns;  // (k/2) dt^2
     int T, P0, S, per_target_velocity, accumulate, bistatic;
+    int spotlight;   // 1: run_physics_spotlight model (sar_batch_sim.py:83-169): pos_rx carries the platform velocity
+    double ant;      // pi l_ant / lambda of the one-way sinc^2 pattern (spotlight)
 };
 
 template <int SPT>
@@ -41,9 +43,10 @@ __device__ __forceinline__ uint32_t frac32(double turns) {
     return (uint32_t)(unsigned long long)(turns * 4294967296.0);  // < 2^32 except turns==1-eps -> saturates below
 }
 
-// closed-interval gate of the reference, evaluated exactly as numpy does in fp64 (:164-166)
-__device__ __forceinline__ bool gate(const double* __restrict__ t_fast, int n, double tau, double half) {
-    return fabs(__dsub_rn(__dsub_rn(t_fast[n], tau), half)) <= half;
+// closed-interval gate of the reference, evaluated exactly as numpy does in fp64 (:164-166): |t_n - tau - off| <= half,
+// off = T_p/2 for the engines whose chirp STARTS at the delay, 0 for the spotlight engine whose chirp is centred on it
+__device__ __forceinline__ bool gate(const double* __restrict__ t_fast, int n, double tau, double off, double half) {
+    return fabs(__dsub_rn(__dsub_rn(t_fast[n], tau), off)) <= half;
 }
 
 template <int SPT>
@@ -71,8 +74,9 @@ __global__ void __launch_bounds__(256) k_echo(EchoConst k, EchoTail<SPT> tail, c
     const double ti = t_slow[pulse];
     const double tx0 = pos_tx[3 * pulse], tx1 = pos_tx[3 * pulse + 1], tx2 = pos_tx[3 * pulse + 2];
     double rx0 = tx0, rx1 = tx1, rx2 = tx2;
-    if (k.bistatic) { rx0 = pos_rx[3 * pulse]; rx1 = pos_rx[3 * pulse + 1]; rx2 = pos_rx[3 * pulse + 2]; }
+    if (k.bistatic || k.spotlight) { rx0 = pos_rx[3 * pulse]; rx1 = pos_rx[3 * pulse + 1]; rx2 = pos_rx[3 * pulse + 2]; }
     const double half = k.t_p / 2;
+    const double off = k.spotlight ? 0.0 : half;   // chirp centre relative to the delay
     const double t_center = k.t_start + (double)nc * k.dt_fast;
 
     float2 acc[SPT];
@@ -92,8 +96,20 @@ __global__ void __launch_bounds__(256) k_echo(EchoConst k, EchoTail<SPT> tail, c
                          pz = __dadd_rn(pos0[3 * b + 2], __dmul_rn(vb[2], ti));
             double dx = px - tx0, dy = py - tx1, dz = pz - tx2;
             const double d_tx = sqrt(__dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz)));
-            double tau;
-            if (k.bistatic) {
+            double tau, gain = 1.0;
+            if (k.spotlight) {
+                // start-stop correction: the receive position is the platform advanced by v * 2 d_tx / c (:133-137)
+                const double ta = __ddiv_rn(__dmul_rn(2.0, d_tx), k.c);
+                const double ex = px - (tx0 + rx0 * ta), ey = py - (tx1 + rx1 * ta), ez = pz - (tx2 + rx2 * ta);
+                const double d_rx = sqrt(__dadd_rn(__dadd_rn(__dmul_rn(ex, ex), __dmul_rn(ey, ey)), __dmul_rn(ez, ez)));
+                tau = __ddiv_rn(__dadd_rn(d_tx, d_rx), k.c);
+                // one-way sinc^2 pattern of the aperture steered at the scene centre (:139-149)
+                const double bn = sqrt(tx0 * tx0 + tx1 * tx1 + tx2 * tx2);
+                double co = -(tx0 * dx + tx1 * dy + tx2 * dz) / (bn * d_tx);
+                co = fmin(1.0, fmax(-1.0, co));
+                const double xv = k.ant * sin(acos(co));
+                if (fabs(xv) > 1e-6) { const double sc = sin(xv) / xv; gain = sc * sc; }
+            } else if (k.bistatic) {
                 dx = px - rx0; dy = py - rx1; dz = pz - rx2;
                 const double d_rx = sqrt(__dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz)));
                 tau = __ddiv_rn(__dadd_rn(d_tx, d_rx), k.c);
@@ -101,27 +117,27 @@ __global__ void __launch_bounds__(256) k_echo(EchoConst k, EchoTail<SPT> tail, c
                 tau = __ddiv_rn(__dmul_rn(2.0, d_tx), k.c);
             }
             // support [lo, hi) in absolute sample indices
-            int lo = (int)ceil((tau - k.t_start) / k.dt_fast);
-            int hi = (int)floor((tau + k.t_p - k.t_start) / k.dt_fast) + 1;
+            int lo = (int)ceil((tau + off - half - k.t_start) / k.dt_fast);
+            int hi = (int)floor((tau + off + half - k.t_start) / k.dt_fast) + 1;
             lo = max(0, min(lo, k.S));
             hi = max(0, min(hi, k.S));
 #pragma unroll 1
-            for (int it = 0; it < 3 && lo > 0 && gate(t_fast, lo - 1, tau, half); ++it) --lo;
+            for (int it = 0; it < 3 && lo > 0 && gate(t_fast, lo - 1, tau, off, half); ++it) --lo;
 #pragma unroll 1
-            for (int it = 0; it < 3 && lo < k.S && !gate(t_fast, lo, tau, half); ++it) ++lo;
+            for (int it = 0; it < 3 && lo < k.S && !gate(t_fast, lo, tau, off, half); ++it) ++lo;
 #pragma unroll 1
-            for (int it = 0; it < 3 && hi < k.S && gate(t_fast, hi, tau, half); ++it) ++hi;
+            for (int it = 0; it < 3 && hi < k.S && gate(t_fast, hi, tau, off, half); ++it) ++hi;
 #pragma unroll 1
-            for (int it = 0; it < 3 && hi > 0 && !gate(t_fast, hi - 1, tau, half); ++it) --hi;
+            for (int it = 0; it < 3 && hi > 0 && !gate(t_fast, hi - 1, tau, off, half); ++it) --hi;
             const int rlo = max(lo - n0, 0), rhi = min(hi - n0, CH);
             if (rlo < rhi) {
                 keep = true;
-                const double uu = t_center - tau - half;
+                const double uu = t_center - tau - off;
                 const double cq = fma(0.5 * k.k_rate * uu, uu, -k.fc * tau);  // turns at the chunk centre
                 const double bq = k.k_rate * uu * k.dt_fast;                  // turns per sample
                 r.x = frac32(cq);
                 r.y = frac32(bq);
-                r.z = __float_as_uint((float)amp[b]);
+                r.z = __float_as_uint((float)(amp[b] * gain));
                 r.w = (uint32_t)rlo | ((uint32_t)rhi << 16);
             }
         }
@@ -222,11 +238,10 @@ int launch_echo(nis_ctx* ctx, const EchoConst& k, const double* pos0, const doub
 
 }  // namespace
 
-extern "C" int nis_echo_accumulate(nis_ctx* ctx, const nis_echo_params* prm, const double* tgt_pos0,
-                                   const double* tgt_vel, const double* tgt_amp, const double* pos_tx,
-                                   const double* pos_rx, const double* t_slow, const double* t_fast, int32_t T,
-                                   int32_t P0, int32_t P1, int32_t S, nis_c32* raw, int32_t accumulate,
-                                   nis_stream stream) {
+static int echo_common(nis_ctx* ctx, const nis_echo_params* prm, const double* tgt_pos0, const double* tgt_vel,
+                       const double* tgt_amp, const double* pos_tx, const double* pos_rx, const double* t_slow,
+                       const double* t_fast, int32_t T, int32_t P0, int32_t P1, int32_t S, nis_c32* raw, int32_t accumulate,
+                       int spotlight, double ant, nis_stream stream) {
     NIS_REQUIRE(ctx && prm && tgt_pos0 && tgt_vel && tgt_amp && pos_tx && t_slow && t_fast && raw,
                 "nis_echo_accumulate: null argument");
     NIS_REQUIRE(T >= 0 && S > 0 && P0 >= 0 && P1 >= P0, "nis_echo_accumulate: bad sizes T=%d S=%d P0=%d P1=%d", T, S, P0, P1);
@@ -239,7 +254,8 @@ extern "C" int nis_echo_accumulate(nis_ctx* ctx, const nis_echo_params* prm, con
     k.t_start = prm->t_start; k.dt_fast = prm->dt_fast;
     k.a_turns = 0.5 * prm->k_rate * prm->dt_fast * prm->dt_fast;
     k.T = T; k.P0 = P0; k.S = S; k.per_target_velocity = prm->per_target_velocity;
-    k.accumulate = accumulate; k.bistatic = pos_rx != nullptr;
+    k.accumulate = accumulate; k.bistatic = (pos_rx != nullptr) && !spotlight;
+    k.spotlight = spotlight; k.ant = ant;
     float2* r = reinterpret_cast<float2*>(raw);
     // chunk = 256*SPT samples: take the wider chunk unless it wastes > 12 % of its threads past S, or the
     // caller knows that the chirps cover only part of the window (samples_per_thread hint)
@@ -248,4 +264,22 @@ extern "C" int nis_echo_accumulate(nis_ctx* ctx, const nis_echo_params* prm, con
     if (wide)
         return launch_echo<16>(ctx, k, tgt_pos0, tgt_vel, tgt_amp, pos_tx, pos_rx, t_slow, t_fast, r, P1 - P0, st);
     return launch_echo<8>(ctx, k, tgt_pos0, tgt_vel, tgt_amp, pos_tx, pos_rx, t_slow, t_fast, r, P1 - P0, st);
+}
+
+extern "C" int nis_echo_accumulate(nis_ctx* ctx, const nis_echo_params* prm, const double* tgt_pos0,
+                                   const double* tgt_vel, const double* tgt_amp, const double* pos_tx,
+                                   const double* pos_rx, const double* t_slow, const double* t_fast, int32_t T,
+                                   int32_t P0, int32_t P1, int32_t S, nis_c32* raw, int32_t accumulate,
+                                   nis_stream stream) {
+    return echo_common(ctx, prm, tgt_pos0, tgt_vel, tgt_amp, pos_tx, pos_rx, t_slow, t_fast, T, P0, P1, S, raw, accumulate,
+                       0, 0.0, stream);
+}
+
+extern "C" int nis_echo_spotlight(nis_ctx* ctx, const nis_echo_params* prm, const double* tgt_pos0, const double* tgt_vel,
+                                  const double* tgt_rcs, const double* pos_sat, const double* vel_sat,
+                                  const double* t_slow, const double* t_fast, int32_t T, int32_t P0, int32_t P1, int32_t S,
+                                  double ant_pi_l_over_lambda, nis_c32* raw, int32_t accumulate, nis_stream stream) {
+    NIS_REQUIRE(vel_sat != nullptr, "nis_echo_spotlight: the platform velocity is required (start-stop correction)");
+    return echo_common(ctx, prm, tgt_pos0, tgt_vel, tgt_rcs, pos_sat, vel_sat, t_slow, t_fast, T, P0, P1, S, raw, accumulate,
+                       1, ant_pi_l_over_lambda, stream);
 }

@@ -36,6 +36,12 @@ class RdaParams(C.Structure):
                 ("prf", C.c_double), ("vr", C.c_double), ("range_grp", C.c_double)]
 
 
+class TdbpParams(C.Structure):
+    _fields_ = [("c", C.c_double), ("fc", C.c_double), ("k_rate", C.c_double), ("t_p", C.c_double), ("fs", C.c_double),
+                ("t_start", C.c_double), ("scene_size", C.c_double), ("n_samples", C.c_int32), ("nx", C.c_int32),
+                ("ny", C.c_int32), ("reserved", C.c_int32)]
+
+
 class GmtiResult(C.Structure):
     _fields_ = [("det_count", C.c_uint32), ("peak_idx", C.c_uint32), ("max_mag_sq", C.c_double)]
 
@@ -50,6 +56,13 @@ SIGNATURES = {
     "nis_ctx_launch_count": (C.c_uint64, [_P]),
     "nis_echo_accumulate": (C.c_int, [_P, C.POINTER(EchoParams), _P, _P, _P, _P, _P, _P, _P,
                                       C.c_int32, C.c_int32, C.c_int32, C.c_int32, _P, C.c_int32, _P]),
+    "nis_echo_spotlight": (C.c_int, [_P, C.POINTER(EchoParams), _P, _P, _P, _P, _P, _P, _P,
+                                     C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_double, _P, C.c_int32, _P]),
+    "nis_tdbp_plan_create": (C.c_int, [_P, C.POINTER(TdbpParams), C.POINTER(_P)]),
+    "nis_tdbp_plan_destroy": (C.c_int, [_P]),
+    "nis_tdbp_range_compress": (C.c_int, [_P, _P, C.c_int64, C.c_int32, _P, _P]),
+    "nis_tdbp_backproject": (C.c_int, [_P, _P, _P, _P, _P, C.c_int32, C.c_int32, C.c_int32, C.c_double, _P, _P, C.c_int32,
+                                       _P]),
     "nis_csa_plan_create": (C.c_int, [_P, C.c_int32, C.c_int32, C.POINTER(CsaParams), C.POINTER(_P)]),
     "nis_csa_plan_destroy": (C.c_int, [_P]),
     "nis_csa_size_class": (C.c_int, [C.c_int32, C.c_int32]),

@@ -106,6 +106,65 @@ def run_custom_physics(targets, t_vec, pos, tuned_prp, t_p, fc, bw, *, params: R
     return raw if return_device else _to_host_c128(raw)
 
 
+# --------------------------------------------------------------------- spotlight echo + backprojection
+def spotlight_window(prm: RadarParams):
+    """Receive window of run_physics_spotlight (sar_batch_sim.py:85-90): (t_start, num_samples)."""
+    win_len = (2000.0 / prm.C) + prm.T_p + 10e-6
+    n = int(np.ceil(win_len * prm.FS))
+    if n % 2 != 0:
+        n += 1
+    return 2 * prm.R0 / prm.C - win_len / 2, n
+
+
+def run_physics_spotlight(base_targets, t_vec, pos_sat, vel_sat, heading_deg, speed, l_ant, *,
+                          params: RadarParams | None = None, device=None, return_device=True):
+    """Spotlight CPI echo of a target block on a heading (sar_batch_sim.py:83-169).  Returns
+    (raw_sig, t_start, num_samples, v_tgt) -- raw_sig a complex64 CUDA tensor [P, S] (the reference returns a device
+    tensor as well, complex128; ``return_device=False`` gives complex128 numpy)."""
+    prm = _params(params)
+    t_start, n = spotlight_window(prm)
+    t_fast = t_start + np.arange(n) / prm.FS                                       # :90
+    phi = np.radians(heading_deg)
+    v_tgt = np.array([speed * np.cos(phi), speed * np.sin(phi), 0])                # :93
+    c, s = np.cos(phi), np.sin(phi)
+    rot = np.array([[c, -s, 0], [s, c, 0], [0, 0, 1]])
+    pos0 = np.array([rot @ np.asarray(t["position"], dtype=np.float64) for t in base_targets])   # :99
+    rcs = np.array([t["rcs"] for t in base_targets], dtype=np.float64)
+    raw = dev.echo_accumulate(pos0, v_tgt, rcs, np.asarray(pos_sat, dtype=np.float64), None,
+                              np.asarray(t_vec, dtype=np.float64), c=prm.C, fc=prm.FC, k_rate=prm.k_rate, t_p=prm.T_p,
+                              t_start=t_start, fs=prm.FS, n_samples=n, device=device or _default_device,
+                              spotlight=(np.asarray(vel_sat, dtype=np.float64), np.pi * l_ant / prm.Lambda, t_fast))
+    return (raw if return_device else _to_host_c128(raw)), t_start, n, v_tgt
+
+
+_tdbp_plans: dict = {}
+
+
+def tdbp_gpu(raw_t, pos_plat, vel_plat, t_start, num_samples, vel_focus, t_pulses, scene_size, nx=512, ny=512, *,
+             params: RadarParams | None = None, device=None, return_device=False):
+    """Time-domain backprojection of one CPI (sar_batch_sim.py:171-238): complex128 image [ny, nx]."""
+    prm = _params(params)
+    device = device or _default_device
+    if torch.is_tensor(raw_t):
+        x = raw_t if raw_t.dtype == torch.complex64 else dev.narrow_c128(raw_t.to(torch.complex128).contiguous())
+        x = x.to(device) if not x.is_cuda else x
+    else:
+        h = np.ascontiguousarray(raw_t)
+        x = torch.from_numpy(h).to(device) if h.dtype == np.complex64 else \
+            dev.narrow_c128(torch.from_numpy(h.astype(np.complex128, copy=False)).to(device))
+    key = (prm.C, prm.FC, prm.k_rate, prm.T_p, prm.FS, float(t_start), int(num_samples), float(scene_size), int(nx), int(ny),
+           x.device.index)
+    plan = _tdbp_plans.get(key)
+    if plan is None:
+        if len(_tdbp_plans) >= 4:
+            _tdbp_plans.pop(next(iter(_tdbp_plans))).close()
+        plan = dev.TdbpPlan(c=prm.C, fc=prm.FC, k_rate=prm.k_rate, t_p=prm.T_p, fs=prm.FS, t_start=float(t_start),
+                            n_samples=int(num_samples), scene_size=float(scene_size), nx=nx, ny=ny, device=x.device)
+        _tdbp_plans[key] = plan
+    img = plan.backproject(plan.range_compress(x), pos_plat, vel_plat, t_pulses, vel_focus)
+    return img if return_device else img.cpu().numpy()
+
+
 # ------------------------------------------------------------------------------------------- CSA
 def sar_focus_csa(phist, center_wavelength_m, pulse_width_sec, chirp_rate_hzpsec, sample_rate_hz, prf_hz,
                   platform_speed_mps, range_ref_m, t_start_fast, *, device=None, return_device=False):

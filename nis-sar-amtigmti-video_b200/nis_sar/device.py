@@ -48,11 +48,13 @@ def chunk_hint(*_args, **_kw) -> int:
 
 
 def echo_accumulate(pos0, vel, rcs, pos_tx, pos_rx, t_slow, *, c, fc, k_rate, t_p, t_start, fs, n_samples,
-                    device="cuda", out=None, accumulate=False, pulse_range=None):
+                    device="cuda", out=None, accumulate=False, pulse_range=None, spotlight=None):
     """K1.  Inputs are numpy / torch fp64 arrays (host or device); returns raw[P, S] complex64 on
     ``device``.  ``vel`` is one xyz triple or a [T,3] array; ``pos_rx`` None selects the monostatic
     delay 2|p - p_tx|/c.  ``pulse_range=(p0, p1)`` restricts the rows that are computed (the pulse
-    block of one rank); rows outside are left untouched."""
+    block of one rank); rows outside are left untouched.  ``spotlight=(vel_sat[P,3], pi l_ant / lambda, t_fast[S])``
+    selects the run_physics_spotlight model (sar_batch_sim.py:83-169): start-stop corrected delay, sinc^2 pattern,
+    amplitude rcs (not its square root), chirp centred on the delay, sample times t_start + n / fs."""
     di = _dev_index(device)
     dev = torch.device("cuda", di)
     lib = _lib.load()
@@ -63,7 +65,8 @@ def echo_accumulate(pos0, vel, rcs, pos_tx, pos_rx, t_slow, *, c, fc, k_rate, t_
         vel_np = np.asarray(vel.cpu().numpy() if torch.is_tensor(vel) else vel, dtype=np.float64)
         per_target = int(vel_np.size == 3 * T and vel_np.ndim == 2 and T > 1)
         vel_d = _f64(vel_np.reshape(-1), dev)
-        amp_d = _f64(np.sqrt(np.asarray(rcs.cpu().numpy() if torch.is_tensor(rcs) else rcs, dtype=np.float64)).reshape(-1), dev)
+        rcs_np = np.asarray(rcs.cpu().numpy() if torch.is_tensor(rcs) else rcs, dtype=np.float64).reshape(-1)
+        amp_d = _f64(rcs_np if spotlight is not None else np.sqrt(rcs_np), dev)
         if amp_d.shape[0] != T:
             raise NisError(f"echo_accumulate: {T} positions but {amp_d.shape[0]} rcs values")
         ptx_d = _f64(np.asarray(pos_tx).reshape(-1, 3), dev)
@@ -73,8 +76,10 @@ def echo_accumulate(pos0, vel, rcs, pos_tx, pos_rx, t_slow, *, c, fc, k_rate, t_
         if ts_d.shape[0] != P or (prx_d is not None and prx_d.shape[0] != P):
             raise NisError("echo_accumulate: pos_tx / pos_rx / t_slow disagree on the number of pulses")
         S = int(n_samples)
-        t_fast = fast_time_axis(t_start, S, fs)
+        t_fast = fast_time_axis(t_start, S, fs) if spotlight is None else np.asarray(spotlight[2], dtype=np.float64)
         tf_d = _f64(t_fast, dev)
+        if spotlight is not None:
+            prx_d = _f64(np.asarray(spotlight[0], dtype=np.float64).reshape(-1, 3), dev)   # platform velocity per pulse
         if out is None:
             out = torch.zeros((P, S), dtype=torch.complex64, device=dev)
             accumulate = False if pulse_range is None else accumulate
@@ -82,11 +87,18 @@ def echo_accumulate(pos0, vel, rcs, pos_tx, pos_rx, t_slow, *, c, fc, k_rate, t_
             raise NisError("echo_accumulate: out must be a contiguous complex64 [P, S] tensor")
         p0, p1 = (0, P) if pulse_range is None else pulse_range
         prm = _lib.EchoParams(c=c, fc=fc, k_rate=k_rate, t_p=t_p, t_start=float(t_fast[0]),
-                              dt_fast=(S / fs) / (S - 1) if S > 1 else 1.0 / fs,
+                              dt_fast=((S / fs) / (S - 1) if S > 1 else 1.0 / fs) if spotlight is None else 1.0 / fs,
                               per_target_velocity=per_target,
-                              samples_per_thread=chunk_hint(pos0_d, ptx_d, t_fast, t_p, c, prx_d))
+                              samples_per_thread=chunk_hint(pos0_d, ptx_d, t_fast, t_p, c,
+                                                            prx_d if spotlight is None else None))
         for q0 in range(p0, p1, MAX_PULSES_PER_LAUNCH):
             q1 = min(p1, q0 + MAX_PULSES_PER_LAUNCH)
+            if spotlight is not None:
+                rc = lib.nis_echo_spotlight(ctx, C.byref(prm), _ptr(pos0_d), _ptr(vel_d), _ptr(amp_d), _ptr(ptx_d),
+                                            _ptr(prx_d), _ptr(ts_d), _ptr(tf_d), T, q0, q1, S, float(spotlight[1]),
+                                            _ptr(out), 1 if accumulate else 0, C.c_void_p(_stream_ptr(di)))
+                _lib.check(rc, "nis_echo_spotlight")
+                continue
             rc = lib.nis_echo_accumulate(ctx, C.byref(prm), _ptr(pos0_d), _ptr(vel_d), _ptr(amp_d), _ptr(ptx_d),
                                          _ptr(prx_d), _ptr(ts_d), _ptr(tf_d), T, q0, q1, S, _ptr(out),
                                          1 if accumulate else 0, C.c_void_p(_stream_ptr(di)))
@@ -262,6 +274,63 @@ def cached_rda_plan(n_pulses, n_ranges, **kw) -> RdaPlan:
         pl = RdaPlan(n_pulses, n_ranges, **kw)
         _rda_plan_cache[key] = pl
     return pl
+
+
+# ------------------------------------------------------------------------------------- TDBP
+class TdbpPlan:
+    """Time-domain backprojection plan (tdbp_gpu, sar_batch_sim.py:171-238): reference-chirp block spectrum, pixel axes."""
+
+    def __init__(self, *, c, fc, k_rate, t_p, fs, t_start, n_samples, scene_size, nx=512, ny=512, device="cuda"):
+        self.di = _dev_index(device)
+        self.n_samples, self.nx, self.ny = int(n_samples), int(nx), int(ny)
+        prm = _lib.TdbpParams(c=c, fc=fc, k_rate=k_rate, t_p=t_p, fs=fs, t_start=t_start, scene_size=scene_size,
+                              n_samples=self.n_samples, nx=self.nx, ny=self.ny, reserved=0)
+        h = C.c_void_p()
+        with torch.cuda.device(self.di):
+            _lib.check(_lib.load().nis_tdbp_plan_create(_lib.context(self.di), C.byref(prm), C.byref(h)), "nis_tdbp_plan_create")
+        self._h = h
+
+    def range_compress(self, raw):
+        """raw: complex64 CUDA [P, n_samples] -> range-compressed pulses, same shape."""
+        if raw.dtype != torch.complex64 or raw.dim() != 2 or raw.stride(1) != 1 or raw.shape[1] != self.n_samples:
+            raise NisError("TdbpPlan.range_compress: raw must be complex64 [P, n_samples] with unit column stride")
+        rc_t = torch.empty((raw.shape[0], self.n_samples), dtype=torch.complex64, device=raw.device)
+        with torch.cuda.device(self.di):
+            _lib.check(_lib.load().nis_tdbp_range_compress(self._h, _ptr(raw), raw.stride(0), raw.shape[0], _ptr(rc_t),
+                                                          C.c_void_p(_stream_ptr(self.di))), "nis_tdbp_range_compress")
+        return rc_t
+
+    def backproject(self, rc_t, pos_plat, vel_plat, t_pulses, vel_focus, pulse_range=None, out=None, accumulate=False):
+        """Sum pulses ``pulse_range`` (default: all) of the range-compressed CPI into the [ny, nx] complex128 image."""
+        dev = rc_t.device
+        P = rc_t.shape[0]
+        pos_d, vel_d = _f64(np.asarray(pos_plat).reshape(-1, 3), dev), _f64(np.asarray(vel_plat).reshape(-1, 3), dev)
+        t_np = np.asarray(t_pulses, dtype=np.float64).reshape(-1)
+        tp_d = _f64(t_np, dev)
+        if pos_d.shape[0] != P or vel_d.shape[0] != P or t_np.shape[0] != P:
+            raise NisError("TdbpPlan.backproject: platform arrays disagree with the number of pulses")
+        if out is None:
+            out = torch.empty((self.ny, self.nx), dtype=torch.complex128, device=dev)
+            accumulate = False
+        p0, p1 = (0, P) if pulse_range is None else pulse_range
+        vf = (C.c_double * 3)(*[float(v) for v in np.asarray(vel_focus, dtype=np.float64).reshape(3)])
+        with torch.cuda.device(self.di):
+            rc = _lib.load().nis_tdbp_backproject(self._h, _ptr(rc_t), _ptr(pos_d), _ptr(vel_d), _ptr(tp_d), P, int(p0), int(p1),
+                                                  float(np.mean(t_np)), C.cast(vf, C.c_void_p), _ptr(out),
+                                                  1 if accumulate else 0, C.c_void_p(_stream_ptr(self.di)))
+        _lib.check(rc, "nis_tdbp_backproject")
+        return out
+
+    def close(self):
+        if self._h is not None:
+            _lib.load().nis_tdbp_plan_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 # ------------------------------------------------------------------------------------ noise

@@ -88,3 +88,8 @@ def airborne_vehicle_preset() -> RadarParams:
     return RadarParams(FC=10e9, BW=300e6, T_p=1.0e-6, FS=360e6, PRF=1.0 / 500e-6, R0=R0,
                        V_sat=150.0, V_eff=150.0, R_sat=0.0, Re=Re, gamma_rad=0.0,
                        window_s=2048 / 360e6, n_samples=2048)
+
+
+def batch_spotlight_preset(fs: float = 600e6, bw: float = 500e6, t_p: float = 20e-6, prf: float = 5000.0) -> RadarParams:
+    """The constants block of sar_batch_sim.py:12-38 (same orbit as the spaceborne preset, PRF 5 kHz)."""
+    return spaceborne_preset(fs=fs, bw=bw, t_p=t_p, prf=prf)

@@ -218,6 +218,33 @@ def golden_viewer():
     np.savez_compressed(os.path.join(OUT, "viewer.npz"), **out)
 
 
+def batch_globals(fs=60e6, bw=50e6, t_p=2e-6):
+    prm = params.spaceborne_preset()
+    return {"C": prm.C, "R0": prm.R0, "FC": 9.65e9, "T_P": t_p, "K_RATE": bw / t_p, "FS": fs, "Lambda": prm.C / 9.65e9}
+
+
+def golden_spotlight_tdbp():
+    """run_physics_spotlight + tdbp_gpu of sar_batch_sim.py on the CPU (torch): a 48-pulse CPI of the destroyer moving at
+    15 m/s on heading 45 deg, backprojected on a 24 x 24 grid with and without target-motion focusing (mBP / StdBP)."""
+    from nis_sar import targets as tg
+    g = batch_globals()
+    spot, tdbp = ref_extract.batch_functions(g)
+    prm = params.spaceborne_preset(prf=5000.0)
+    n_p = 48
+    t_vec = (np.arange(n_p) - (n_p - 1) / 2) / 5000.0 + 0.03
+    pos_sat, vel_sat = scenes.orbit_trajectory(prm, t_vec, along="x")
+    base = tg.generate_destroyer(center_pos=(0, 0, 0))[::2]
+    l_ant = g["Lambda"] * g["R0"] / 500.0
+    raw, t_st, n_sp, v_tgt = spot(base, t_vec, pos_sat, vel_sat, heading_deg=45, speed=15.0, l_ant=l_ant)
+    out = {"g_keys": np.array(list(g.keys())), "g_vals": np.array(list(g.values())), "t_vec": t_vec, "pos_sat": pos_sat,
+           "vel_sat": vel_sat, "l_ant": l_ant, "raw": raw.numpy().astype(np.complex64), "t_start": t_st, "n_samples": n_sp,
+           "v_tgt": v_tgt, "pos0": np.array([t["position"] for t in base], dtype=float),
+           "rcs": np.array([t["rcs"] for t in base], dtype=float)}
+    for tag, vf in (("mbp", v_tgt), ("stdbp", np.zeros(3))):
+        out["img_" + tag] = tdbp(raw, pos_sat, vel_sat, t_st, n_sp, vel_focus=vf, t_pulses=t_vec, scene_size=500.0, nx=24, ny=24)
+    np.savez_compressed(os.path.join(OUT, "spotlight_tdbp.npz"), **out)
+
+
 if __name__ == "__main__":
     if not ref_extract.reference_available():
         sys.exit("reference tree not found: fixtures can only be regenerated in the build container")
@@ -229,5 +256,6 @@ if __name__ == "__main__":
     golden_rda()
     golden_noise()
     golden_viewer()
+    golden_spotlight_tdbp()
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))

@@ -162,3 +162,13 @@ def viewer_sardata_class():
     ns = {"np": np}
     exec(compile(ast.Module(body=[nodes[0]], type_ignores=[]), path, "exec"), ns)
     return ns["SARData"]
+
+
+def batch_functions(g: dict):
+    """``run_physics_spotlight`` and ``tdbp_gpu`` of sar_batch_sim.py (:83-169, :171-238) on the CPU, bound to the module
+    constants in ``g`` (C, R0, FC, T_P, K_RATE, FS, Lambda)."""
+    import torch
+    ns = {"np": np, "torch": torch, "device": torch.device("cpu")}
+    ns.update({k: g[k] for k in ("C", "R0", "FC", "T_P", "K_RATE", "FS", "Lambda")})
+    f = _extract("sar_batch_sim.py", ("run_physics_spotlight", "tdbp_gpu"), ns)
+    return _quiet(f["run_physics_spotlight"]), _quiet(f["tdbp_gpu"])

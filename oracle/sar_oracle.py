@@ -354,3 +354,111 @@ def viewer_visible_stats(prods, mode, scale, c_indices, r_indices):
         vmax = np.percentile(data, 99.9)
         out["clim"] = (vmax - 60 if scale == "dB" else 0, vmax)
     return out
+
+
+# ---------------------------------------------------------------------------- spotlight echo + backprojection (8f, N4)
+def spotlight_window(g):
+    """Receive window of ``run_physics_spotlight`` (sar_batch_sim.py:85-90): 2 km of swath + pulse + 10 us, an even
+    number of samples, centred on the scene-centre delay.  g: dict with C, R0, T_P, FS."""
+    win_len = (2000.0 / g["C"]) + g["T_P"] + 10e-6
+    n = int(np.ceil(win_len * g["FS"]))
+    if n % 2 != 0:
+        n += 1
+    t_start = 2 * g["R0"] / g["C"] - win_len / 2
+    return t_start, n
+
+
+def echo_spotlight(pos0, rcs, t_vec, pos_sat, vel_sat, heading_deg, speed, l_ant, g):
+    """``run_physics_spotlight`` (sar_batch_sim.py:83-169).  Target block rotated by the heading and moving at
+    ``speed`` along it (:92-100); start-stop corrected two-way delay: the receive position is the platform advanced by
+    v_sat * 2 d_tx / c (:133-137); one-way sinc^2 pattern of an aperture l_ant steered at the scene centre (:139-149);
+    amplitude rcs * gain (NOT sqrt); chirp centred ON the delay: pi K (t - tau)^2 - 2 pi FC tau for |t - tau| <= T_P/2
+    (:151-155).  g: dict with C, R0, FC, T_P, K_RATE, FS, Lambda.  Returns (raw[P, S], t_start, S, v_tgt)."""
+    t_start, n = spotlight_window(g)
+    t_fast = t_start + np.arange(n) / g["FS"]
+    phi = np.radians(heading_deg)
+    v_tgt = np.array([speed * np.cos(phi), speed * np.sin(phi), 0])
+    c, s = np.cos(phi), np.sin(phi)
+    rot = np.array([[c, -s, 0], [s, c, 0], [0, 0, 1]])
+    p0 = np.array([rot @ np.asarray(p, dtype=float) for p in pos0])
+    rcs = np.asarray(rcs, dtype=float)
+    raw = np.zeros((len(t_vec), n), dtype=complex)
+    for i, t in enumerate(t_vec):
+        p_tgt = p0 + v_tgt[None, :] * t
+        diff_tx = p_tgt - pos_sat[i][None, :]
+        dist_tx = np.linalg.norm(diff_tx, axis=1)
+        p_rx = pos_sat[i][None, :] + vel_sat[i][None, :] * (2 * dist_tx / g["C"])[:, None]
+        dist_rx = np.linalg.norm(p_tgt - p_rx, axis=1)
+        tau = (dist_tx + dist_rx) / g["C"]
+        b_vec = -pos_sat[i]
+        look = b_vec / np.linalg.norm(b_vec)
+        cos_off = np.clip((diff_tx / dist_tx[:, None]) @ look, -1, 1)
+        x = np.pi * l_ant * np.sin(np.arccos(cos_off)) / g["Lambda"]
+        gain = np.ones_like(x)
+        m = np.abs(x) > 1e-6
+        gain[m] = (np.sin(x[m]) / x[m]) ** 2
+        t_local = t_fast[None, :] - tau[:, None]
+        mask = np.abs(t_local) <= (g["T_P"] / 2)
+        phase = np.pi * g["K_RATE"] * t_local ** 2 - 2 * np.pi * g["FC"] * tau[:, None]
+        raw[i] = np.sum((rcs * gain)[:, None] * np.exp(1j * phase) * mask, axis=0)
+    return raw, t_start, n, v_tgt
+
+
+def tdbp_range_compress(raw, g, num_samples):
+    """Circular matched filtering of ``tdbp_gpu`` (sar_batch_sim.py:179-185): the reference chirp has int(T_P FS) taps on
+    linspace(-T_P/2, T_P/2), is fftshifted, zero-padded to num_samples, and correlated through length-num_samples FFTs."""
+    n_ref = int(g["T_P"] * g["FS"])
+    t_ref = np.linspace(-g["T_P"] / 2, g["T_P"] / 2, n_ref)
+    ref_f = np.fft.fft(np.fft.fftshift(np.exp(1j * np.pi * g["K_RATE"] * t_ref ** 2)), n=num_samples)
+    return np.fft.ifft(np.fft.fft(raw, n=num_samples, axis=1) * np.conj(ref_f)[None, :], axis=1)
+
+
+def grid_sample_row_f32(row_f32, x_norm_f32):
+    """torch.nn.functional.grid_sample(input[1, 1, 1, W], grid(x, y=0), bilinear, zeros padding, align_corners=False)
+    as the CPU kernel evaluates it in float32: ix = fma(x + 1, W, -1) / 2 (ONE rounding of the multiply-subtract --
+    pinned against torch in oracle/make_golden.py), neighbours floor(ix) and +1 with weights (i0 + 1 - ix), (ix - i0),
+    out-of-range neighbours contribute zero."""
+    f32 = np.float32
+    w = row_f32.shape[-1]
+    xp1 = (x_norm_f32.astype(f32) + f32(1)).astype(f32)
+    ix = ((xp1.astype(np.float64) * w - 1.0).astype(f32) / f32(2)).astype(f32)    # the fp64 product is exact: one rounding
+    i0 = np.floor(ix)
+    w1 = (ix - i0).astype(f32)
+    w0 = ((i0 + f32(1)) - ix).astype(f32)
+    i0 = i0.astype(np.int64)
+    i1 = i0 + 1
+    a = np.where((i0 >= 0) & (i0 < w), row_f32[np.clip(i0, 0, w - 1)], f32(0)).astype(row_f32.dtype)
+    b = np.where((i1 >= 0) & (i1 < w), row_f32[np.clip(i1, 0, w - 1)], f32(0)).astype(row_f32.dtype)
+    return a * w0 + b * w1
+
+
+def tdbp(raw, pos_plat, vel_plat, t_start, num_samples, vel_focus, t_pulses, scene_size, g, nx=512, ny=512):
+    """Time-domain backprojection, ``tdbp_gpu`` (sar_batch_sim.py:171-238).  Per pixel and pulse (fp64): the pixel moves
+    with vel_focus about the CPI centre (:207-209); two-way delay with the start-stop correction on both ends (:219-223);
+    a range-Doppler coupling shift -FC (2 v_rad / C) / K_RATE (:214-217); the range-compressed pulse is sampled at
+    (tau - t_start + t_shift) FS - 0.5 by float32 linear interpolation (grid_sample, align_corners=False, :225-230);
+    x exp(j 2 pi FC tau), summed over pulses in complex128 (:232-235).  Returns [ny, nx]."""
+    rc = tdbp_range_compress(np.asarray(raw), g, num_samples)
+    rc_re, rc_im = rc.real.astype(np.float32), rc.imag.astype(np.float32)
+    x_axis = np.linspace(-scene_size / 2, scene_size / 2, nx)
+    y_axis = np.linspace(-scene_size / 2, scene_size / 2, ny)
+    gx, gy = np.meshgrid(x_axis, y_axis, indexing="xy")
+    grid = np.stack((gx.ravel(), gy.ravel(), np.zeros(gx.size)), axis=1)
+    v_f = np.asarray(vel_focus, dtype=float)
+    t_p = np.asarray(t_pulses, dtype=float)
+    dt = t_p - np.mean(t_p)
+    img = np.zeros(grid.shape[0], dtype=complex)
+    for k in range(len(t_p)):
+        gk = grid + v_f[None, :] * dt[k]
+        diff_tx = gk - pos_plat[k][None, :]
+        dist_tx = np.linalg.norm(diff_tx, axis=1)
+        v_rad = (diff_tx / dist_tx[:, None]) @ (vel_plat[k] - v_f)
+        t_shift = (-g["FC"] * (2 * v_rad / g["C"])) / g["K_RATE"]
+        tau_a = 2 * dist_tx / g["C"]
+        pos_rx = pos_plat[k][None, :] + vel_plat[k][None, :] * tau_a[:, None]
+        g_rx = gk + v_f[None, :] * tau_a[:, None]
+        tau = (dist_tx + np.linalg.norm(g_rx - pos_rx, axis=1)) / g["C"]
+        idx_norm = (2 * (((tau - t_start + t_shift) * g["FS"]) / num_samples) - 1).astype(np.float32)
+        samp = grid_sample_row_f32(rc_re[k], idx_norm).astype(np.float64) + 1j * grid_sample_row_f32(rc_im[k], idx_norm).astype(np.float64)
+        img += samp * np.exp(1j * (2 * np.pi * g["FC"] * tau))
+    return img.reshape(ny, nx)

@@ -597,3 +597,59 @@ def test_viewer_products_stats_and_clim(api, tmp_path):
                 assert abs(got["cancellation_ratio"] / want["cancellation_ratio"] - 1) < 1e-5
             lo, hi = sar.clim(mode, scale, c_idx, r_idx)
             assert abs(hi - want["clim"][1]) <= 2e-5 * max(1.0, abs(hi)) and abs(lo - want["clim"][0]) <= 2e-5 * max(1.0, abs(lo))
+
+
+# ------------------------------------------------------------------------------------------ spotlight + TDBP (8f, N4)
+def _batch_params(fs, bw, t_p):
+    return params.batch_spotlight_preset(fs=fs, bw=bw, t_p=t_p)
+
+
+def _batch_globals(prm):
+    return {"C": prm.C, "R0": prm.R0, "FC": prm.FC, "T_P": prm.T_p, "K_RATE": prm.k_rate, "FS": prm.FS, "Lambda": prm.Lambda}
+
+
+def test_spotlight_echo_and_tdbp_golden(api):
+    """run_physics_spotlight and tdbp_gpu against the outputs of sar_batch_sim.py's own functions (torch, CPU)."""
+    g = np.load(os.path.join(GOLDEN, "spotlight_tdbp.npz"))
+    G = dict(zip(g["g_keys"], g["g_vals"].astype(float)))
+    prm = _batch_params(G["FS"], G["K_RATE"] * G["T_P"], G["T_P"])
+    base = [{"position": p, "rcs": r} for p, r in zip(g["pos0"], g["rcs"])]
+    raw, t0, n, vt = api.run_physics_spotlight(base, g["t_vec"], g["pos_sat"], g["vel_sat"], 45.0, 15.0, float(g["l_ant"]),
+                                               params=prm)
+    assert t0 == float(g["t_start"]) and n == int(g["n_samples"]) and np.allclose(vt, g["v_tgt"], rtol=0, atol=1e-12)
+    r = raw.cpu().numpy()
+    print(f"spotlight echo rel-L2 {_rel(r, g['raw']):.3e}")
+    assert _rel(r, g["raw"]) < TOL_L2
+    assert np.array_equal(r != 0, g["raw"] != 0)
+    for tag, vf in (("mbp", g["v_tgt"]), ("stdbp", np.zeros(3))):
+        img = api.tdbp_gpu(g["raw"], g["pos_sat"], g["vel_sat"], t0, n, vf, g["t_vec"], 500.0, nx=24, ny=24, params=prm)
+        assert img.dtype == np.complex128 and img.shape == (24, 24)
+        print(f"TDBP {tag}: rel-L2 {_rel(img, g['img_' + tag]):.3e}")
+        assert _rel(img, g["img_" + tag]) < TOL_L2, tag
+        assert np.unravel_index(np.argmax(np.abs(img)), img.shape) == np.unravel_index(np.argmax(np.abs(g["img_" + tag])), img.shape)
+
+
+@pytest.mark.parametrize("fs,bw,t_p,n_pulses,n_pix", [(60e6, 50e6, 2e-6, 160, 40), (600e6, 500e6, 20e-6, 40, 32)])
+def test_spotlight_tdbp_vs_oracle(api, fs, bw, t_p, n_pulses, n_pix):
+    """A CPI through echo synthesis -> circular range compression -> backprojection against the numpy oracle; the second
+    case is the reference's real window (22004 samples, 12000-tap chirp: six overlap-save blocks of 16384)."""
+    from nis_sar import scenes, targets as tg
+    prm = _batch_params(fs, bw, t_p)
+    G = _batch_globals(prm)
+    t_vec = (np.arange(n_pulses) - (n_pulses - 1) / 2) / prm.PRF - 0.2
+    pos_sat, vel_sat = scenes.orbit_trajectory(prm, t_vec, along="x")
+    base = tg.generate_destroyer(center_pos=(0, 0, 0))
+    l_ant = prm.Lambda * prm.R0 / 500.0
+    raw, t0, n, vt = api.run_physics_spotlight(base, t_vec, pos_sat, vel_sat, 135.0, 15.0, l_ant, params=prm)
+    pos0 = np.array([t["position"] for t in base], dtype=float)
+    rcs = np.array([t["rcs"] for t in base], dtype=float)
+    oraw, ot0, on, ovt = orc.echo_spotlight(pos0, rcs, t_vec, pos_sat, vel_sat, 135.0, 15.0, l_ant, G)
+    assert (t0, n) == (ot0, on) and np.array_equal(vt, ovt)
+    e_echo = _rel(raw.cpu().numpy(), oraw)
+    for vf in (vt, np.zeros(3)):
+        img = api.tdbp_gpu(raw, pos_sat, vel_sat, t0, n, vf, t_vec, 500.0, nx=n_pix, ny=n_pix, params=prm)
+        ref = orc.tdbp(raw.cpu().numpy().astype(np.complex128), pos_sat, vel_sat, t0, n, vf, t_vec, 500.0, G, nx=n_pix, ny=n_pix)
+        e = _rel(img, ref)
+        print(f"spotlight {n_pulses} pulses x {n} samples: echo {e_echo:.2e}, TDBP(vf={'tgt' if np.any(vf) else '0'}) {e:.2e}")
+        assert e < TOL_L2
+    assert e_echo < TOL_L2

@@ -205,3 +205,18 @@ def test_viewer_products_match_reference():
         for m in orc.VIEWER_MODES:
             assert np.array_equal(o[m], g[tag + m]), m
     assert float(g["cal_phase"]) == orc.balance_phase(g["s1"], g["s2"])
+
+
+# ------------------------------------------------------------------------------------------ spotlight + TDBP (N4)
+def test_spotlight_echo_and_tdbp_match_reference():
+    """oracle.echo_spotlight / oracle.tdbp against run_physics_spotlight / tdbp_gpu of sar_batch_sim.py run on the CPU
+    (torch) in the build container -- including torch's float32 grid_sample arithmetic."""
+    g = _load("spotlight_tdbp.npz")
+    G = dict(zip(g["g_keys"], g["g_vals"].astype(float)))
+    raw, t0, n, vt = orc.echo_spotlight(g["pos0"], g["rcs"], g["t_vec"], g["pos_sat"], g["vel_sat"], 45, 15.0,
+                                        float(g["l_ant"]), G)
+    assert t0 == float(g["t_start"]) and n == int(g["n_samples"]) and np.array_equal(vt, g["v_tgt"])
+    assert _rel(raw, g["raw"]) < 1e-7 and np.array_equal(raw != 0, g["raw"] != 0)
+    for tag, vf in (("mbp", g["v_tgt"]), ("stdbp", np.zeros(3))):
+        img = orc.tdbp(raw, g["pos_sat"], g["vel_sat"], t0, n, vf, g["t_vec"], 500.0, G, nx=24, ny=24)
+        assert _rel(img, g["img_" + tag]) < 1e-6, tag
