@@ -252,12 +252,14 @@ NIS_API int nis_region_select(nis_ctx* ctx, const float* map, int64_t pitch, int
  * Replaces add_ocean_noise (sar_satellite_sim.py:331-344 and its copies sar_vehicle_sim.py:152-165,
  * sar_satellite_moving_sim.py:188-206) and generate_noise_tensor (sar_batch_sim.py:65-81): complex Gaussian thermal
  * noise at P / 10^(snr_db/10) plus K-distributed clutter (Gamma(k_nu, 1/k_nu) texture x Exp(1) speckle, uniform phase)
- * at P / 10^(scr_db/10).  P = *power_sum_dev / n when power_sum_dev != NULL (the output of nis_power_sum: no host
- * round trip), else ref_power.  accumulate != 0: x += noise (add_ocean_noise); 0: x = noise (generate_noise_tensor).
+ * at P / 10^(scr_db/10).  P = *power_dev * power_value when power_dev != NULL -- the output of nis_power_sum with
+ * power_value = 1/n (mean power, add_ocean_noise) or of nis_power_max with power_value = 1 (peak power, sar_batch_sim.py:317):
+ * no host round trip -- else P = power_value.  accumulate != 0: x += noise; 0: x = noise (generate_noise_tensor).
  * Counter-based generator (Philox4x32-10 keyed by seed, counter = sample index): reproducible, launch-shape independent.
  */
 NIS_API int nis_power_sum(nis_ctx* ctx, const nis_c32* x, uint64_t n, double* sum_dev /* dev, 1 double */, nis_stream stream);
-NIS_API int nis_noise_add(nis_ctx* ctx, nis_c32* x, uint64_t n, const double* power_sum_dev, double ref_power,
+NIS_API int nis_power_max(nis_ctx* ctx, const nis_c32* x, uint64_t n, double* max_dev /* dev, 1 double */, nis_stream stream);
+NIS_API int nis_noise_add(nis_ctx* ctx, nis_c32* x, uint64_t n, const double* power_dev, double power_value,
                   double snr_db, double scr_db, double k_nu, uint64_t seed, int32_t accumulate, nis_stream stream);
 
 /* ------------------------------------------------------------------ buffer format helpers

@@ -80,10 +80,18 @@ __global__ void __launch_bounds__(256) k_power_sum(const float2* __restrict__ x,
     }
 }
 
-__global__ void __launch_bounds__(256) k_noise_add(float2* __restrict__ x, uint64_t n, const double* __restrict__ power_sum,
-                                                   double ref_power, double inv_snr, double inv_scr, float k_nu,
+// |x|^2 is non-negative, so its fp64 bit pattern orders like an unsigned integer
+__global__ void __launch_bounds__(256) k_power_max(const float2* __restrict__ x, uint64_t n, double* __restrict__ out) {
+    double m = 0.0;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x)
+        m = fmax(m, sq_mag_f64(x[i]));
+    atomic_max_f64(out, warp_max_f64(m));
+}
+
+__global__ void __launch_bounds__(256) k_noise_add(float2* __restrict__ x, uint64_t n, const double* __restrict__ power_dev,
+                                                   double power_value, double inv_snr, double inv_scr, float k_nu,
                                                    uint2 key, int accumulate) {
-    const double p = power_sum != nullptr ? *power_sum / (double)n : ref_power;
+    const double p = power_dev != nullptr ? *power_dev * power_value : power_value;
     const float sig_n = (float)sqrt(0.5 * p * inv_snr);   // sqrt(noise_power / 2)
     const float pc = (float)(p * inv_scr);                 // clutter_power
     const float inv_nu = 1.0f / k_nu;
@@ -121,12 +129,25 @@ extern "C" int nis_power_sum(nis_ctx* ctx, const nis_c32* x, uint64_t n, double*
     return NIS_OK;
 }
 
+extern "C" int nis_power_max(nis_ctx* ctx, const nis_c32* x, uint64_t n, double* max_dev, nis_stream stream) {
+    NIS_REQUIRE(ctx && x && max_dev, "nis_power_max: null argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    NIS_CUDA_TRY(cudaMemsetAsync(max_dev, 0, sizeof(double), st));
+    if (n == 0) return NIS_OK;
+    uint64_t blocks = (n + 256 * 8 - 1) / (256 * 8);
+    const uint64_t cap = (uint64_t)ctx->num_sms * 8;
+    if (blocks > cap) blocks = cap;
+    k_power_max<<<(unsigned)blocks, 256, 0, st>>>(reinterpret_cast<const float2*>(x), n, max_dev);
+    NIS_LAUNCH_CHECK(ctx);
+    return NIS_OK;
+}
+
 extern "C" int nis_noise_add(nis_ctx* ctx, nis_c32* x, uint64_t n, const double* power_sum_dev, double ref_power,
                              double snr_db, double scr_db, double k_nu, uint64_t seed, int32_t accumulate,
                              nis_stream stream) {
     NIS_REQUIRE(ctx && x, "nis_noise_add: null argument");
     NIS_REQUIRE(k_nu > 0, "nis_noise_add: the K-distribution shape must be positive (got %g)", k_nu);
-    NIS_REQUIRE(power_sum_dev != nullptr || ref_power >= 0, "nis_noise_add: negative reference power");
+    NIS_REQUIRE(ref_power >= 0, "nis_noise_add: negative reference power / power scale");
     if (n == 0) return NIS_OK;
     cudaStream_t st = (cudaStream_t)stream;
     uint64_t blocks = (n + 256 * 4 - 1) / (256 * 4);

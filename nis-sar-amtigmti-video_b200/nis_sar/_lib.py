@@ -79,6 +79,7 @@ SIGNATURES = {
     "nis_region_stats": (C.c_int, [_P, _P, C.c_int64, C.c_int32, C.c_int32, C.c_int32, _P, _P]),
     "nis_region_select": (C.c_int, [_P, _P, C.c_int64, C.c_int32, C.c_int32, _P, C.c_int32, _P, _P]),
     "nis_power_sum": (C.c_int, [_P, _P, C.c_uint64, _P, _P]),
+    "nis_power_max": (C.c_int, [_P, _P, C.c_uint64, _P, _P]),
     "nis_noise_add": (C.c_int, [_P, _P, C.c_uint64, _P, C.c_double, C.c_double, C.c_double, C.c_double, C.c_uint64,
                                 C.c_int32, _P]),
     "nis_gmti_fused": (C.c_int, [_P, _P, _P, C.c_uint64, C.c_double, C.c_double,

@@ -242,10 +242,12 @@ def add_ocean_noise(raw_data, snr_db, scr_db=10.0, k_nu=1.0, *, seed=None, devic
 
 
 def generate_noise_tensor(shape, ref_power, snr_db, scr_db=10.0, k_nu=1.0, *, seed=None, device=None):
-    """Noise + clutter alone, for a given reference power (sar_batch_sim.py:65-81): a complex64 CUDA tensor."""
-    device = device or _default_device
+    """Noise + clutter alone, for a given reference power (sar_batch_sim.py:65-81): a complex64 CUDA tensor.
+    ``ref_power``: a number or a 1-element CUDA tensor (e.g. ``nis_sar.device.peak_power(raw_sig)``, :317)."""
+    device = device or (ref_power.device if torch.is_tensor(ref_power) and ref_power.is_cuda else _default_device)
     x = torch.empty(tuple(shape), dtype=torch.complex64, device=device)
-    return dev.add_noise(x, snr_db, scr_db, k_nu, _draw_seed(seed), ref_power=float(ref_power), accumulate=False)
+    return dev.add_noise(x, snr_db, scr_db, k_nu, _draw_seed(seed),
+                         ref_power=ref_power if torch.is_tensor(ref_power) else float(ref_power), accumulate=False)
 
 
 # ------------------------------------------------------------------------------------------- RDA

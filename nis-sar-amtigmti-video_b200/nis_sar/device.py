@@ -336,9 +336,9 @@ class TdbpPlan:
 # ------------------------------------------------------------------------------------ noise
 def add_noise(x, snr_db, scr_db=10.0, k_nu=1.0, seed=0, ref_power=None, accumulate=True):
     """Thermal noise + K-distributed clutter into the complex64 CUDA tensor ``x`` in place (add_ocean_noise,
-    sar_satellite_sim.py:331-344).  ``ref_power`` None: the mean power of ``x`` itself, reduced on the device and
-    consumed there (no host synchronisation).  ``accumulate`` False overwrites ``x`` with the noise alone
-    (generate_noise_tensor, sar_batch_sim.py:65-81)."""
+    sar_satellite_sim.py:331-344).  ``ref_power``: None = the mean power of ``x`` itself, "max" = its peak power
+    (sar_batch_sim.py:317) -- both reduced on the device and consumed there, no host synchronisation --, or a number.
+    ``accumulate`` False overwrites ``x`` with the noise alone (generate_noise_tensor, sar_batch_sim.py:65-81)."""
     if x.dtype != torch.complex64 or not x.is_contiguous():
         raise NisError("add_noise: x must be a contiguous complex64 CUDA tensor")
     di = x.device.index
@@ -346,14 +346,30 @@ def add_noise(x, snr_db, scr_db=10.0, k_nu=1.0, seed=0, ref_power=None, accumula
     n = x.numel()
     with torch.cuda.device(di):
         st = C.c_void_p(_stream_ptr(di))
-        psum = None
+        pdev, pval = None, 0.0
         if ref_power is None:
-            psum = torch.empty(1, dtype=torch.float64, device=x.device)
-            _lib.check(lib.nis_power_sum(ctx, _ptr(x), n, _ptr(psum), st), "nis_power_sum")
-        _lib.check(lib.nis_noise_add(ctx, _ptr(x), n, _ptr(psum), float(ref_power or 0.0), float(snr_db), float(scr_db),
-                                     float(k_nu), int(seed) & 0xFFFFFFFFFFFFFFFF, 1 if accumulate else 0, st),
-                   "nis_noise_add")
+            pdev, pval = torch.empty(1, dtype=torch.float64, device=x.device), 1.0 / max(n, 1)
+            _lib.check(lib.nis_power_sum(ctx, _ptr(x), n, _ptr(pdev), st), "nis_power_sum")
+        elif isinstance(ref_power, str) and ref_power == "max":
+            pdev, pval = torch.empty(1, dtype=torch.float64, device=x.device), 1.0
+            _lib.check(lib.nis_power_max(ctx, _ptr(x), n, _ptr(pdev), st), "nis_power_max")
+        elif torch.is_tensor(ref_power):
+            pdev, pval = ref_power.to(device=x.device, dtype=torch.float64).reshape(1).contiguous(), 1.0
+        else:
+            pval = float(ref_power)
+        _lib.check(lib.nis_noise_add(ctx, _ptr(x), n, _ptr(pdev), pval, float(snr_db), float(scr_db), float(k_nu),
+                                     int(seed) & 0xFFFFFFFFFFFFFFFF, 1 if accumulate else 0, st), "nis_noise_add")
     return x
+
+
+def peak_power(x):
+    """max |x|^2 of a complex64 CUDA tensor as a 1-element float64 CUDA tensor (sar_batch_sim.py:317)."""
+    di = x.device.index
+    out = torch.empty(1, dtype=torch.float64, device=x.device)
+    with torch.cuda.device(di):
+        _lib.check(_lib.load().nis_power_max(_lib.context(di), _ptr(x.contiguous()), x.numel(), _ptr(out),
+                                             C.c_void_p(_stream_ptr(di))), "nis_power_max")
+    return out
 
 
 # ------------------------------------------------------------------------------------- GMTI

@@ -653,3 +653,40 @@ def test_spotlight_tdbp_vs_oracle(api, fs, bw, t_p, n_pulses, n_pix):
         print(f"spotlight {n_pulses} pulses x {n} samples: echo {e_echo:.2e}, TDBP(vf={'tgt' if np.any(vf) else '0'}) {e:.2e}")
         assert e < TOL_L2
     assert e_echo < TOL_L2
+
+
+def test_videosar_frames_and_peak_power_noise(api, dev):
+    """The frame loop of sar_batch_sim.py:300-326: sliding CPI windows, per-frame echo -> (noise at the peak power) ->
+    backprojection; noise-free frames equal the oracle's, and the injected noise has the power the peak implies."""
+    import torch
+    from nis_sar import scenes, targets as tg, video
+    prm = params.batch_spotlight_preset(fs=60e6, bw=50e6, t_p=2e-6)
+    G = _batch_globals(prm)
+    total, step, cpi = 96, 16, 64
+    t_all = np.linspace(-0.01, 0.01, total)
+    pos_all, vel_all = scenes.orbit_trajectory(prm, t_all, along="x")
+    base = tg.generate_destroyer(center_pos=(0, 0, 0))[::3]
+    l_ant = prm.Lambda * prm.R0 / 500.0
+    kw = dict(heading_deg=90.0, speed=15.0, l_ant=l_ant, scene_size=500.0, step_pulses=step, cpi_pulses=cpi,
+              num_frames=10, nx=20, ny=20, params=prm)
+    assert video.cpi_windows(total, step, cpi, 10) == [(0, 64), (16, 80), (32, 96)]
+    frames = video.render_frames(base, t_all, pos_all, vel_all, focus_tgt=True, **kw)
+    assert sorted(frames) == [0, 1, 2]
+    pos0 = np.array([t["position"] for t in base], dtype=float)
+    rcs = np.array([t["rcs"] for t in base], dtype=float)
+    for f, (i0, i1) in enumerate(video.cpi_windows(total, step, cpi, 10)):
+        raw, t0, n, vt = orc.echo_spotlight(pos0, rcs, t_all[i0:i1], pos_all[i0:i1], vel_all[i0:i1], 90.0, 15.0, l_ant, G)
+        ref = orc.tdbp(raw.astype(np.complex64).astype(complex), pos_all[i0:i1], vel_all[i0:i1], t0, n, vt, t_all[i0:i1],
+                       500.0, G, nx=20, ny=20)
+        assert _rel(frames[f], ref) < TOL_L2, f
+    # peak-power referenced noise (sar_batch_sim.py:317-318)
+    raw, t0, n, vt = api.run_physics_spotlight(base, t_all[:cpi], pos_all[:cpi], vel_all[:cpi], 90.0, 15.0, l_ant, params=prm)
+    peak = float(dev.peak_power(raw).item())
+    assert abs(peak / float((raw.abs() ** 2).max().item()) - 1) < 1e-6
+    clean = raw.clone()
+    dev.add_noise(raw, 20.0, scr_db=15.0, seed=3, ref_power="max")
+    added = (raw - clean).cpu().numpy()
+    want = peak / 100.0 + peak / 10 ** 1.5
+    assert abs(np.mean(np.abs(added) ** 2) / want - 1) < 0.03
+    noise = api.generate_noise_tensor(clean.shape, dev.peak_power(clean), 20.0, scr_db=15.0, seed=3)
+    assert torch.equal(noise, raw - clean) or np.allclose(noise.cpu().numpy(), added, atol=1e-4 * np.sqrt(want))
