@@ -63,38 +63,69 @@ __global__ void __launch_bounds__(P::NT) k_tdbp_range(const float2* __restrict__
 // ------------------------------------------------------------------------------ backprojection
 struct TdbpConst {
     double c, inv_c, fc, k_rate, fs, t_start, t_centre, inv_w;
-    double x0, dx, y0, dy;     // pixel (i, j) sits at (x0 + i dx, y0 + j dy, 0); the last pixel of a row is pinned to -x0
+    double two_inv_c, xn_tau, xn_vrad, xn_0, fc_2p32;   // folded constants of the sample coordinate and the carrier phase
     double vfx, vfy, vfz;
     int nx, ny, n_pulses, W;
 };
 
-__global__ void __launch_bounds__(128) k_tdbp(TdbpConst k, const float2* __restrict__ rc, const double* __restrict__ pos,
-                                              const double* __restrict__ vel, const double* __restrict__ t_pulses,
-                                              const double* __restrict__ xs, const double* __restrict__ ys,
-                                              int p_begin, int p_end, double2* __restrict__ img, int accumulate) {
+// 1/sqrt(a) and sqrt(a) to within ~1 ulp without the DSQRT / DRCP sequences (~55 instructions) and -- after the first
+// pulse -- without touching the conversion / MUFU pipe at all: the seed y0 is the reciprocal distance of the previous
+// evaluation (pulse to pulse and transmit to receive the distance changes by ~1e-6 relative), refined by one third-order
+// step (error h^3: 1e-6 -> 1e-18) and one Heron correction of the root.  A float rsqrt seed (2^-22 -> 2^-66) serves the
+// first pulse and any caller whose consecutive pulses are not close (|h| test).
+__device__ __forceinline__ void rsqrt_sqrt(double a, double y0, double& rinv, double& root) {
+    double y = y0;
+    double h = fma(-a * y, y, 1.0);
+    if (fabs(h) > 1e-4) {
+        y = (double)rsqrtf((float)a);
+        h = fma(-a * y, y, 1.0);
+    }
+    y = fma(y * h, fma(0.375, h, 0.5), y);
+    const double r = a * y;
+    root = fma(0.5 * y, fma(-r, r, a), r);
+    rinv = y;
+}
+
+// per-pulse quantities that every pixel shares (6 doubles): the pixel-independent part of (pixel - platform) with the pixel
+// moved by the focusing velocity about the CPI centre (:207-210), and the platform velocity relative to the focused frame
+__global__ void k_tdbp_pulse_table(TdbpConst k, const double* __restrict__ pos, const double* __restrict__ vel,
+                                   const double* __restrict__ t_pulses, int n_pulses, double* __restrict__ tab) {
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= n_pulses) return;
+    const double dt = t_pulses[q] - k.t_centre;
+    tab[6 * q + 0] = k.vfx * dt - pos[3 * q];
+    tab[6 * q + 1] = k.vfy * dt - pos[3 * q + 1];
+    tab[6 * q + 2] = k.vfz * dt - pos[3 * q + 2];
+    tab[6 * q + 3] = vel[3 * q] - k.vfx;
+    tab[6 * q + 4] = vel[3 * q + 1] - k.vfy;
+    tab[6 * q + 5] = vel[3 * q + 2] - k.vfz;
+}
+
+__global__ void __launch_bounds__(64) k_tdbp(TdbpConst k, const float2* __restrict__ rc, const double* __restrict__ tab,
+                                             const double* __restrict__ xs, const double* __restrict__ ys, int p_begin,
+                                             int p_end, double2* __restrict__ img, int accumulate) {
     const int pix = blockIdx.x * blockDim.x + threadIdx.x;
     if (pix >= k.nx * k.ny) return;
     const double gx0 = xs[pix % k.nx], gy0 = ys[pix / k.nx];
     double ar = 0.0, ai = 0.0;
+    float pr = 0.f, pi = 0.f;        // fp32 partial sums, flushed into the fp64 accumulators every 8 pulses
+    double inv = 0.0;                // reciprocal distance carried from pulse to pulse (seed of the next one)
     const float wf = (float)k.W;
     for (int q = p_begin; q < p_end; ++q) {
-        const double dt = t_pulses[q] - k.t_centre;
-        const double px = pos[3 * q], py = pos[3 * q + 1], pz = pos[3 * q + 2];
-        const double vx = vel[3 * q], vy = vel[3 * q + 1], vz = vel[3 * q + 2];
-        // pixel moved with the focusing velocity about the CPI centre (:207-209)
-        const double gx = gx0 + k.vfx * dt, gy = gy0 + k.vfy * dt, gz = k.vfz * dt;
-        const double dx = gx - px, dy = gy - py, dz = gz - pz;
-        const double d_tx = sqrt(dx * dx + dy * dy + dz * dz);
-        const double inv = 1.0 / d_tx;
-        const double v_rad = ((vx - k.vfx) * dx + (vy - k.vfy) * dy + (vz - k.vfz) * dz) * inv;
-        const double t_shift = (-k.fc * (2.0 * v_rad * k.inv_c)) * (1.0 / k.k_rate);               // (:214-217)
-        const double ta = 2.0 * d_tx * k.inv_c;
-        // both ends advanced by the one-way-and-back flight time (:219-222)
-        const double ex = (gx + k.vfx * ta) - (px + vx * ta), ey = (gy + k.vfy * ta) - (py + vy * ta),
-                     ez = (gz + k.vfz * ta) - (pz + vz * ta);
-        const double tau = (d_tx + sqrt(ex * ex + ey * ey + ez * ez)) * k.inv_c;
-        const double idx_f = (tau - k.t_start + t_shift) * k.fs;
-        const float xn = (float)(2.0 * (idx_f * k.inv_w) - 1.0);                           // grid.float() (:228)
+        const double* tq = tab + 6 * q;                       // warp-uniform loads
+        const double dx = gx0 + tq[0], dy = gy0 + tq[1], dz = tq[2];
+        const double rvx = tq[3], rvy = tq[4], rvz = tq[5];
+        double d_tx;
+        rsqrt_sqrt(fma(dx, dx, fma(dy, dy, dz * dz)), inv, inv, d_tx);
+        const double v_rad = fma(rvx, dx, fma(rvy, dy, rvz * dz)) * inv;          // (v_plat - v_focus) . r_unit (:211-213)
+        const double ta = d_tx * k.two_inv_c;                                      // 2 d_tx / c
+        // both ends advanced by the flight time (:219-222): (g + v_f ta) - (p + v ta) = d - (v - v_f) ta
+        const double ex = fma(-rvx, ta, dx), ey = fma(-rvy, ta, dy), ez = fma(-rvz, ta, dz);
+        double d_rx, inv_rx;
+        rsqrt_sqrt(fma(ex, ex, fma(ey, ey, ez * ez)), inv, inv_rx, d_rx);
+        const double tau = (d_tx + d_rx) * k.inv_c;
+        // idx_norm = 2 ((tau - t_start + t_shift) FS / W) - 1 with t_shift = -FC (2 v_rad / C) / K_RATE (:214-226)
+        const float xn = (float)fma(tau, k.xn_tau, fma(v_rad, k.xn_vrad, k.xn_0));   // grid.float() (:228)
         // grid_sample, bilinear, zeros padding, align_corners=False, as the CPU kernel rounds it
         const float ix = __fmul_rn(__fmaf_rn(__fadd_rn(xn, 1.0f), wf, -1.0f), 0.5f);
         const float f0 = floorf(ix);
@@ -104,16 +135,22 @@ __global__ void __launch_bounds__(128) k_tdbp(TdbpConst k, const float2* __restr
         float2 a = make_float2(0.f, 0.f), b = make_float2(0.f, 0.f);
         if (i0 >= 0 && i0 < k.W) a = __ldg(row + i0);
         if (i0 + 1 >= 0 && i0 + 1 < k.W) b = __ldg(row + i0 + 1);
-        const double sr = (double)__fadd_rn(__fmul_rn(a.x, w0), __fmul_rn(b.x, w1));
-        const double si = (double)__fadd_rn(__fmul_rn(a.y, w0), __fmul_rn(b.y, w1));
-        // exp(j 2 pi FC tau): the carrier phase is ~4e7 turns -- reduced mod 1 in fp64, then a float sincos
-        double turns = k.fc * tau;
-        turns -= floor(turns);
-        float sn, cs;
-        sincospif(2.0f * (float)turns, &sn, &cs);
-        ar += sr * (double)cs - si * (double)sn;
-        ai += sr * (double)sn + si * (double)cs;
+        const float sr = __fadd_rn(__fmul_rn(a.x, w0), __fmul_rn(b.x, w1));
+        const float si = __fadd_rn(__fmul_rn(a.y, w0), __fmul_rn(b.y, w1));
+        // exp(j 2 pi FC tau): ~4e7 turns.  tau * (FC 2^32) < 2^63 keeps the fraction in the low 32 bits of the integer
+        // (7e-9 turns of resolution); two MUFU ops on the fixed-point fraction.  The rotated sample is formed in fp32
+        // (1e-7 relative, incoherent over the pulses), summed in fp32 over 8 pulses and then accumulated in fp64.
+        const float2 e = cis_u32((uint32_t)(unsigned long long)(long long)(tau * k.fc_2p32));
+        pr += fmaf(sr, e.x, -si * e.y);
+        pi += fmaf(sr, e.y, si * e.x);
+        if (((q - p_begin) & 7) == 7) {
+            ar += (double)pr;
+            ai += (double)pi;
+            pr = pi = 0.f;
+        }
     }
+    ar += (double)pr;
+    ai += (double)pi;
     if (accumulate) {
         img[pix].x += ar;
         img[pix].y += ai;
@@ -292,13 +329,27 @@ extern "C" int nis_tdbp_backproject(nis_tdbp_plan* pl, const nis_c32* rc, const 
                 p_begin, p_end, n_pulses);
     const nis_tdbp_params& p = pl->prm;
     TdbpConst k{};
+    {
+        const double shift_scale = (-p.fc * (2.0 / p.c)) / p.k_rate;      // t_shift per unit radial velocity
+        const double a = 2.0 * p.fs / (double)p.n_samples;               // d idx_norm / d time
+        k.two_inv_c = 2.0 / p.c;
+        k.xn_tau = a;
+        k.xn_vrad = a * shift_scale;
+        k.xn_0 = -p.t_start * a - 1.0;
+        k.fc_2p32 = p.fc * 4294967296.0;
+    }
     k.c = p.c; k.inv_c = 1.0 / p.c; k.inv_w = 1.0 / (double)p.n_samples; k.fc = p.fc; k.k_rate = p.k_rate; k.fs = p.fs; k.t_start = p.t_start; k.t_centre = t_centre;
     k.vfx = vel_focus_host[0]; k.vfy = vel_focus_host[1]; k.vfz = vel_focus_host[2];
     k.nx = p.nx; k.ny = p.ny; k.n_pulses = n_pulses; k.W = p.n_samples;
     const int n_pix = p.nx * p.ny;
-    k_tdbp<<<(n_pix + 127) / 128, 128, 0, (cudaStream_t)stream>>>(k, reinterpret_cast<const float2*>(rc), pos_plat, vel_plat,
-                                                                    t_pulses, pl->xs, pl->ys, p_begin, p_end,
-                                                                    reinterpret_cast<double2*>(image), accumulate);
+    cudaStream_t st = (cudaStream_t)stream;
+    int rc2 = pl->ctx->ensure_scratch((size_t)n_pulses * 6 * sizeof(double));
+    if (rc2 != NIS_OK) return rc2;
+    double* tab = reinterpret_cast<double*>(pl->ctx->scratch);
+    k_tdbp_pulse_table<<<(n_pulses + 127) / 128, 128, 0, st>>>(k, pos_plat, vel_plat, t_pulses, n_pulses, tab);
+    NIS_LAUNCH_CHECK(pl->ctx);
+    k_tdbp<<<(n_pix + 63) / 64, 64, 0, st>>>(k, reinterpret_cast<const float2*>(rc), tab, pl->xs, pl->ys, p_begin, p_end,
+                                             reinterpret_cast<double2*>(image), accumulate);
     NIS_LAUNCH_CHECK(pl->ctx);
     return NIS_OK;
 }

@@ -72,6 +72,31 @@ def rda(n_pulses, n_ranges, iters=10, t_p=10e-6):
     plan.close()
 
 
+def tdbp(n_pulses=2500, n_pix=512):
+    """One VideoSAR frame of sar_batch_sim.py at its real size: 35-scatterer destroyer, 2500-pulse CPI, 22004-sample
+    window, 12000-tap chirp, 512 x 512 pixels."""
+    from nis_sar import api, targets as tg
+    prm = params.batch_spotlight_preset()
+    t_vec = (np.arange(n_pulses) - (n_pulses - 1) / 2) / prm.PRF
+    pos_sat, vel_sat = scenes.orbit_trajectory(prm, t_vec, along="x")
+    base = tg.generate_destroyer(center_pos=(0, 0, 0))
+    l_ant = prm.Lambda * prm.R0 / 500.0
+    raw, t0, n, vt = api.run_physics_spotlight(base, t_vec, pos_sat, vel_sat, 45.0, 15.0, l_ant, params=prm)
+    ms_echo = time_cuda(lambda: api.run_physics_spotlight(base, t_vec, pos_sat, vel_sat, 45.0, 15.0, l_ant, params=prm), 3, 1)
+    plan = dev.TdbpPlan(c=prm.C, fc=prm.FC, k_rate=prm.k_rate, t_p=prm.T_p, fs=prm.FS, t_start=t0, n_samples=n,
+                        scene_size=500.0, nx=n_pix, ny=n_pix)
+    rc = plan.range_compress(raw)
+    ms_rc = time_cuda(lambda: plan.range_compress(raw), 5, 1)
+    img = plan.backproject(rc, pos_sat, vel_sat, t_vec, vt)
+    ms_bp = time_cuda(lambda: plan.backproject(rc, pos_sat, vel_sat, t_vec, vt, out=img), 5, 1)
+    pairs = n_pulses * n_pix * n_pix
+    print(json.dumps({"what": "tdbp_frame", "n_pulses": n_pulses, "n_samples": n, "pixels": n_pix * n_pix,
+                      "ms_echo_incl_host_setup": ms_echo, "ms_range_compress": ms_rc, "ms_backproject": ms_bp,
+                      "G_pixel_pulses_per_s": pairs / ms_bp * 1e-6,
+                      "frames_per_s": 1e3 / (ms_echo + ms_rc + ms_bp)}), flush=True)
+    plan.close()
+
+
 def gmti(n):
     a = torch.view_as_complex(torch.randn((n, n, 2), device="cuda"))
     b = torch.view_as_complex(torch.randn((n, n, 2), device="cuda"))
@@ -116,6 +141,8 @@ if __name__ == "__main__":
         if k == "csa":
             a, b = arg.split("x")
             csa_stages(int(a), int(b))
+        elif k == "tdbp":
+            tdbp(*(int(v) for v in arg.split("x"))) if arg else tdbp()
         elif k == "rda":
             a, b = arg.split("x")
             rda(int(a), int(b))
