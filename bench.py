@@ -400,6 +400,37 @@ def run_gpu_arm(args):
                "cpu_port": {"mpixels_per_s": xs.size / rda_cpu_s / 1e6, "cores": 1,
                             "sample": f"numpy port of sar_focus_rda on 4096 samples x 256 pulses, {rda_cpu_s:.1f} s"}}
 
+    # ------------------------------------------------ next-row N4: one VideoSAR frame of sar_batch_sim.py at its real size
+    video = None
+    if world == 1:
+        from nis_sar import params as nparams, scenes as nscenes, targets as ntargets
+        vprm = nparams.batch_spotlight_preset()
+        n_p, n_pix = 2500, 512
+        t_cpi = (np.arange(n_p) - (n_p - 1) / 2) / vprm.PRF
+        p_cpi, v_cpi = nscenes.orbit_trajectory(vprm, t_cpi, along="x")
+        ship = ntargets.generate_destroyer(center_pos=(0, 0, 0))
+        l_ant = vprm.Lambda * vprm.R0 / 500.0
+
+        def video_frame():
+            r, t_st, n_sp, v_t = api.run_physics_spotlight(ship, t_cpi, p_cpi, v_cpi, 45.0, 15.0, l_ant, params=vprm,
+                                                           device=device)
+            dev.add_noise(r, 30.0, seed=1, ref_power="max")
+            return api.tdbp_gpu(r, p_cpi, v_cpi, t_st, n_sp, v_t, t_cpi, 500.0, nx=n_pix, ny=n_pix, params=vprm,
+                                device=device)             # complex128 image on the host, as the reference returns
+        for _ in range(2):
+            video_frame()
+        torch.cuda.synchronize(device)
+        t0v = time.perf_counter()
+        nvf = 5
+        for _ in range(nvf):
+            video_frame()
+        torch.cuda.synchronize(device)
+        vms = (time.perf_counter() - t0v) / nvf * 1e3
+        video = {"workload": "sar_batch_sim.py frame: 35-scatterer destroyer, 2500-pulse CPI x 22004 samples (12000-tap chirp), "
+                             "noise at the peak power, 512 x 512 backprojection; host scene arrays in, complex128 image out",
+                 "ms_per_frame_e2e": vms, "frames_per_s": 1e3 / vms,
+                 "g_pixel_pulses_per_s": n_p * n_pix * n_pix / (vms * 1e-3) / 1e9}
+
     # ------------------------------------------------ reduce over ranks (max time)
     times = torch.tensor([total_ms, e2e_s * 1e3, echo_ms, csa_ms], dtype=torch.float64, device=device)
     if world > 1:
@@ -463,6 +494,8 @@ def run_gpu_arm(args):
     if ati is not None:
         ati["frac_of_hbm_peak"] = ati["achieved_GBps"] / peak_gbs
         line["ati_frame"] = ati
+    if video is not None:
+        line["videosar_frame"] = video
     if rda is not None:
         rda["frac_of_hbm_peak"] = rda["achieved_GBps"] / peak_gbs
         line["rda_frame"] = rda

@@ -49,7 +49,8 @@ __device__ __forceinline__ bool gate(const double* __restrict__ t_fast, int n, d
     return fabs(__dsub_rn(__dsub_rn(t_fast[n], tau), off)) <= half;
 }
 
-template <int SPT>
+// SPOT: the spotlight model is a separate instantiation, so that the stripmap engines keep their register budget
+template <int SPT, bool SPOT>
 __global__ void __launch_bounds__(256) k_echo(EchoConst k, EchoTail<SPT> tail, const double* __restrict__ pos0,
                                               const double* __restrict__ vel, const double* __restrict__ amp,
                                               const double* __restrict__ pos_tx, const double* __restrict__ pos_rx,
@@ -74,9 +75,9 @@ __global__ void __launch_bounds__(256) k_echo(EchoConst k, EchoTail<SPT> tail, c
     const double ti = t_slow[pulse];
     const double tx0 = pos_tx[3 * pulse], tx1 = pos_tx[3 * pulse + 1], tx2 = pos_tx[3 * pulse + 2];
     double rx0 = tx0, rx1 = tx1, rx2 = tx2;
-    if (k.bistatic || k.spotlight) { rx0 = pos_rx[3 * pulse]; rx1 = pos_rx[3 * pulse + 1]; rx2 = pos_rx[3 * pulse + 2]; }
+    if (k.bistatic || SPOT) { rx0 = pos_rx[3 * pulse]; rx1 = pos_rx[3 * pulse + 1]; rx2 = pos_rx[3 * pulse + 2]; }
     const double half = k.t_p / 2;
-    const double off = k.spotlight ? 0.0 : half;   // chirp centre relative to the delay
+    const double off = SPOT ? 0.0 : half;   // chirp centre relative to the delay
     const double t_center = k.t_start + (double)nc * k.dt_fast;
 
     float2 acc[SPT];
@@ -97,7 +98,7 @@ __global__ void __launch_bounds__(256) k_echo(EchoConst k, EchoTail<SPT> tail, c
             double dx = px - tx0, dy = py - tx1, dz = pz - tx2;
             const double d_tx = sqrt(__dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz)));
             double tau, gain = 1.0;
-            if (k.spotlight) {
+            if constexpr (SPOT) {
                 // start-stop correction: the receive position is the platform advanced by v * 2 d_tx / c (:133-137)
                 const double ta = __ddiv_rn(__dmul_rn(2.0, d_tx), k.c);
                 const double ex = px - (tx0 + rx0 * ta), ey = py - (tx1 + rx1 * ta), ez = pz - (tx2 + rx2 * ta);
@@ -109,7 +110,7 @@ __global__ void __launch_bounds__(256) k_echo(EchoConst k, EchoTail<SPT> tail, c
                 co = fmin(1.0, fmax(-1.0, co));
                 const double xv = k.ant * sin(acos(co));
                 if (fabs(xv) > 1e-6) { const double sc = sin(xv) / xv; gain = sc * sc; }
-            } else if (k.bistatic) {
+            } else if (k.bistatic) {   // (not reached in the spotlight instantiation)
                 dx = px - rx0; dy = py - rx1; dz = pz - rx2;
                 const double d_rx = sqrt(__dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz)));
                 tau = __ddiv_rn(__dadd_rn(d_tx, d_rx), k.c);
@@ -231,7 +232,8 @@ int launch_echo(nis_ctx* ctx, const EchoConst& k, const double* pos0, const doub
     }
     constexpr int CH = 256 * SPT;
     dim3 grid((k.S + CH - 1) / CH, n_pulses);
-    k_echo<SPT><<<grid, 256, 0, st>>>(k, tail, pos0, vel, amp, pos_tx, pos_rx, t_slow, t_fast, raw);
+    if (k.spotlight) k_echo<SPT, true><<<grid, 256, 0, st>>>(k, tail, pos0, vel, amp, pos_tx, pos_rx, t_slow, t_fast, raw);
+    else k_echo<SPT, false><<<grid, 256, 0, st>>>(k, tail, pos0, vel, amp, pos_tx, pos_rx, t_slow, t_fast, raw);
     NIS_LAUNCH_CHECK(ctx);
     return NIS_OK;
 }
