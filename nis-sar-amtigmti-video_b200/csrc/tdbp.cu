@@ -20,6 +20,10 @@
 #include "common.cuh"
 #include "fft.cuh"
 
+#ifndef TDBP_UNROLL
+#define TDBP_UNROLL 4
+#endif
+
 using namespace nis;
 using namespace nis::fft;
 
@@ -109,20 +113,21 @@ __global__ void __launch_bounds__(64) k_tdbp(TdbpConst k, const float2* __restri
     const double gx0 = xs[pix % k.nx], gy0 = ys[pix / k.nx];
     double ar = 0.0, ai = 0.0;
     float pr = 0.f, pi = 0.f;        // fp32 partial sums, flushed into the fp64 accumulators every 8 pulses
-    double inv = 0.0;                // reciprocal distance carried from pulse to pulse (seed of the next one)
+    double inv = 0.0;                // reciprocal distance carried from pulse to pulse (seed of the next ones)
     const float wf = (float)k.W;
-    for (int q = p_begin; q < p_end; ++q) {
+    // one pulse: returns the rotated sample; `seed` ~ 1 / distance
+    auto pulse = [&](int q, double seed, double& inv_out, float& re, float& im) {
         const double* tq = tab + 6 * q;                       // warp-uniform loads
         const double dx = gx0 + tq[0], dy = gy0 + tq[1], dz = tq[2];
         const double rvx = tq[3], rvy = tq[4], rvz = tq[5];
-        double d_tx;
-        rsqrt_sqrt(fma(dx, dx, fma(dy, dy, dz * dz)), inv, inv, d_tx);
-        const double v_rad = fma(rvx, dx, fma(rvy, dy, rvz * dz)) * inv;          // (v_plat - v_focus) . r_unit (:211-213)
+        double d_tx, iv;
+        rsqrt_sqrt(fma(dx, dx, fma(dy, dy, dz * dz)), seed, iv, d_tx);
+        const double v_rad = fma(rvx, dx, fma(rvy, dy, rvz * dz)) * iv;           // (v_plat - v_focus) . r_unit (:211-213)
         const double ta = d_tx * k.two_inv_c;                                      // 2 d_tx / c
         // both ends advanced by the flight time (:219-222): (g + v_f ta) - (p + v ta) = d - (v - v_f) ta
         const double ex = fma(-rvx, ta, dx), ey = fma(-rvy, ta, dy), ez = fma(-rvz, ta, dz);
         double d_rx, inv_rx;
-        rsqrt_sqrt(fma(ex, ex, fma(ey, ey, ez * ez)), inv, inv_rx, d_rx);
+        rsqrt_sqrt(fma(ex, ex, fma(ey, ey, ez * ez)), iv, inv_rx, d_rx);
         const double tau = (d_tx + d_rx) * k.inv_c;
         // idx_norm = 2 ((tau - t_start + t_shift) FS / W) - 1 with t_shift = -FC (2 v_rad / C) / K_RATE (:214-226)
         const float xn = (float)fma(tau, k.xn_tau, fma(v_rad, k.xn_vrad, k.xn_0));   // grid.float() (:228)
@@ -141,13 +146,35 @@ __global__ void __launch_bounds__(64) k_tdbp(TdbpConst k, const float2* __restri
         // (7e-9 turns of resolution); two MUFU ops on the fixed-point fraction.  The rotated sample is formed in fp32
         // (1e-7 relative, incoherent over the pulses), summed in fp32 over 8 pulses and then accumulated in fp64.
         const float2 e = cis_u32((uint32_t)(unsigned long long)(long long)(tau * k.fc_2p32));
-        pr += fmaf(sr, e.x, -si * e.y);
-        pi += fmaf(sr, e.y, si * e.x);
-        if (((q - p_begin) & 7) == 7) {
+        re = fmaf(sr, e.x, -si * e.y);
+        im = fmaf(sr, e.y, si * e.x);
+        inv_out = iv;
+    };
+    int q = p_begin;
+    // U pulses per iteration: U independent fp64 dependency chains in flight per thread (measured: 4.45 ms at U = 1,
+    // 3.67 ms at U = 2, 3.44 ms at U = 4 for the full-size frame)
+    constexpr int U = TDBP_UNROLL;
+    for (int it = 0; q + U <= p_end; q += U, ++it) {
+        float re[U], im[U];
+        double iv[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) pulse(q + u, inv, iv[u], re[u], im[u]);
+        inv = iv[U - 1];
+#pragma unroll
+        for (int u = 0; u < U; ++u) { pr += re[u]; pi += im[u]; }
+        if ((it & (8 / U - 1)) == 8 / U - 1) {
             ar += (double)pr;
             ai += (double)pi;
             pr = pi = 0.f;
         }
+    }
+    for (; q < p_end; ++q) {
+        float r0, i0;
+        double inv0;
+        pulse(q, inv, inv0, r0, i0);
+        inv = inv0;
+        pr += r0;
+        pi += i0;
     }
     ar += (double)pr;
     ai += (double)pi;

@@ -9,6 +9,7 @@ Checks, with N ranks against a one-GPU computation on rank 0:
   2. pulse-block echo + all-gather                                    -> bit-equal vs unsharded
   3. frame-parallel CSA (config 4 style)                              -> frames identical to a local recompute
   4. one receive channel per rank, ring exchange, DPCA/ATI per pair   -> indices equal to a local recompute
+  5. VideoSAR frames (spotlight echo -> TDBP), round robin            -> frames identical to a local recompute
 Prints one JSON line on rank 0."""
 import json
 import os
@@ -85,6 +86,30 @@ def main():
     flag = torch.tensor([ok], device=device)
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
     out["channel_pairs_ok"] = bool(flag.item())
+    # ---- 5: VideoSAR frames (spotlight echo -> backprojection), round robin over ranks, timed
+    from nis_sar import video, targets as tg
+    vp = params.batch_spotlight_preset(fs=60e6, bw=50e6, t_p=2e-6)
+    total, step, cpi, nfr = 1000, 100, 400, 7
+    t_all = np.linspace(-0.1, 0.1, total)
+    pos_all, vel_all = scenes.orbit_trajectory(vp, t_all, along="x")
+    base = tg.generate_destroyer(center_pos=(0, 0, 0))
+    kwv = dict(heading_deg=45.0, speed=15.0, l_ant=vp.Lambda * vp.R0 / 500.0, scene_size=500.0, step_pulses=step,
+               cpi_pulses=cpi, num_frames=nfr, nx=128, ny=128, params=vp, device=device, return_device=True)
+    torch.cuda.synchronize()
+    dist.barrier()
+    ev0.record()
+    mine_v = video.render_frames(base, t_all, pos_all, vel_all, **kwv)
+    ev1.record()
+    torch.cuda.synchronize()
+    out["video_frames_owned"] = sorted(mine_v)
+    out["video_ms_all_frames"] = nd.max_over_ranks(ev0.elapsed_time(ev1), device)
+    chk = all(torch.equal(v, video.render_frames(base, t_all, pos_all, vel_all, frames=[f], **kwv)[f]) for f, v in mine_v.items())
+    flag = torch.tensor([1 if chk else 0], device=device)
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    out["video_frames_ok"] = bool(flag.item())
+    counts = torch.tensor([len(mine_v)], device=device)
+    dist.all_reduce(counts)
+    out["video_frames_total"] = int(counts.item())
     if rank == 0:
         print(json.dumps(out))
     dist.destroy_process_group()
