@@ -366,6 +366,62 @@ def run_gpu_arm(args):
         p4.close()
         p4b.close()
 
+    # ------------------------------------------------ the other BASELINE.json configs, one line each (single GPU)
+    other = None
+    if world == 1:
+        other = {}
+        # configs[0]: the reference's default ATI scene shape after the pulse shift, 7199 x 13200, two channels + GMTI
+        na, nr = 7199, 13200
+        pd = dev.CsaPlan(na, nr, lam=prm.Lambda, kr=prm.k_rate, fs=prm.FS, prf=prm.PRF, vr=prm.V_eff, r_ref=prm.R0,
+                         t_start=prm.t_start_fast, device=device)
+        chd = torch.view_as_complex(torch.randn((na + 1, nr, 2), device=device))
+        sd1 = torch.empty((nr, na), dtype=torch.complex64, device=device)
+        sd2 = torch.empty_like(sd1)
+        mxd = torch.zeros(1, dtype=torch.float64, device=device)
+
+        def default_frame():
+            pd.focus(chd[1:], out=sd1, max_sq=mxd)
+            pd.focus(chd[:-1], out=sd2)
+            return dev.gmti_fused(sd1, sd2, max_sq=mxd, lazy=True, want=("ati_phase_masked", "dpca_mag"))
+        for _ in range(2):
+            default_frame()
+        torch.cuda.synchronize(device)
+        ea, eb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        cur = torch.cuda.current_stream(device)
+        ea.record(cur)
+        for _ in range(5):
+            default_frame()
+        eb.record(cur)
+        torch.cuda.synchronize(device)
+        dms = ea.elapsed_time(eb) / 5
+        other["default_ati_scene"] = {"workload": "configs[0] shape: 2 channels x CSA 7199 x 13200 (general-size path: mixed radix "
+                                                  "13200, Bluestein 7199) + fused DPCA/ATI detection",
+                                      "ms_per_frame": dms, "mpixels_per_s": 2 * na * nr / (dms * 1e-3) / 1e6}
+        pd.close()
+        del chd, sd1, sd2
+        torch.cuda.empty_cache()
+        # configs[2]: dense vehicle scene, 1e5 scatterers, airborne geometry (S = 2048); a 256-pulse block of the 32768
+        from nis_sar import scenes as nsc
+        from oracle import sar_oracle as orc2
+        vs = nsc.vehicle_scene(seed=0, num_pulses=256, num_scatterers=100000)
+        vpr = vs["prm"]
+        vkw = dict(c=vpr.C, fc=vpr.FC, k_rate=vpr.k_rate, t_p=vpr.T_p, t_start=orc2.vehicle_window_start(vpr.as_globals()),
+                   fs=360e6, n_samples=2048, device=device)
+        vargs = (vs["pos"], np.zeros(3), vs["rcs"], vs["pos_sat"], None, vs["t_vec"])
+        vout = dev.echo_accumulate(*vargs, **vkw)
+        torch.cuda.synchronize(device)
+        ea.record(cur)
+        for _ in range(3):
+            dev.echo_accumulate(*vargs, out=vout, **vkw)
+        eb.record(cur)
+        torch.cuda.synchronize(device)
+        vms = ea.elapsed_time(eb) / 3
+        other["dense_vehicle_echo"] = {"workload": "configs[2]: 1e5 scatterers x 256 of 32768 pulses x 2048 samples (sar_vehicle_sim.py "
+                                                   "geometry); includes the host->device copy of the scatterer arrays",
+                                       "ms": vms, "g_scatterer_samples_per_s": 1e5 * 256 * 2048 / (vms * 1e-3) / 1e9,
+                                       "gsamples_per_s": 256 * 2048 / (vms * 1e-3) / 1e9}
+        del vout
+
     # ------------------------------------------------ next-row N1: Range-Doppler focusing of a 4096 x 4096 frame
     rda = None
     if world == 1:
@@ -494,6 +550,8 @@ def run_gpu_arm(args):
     if ati is not None:
         ati["frac_of_hbm_peak"] = ati["achieved_GBps"] / peak_gbs
         line["ati_frame"] = ati
+    if other:
+        line["other_configs"] = other
     if video is not None:
         line["videosar_frame"] = video
     if rda is not None:

@@ -641,7 +641,9 @@ int setup_az_four_step(nis_csa_plan* pl) {
         case 16: pl->inner_w = 32; pl->inner = launch_inner<P16, 32>; TRY_RC(upload_twiddles<P16>(&pl->tw_inner)); break;
         case 64: pl->inner_w = 32; pl->inner = launch_inner<P64, 32>; TRY_RC(upload_twiddles<P64>(&pl->tw_inner)); break;
         case 256: pl->inner_w = 16; pl->inner = launch_inner<P256, 16>; TRY_RC(upload_twiddles<P256>(&pl->tw_inner)); break;
-        case 512: pl->inner_w = 8; pl->inner = launch_inner<P512, 8>; TRY_RC(upload_twiddles<P512>(&pl->tw_inner)); break;
+        // 512-point tiles: 16 columns (128-byte row pieces, one 512-thread CTA per SM) measured 12 % faster than 8 columns
+        // (three 256-thread CTAs per SM): 0.194 vs 0.220 ms per transform at 8192^2; 4 columns: 0.245 ms
+        case 512: pl->inner_w = 16; pl->inner = launch_inner<P512, 16>; TRY_RC(upload_twiddles<P512>(&pl->tw_inner)); break;
         default: pl->inner_w = 8; pl->inner = launch_inner<P1024, 8>; TRY_RC(upload_twiddles<P1024>(&pl->tw_inner)); break;
     }
 #undef TRY_RC
@@ -729,7 +731,7 @@ namespace csa {
 bool az_engine_supported(int n_az, int n_rg) {
     for (const auto& s : kAzSplits)
         if (s.n == n_az) {
-            const int w = (s.a2 <= 64) ? 32 : (s.a2 == 256 ? 16 : 8);   // tile width of the inner transform (setup_az_four_step)
+            const int w = (s.a2 <= 64) ? 32 : (s.a2 <= 512 ? 16 : 8);   // tile width of the inner transform (setup_az_four_step)
             return n_rg % w == 0;
         }
     return false;

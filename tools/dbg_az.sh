@@ -1,1 +1,2 @@
-for cfg in "4096 0" "4096 1" "4096 11" "4096 13" "8192 0" "8192 1" "8192 11" "8192 12" "2048 0" "2048 1" "2048 11"; do set -- $cfg; NIS_DEBUG=1 python tools/sched_bench.py azone $1 $2 2>&1 | grep -v "^\[nis\].*inv=1" | cut -c1-290 | tail -2; done
+for w in 8 16 4; do echo "W=$w"; NIS_INNER_W=$w python tools/sched_bench.py azone 8192 0 2>&1 | tail -1 | cut -c1-290; done
+python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -2
