@@ -105,7 +105,8 @@ NIS_API int nis_echo_accumulate(nis_ctx* ctx, const nis_echo_params* prm,
                         const double* t_fast   /* dev [S] exact sample times (linspace grid) */,
                         int32_t T, int32_t P0, int32_t P1, int32_t S,
                         nis_c32* raw /* dev [P][S], rows P0..P1-1 are written */,
-                        int32_t accumulate /* 0: overwrite rows, 1: add to them */,
+                        int32_t accumulate /* 0: overwrite rows, 1: add to them, 2: add atomically (several devices
+                                              * reducing their scatterer shards into one buffer, local or peer-mapped) */,
                         nis_stream stream);
 
 /* ------------------------------------------------------------------ K2: Chirp Scaling focusing
@@ -261,6 +262,17 @@ NIS_API int nis_power_sum(nis_ctx* ctx, const nis_c32* x, uint64_t n, double* su
 NIS_API int nis_power_max(nis_ctx* ctx, const nis_c32* x, uint64_t n, double* max_dev /* dev, 1 double */, nis_stream stream);
 NIS_API int nis_noise_add(nis_ctx* ctx, nis_c32* x, uint64_t n, const double* power_dev, double power_value,
                   double snr_db, double scr_db, double k_nu, uint64_t seed, int32_t accumulate, nis_stream stream);
+
+/* ------------------------------------------------------------------ peer memory (multi-GPU exchange steps)
+ * Where the path exchanges data -- partial echoes of scatterer shards, the neighbour channel of a DPCA/ATI pair -- the
+ * kernels above read / reduce into another GPU's HBM directly over NVLink: a peer-mapped pointer is passed like any other
+ * buffer (nis_echo_accumulate(..., accumulate = 2) adds a rank's partial echo into the owner's rows; nis_gmti_fused takes
+ * slc2 = the neighbour's image).  One process per GPU: the owner allocates and exports (64-byte CUDA IPC handle, sent
+ * over the caller's control plane), the others map it into their current device's context. */
+NIS_API int nis_peer_alloc(uint64_t bytes, void** ptr, uint8_t* handle64);
+NIS_API int nis_peer_free(void* ptr);
+NIS_API int nis_peer_open(const uint8_t* handle64, void** ptr);
+NIS_API int nis_peer_close(void* ptr);
 
 /* ------------------------------------------------------------------ buffer format helpers
  * The reference's arrays are complex128; these convert on the device so that host<->device copies

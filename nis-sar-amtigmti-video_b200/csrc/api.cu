@@ -154,3 +154,38 @@ extern "C" int nis_transpose_c32(nis_ctx* ctx, const nis_c32* in, nis_c32* out, 
     return launch_transpose(ctx, reinterpret_cast<const float2*>(in), cols, reinterpret_cast<float2*>(out), rows, cols,
                             (cudaStream_t)stream);
 }
+
+// ---- peer memory: buffers that other processes (one per GPU) map into their own address space over CUDA IPC, so that
+// their kernels load from / reduce into this GPU's HBM directly over NVLink.
+extern "C" int nis_peer_alloc(uint64_t bytes, void** ptr, uint8_t* handle64) {
+    NIS_REQUIRE(ptr && handle64 && bytes > 0, "nis_peer_alloc: bad argument");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    NIS_CUDA_TRY(cudaMalloc(ptr, bytes));
+    cudaIpcMemHandle_t h;
+    cudaError_t e = cudaIpcGetMemHandle(&h, *ptr);
+    if (e != cudaSuccess) {
+        cudaFree(*ptr);
+        *ptr = nullptr;
+        nis::set_error("cudaIpcGetMemHandle failed: %s", cudaGetErrorString(e));
+        return NIS_ERR_CUDA;
+    }
+    memcpy(handle64, &h, 64);
+    return NIS_OK;
+}
+extern "C" int nis_peer_free(void* ptr) {
+    if (ptr) NIS_CUDA_TRY(cudaFree(ptr));
+    return NIS_OK;
+}
+// maps a buffer exported by another process into the CURRENT device's context; peer access to the exporting GPU is
+// enabled as part of the mapping (cudaIpcMemLazyEnablePeerAccess)
+extern "C" int nis_peer_open(const uint8_t* handle64, void** ptr) {
+    NIS_REQUIRE(ptr && handle64, "nis_peer_open: null argument");
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle64, 64);
+    NIS_CUDA_TRY(cudaIpcOpenMemHandle(ptr, h, cudaIpcMemLazyEnablePeerAccess));
+    return NIS_OK;
+}
+extern "C" int nis_peer_close(void* ptr) {
+    if (ptr) NIS_CUDA_TRY(cudaIpcCloseMemHandle(ptr));
+    return NIS_OK;
+}

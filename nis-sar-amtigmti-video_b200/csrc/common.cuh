@@ -14,6 +14,13 @@ constexpr int kNumSMsB200 = 148;
 
 void set_error(const char* fmt, ...);
 
+// device the calling thread is bound to (function attributes and occupancy answers are cached per device)
+inline int current_device() {
+    int d = 0;
+    cudaGetDevice(&d);
+    return d;
+}
+
 #define NIS_CUDA_TRY(expr)                                                              \
     do {                                                                                \
         cudaError_t _e = (expr);                                                        \

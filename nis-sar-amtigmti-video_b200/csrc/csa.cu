@@ -429,7 +429,8 @@ int launch_outer_fwd(nis_csa_plan* pl, const float2* in, int64_t in_pitch, int c
 template <int A1, int TN, int TA>
 int launch_outer_inv(nis_csa_plan* pl, float2* slc, double* max_sq, int col0, int ncols, cudaStream_t st) {
     const size_t smem = (size_t)A1 * TN * (TA + 1) * sizeof(float2);
-    static bool attr_done = false;
+    static bool attr_done_dev[64] = {};
+    bool& attr_done = attr_done_dev[nis::current_device() & 63];
     if (!attr_done) {
         NIS_CUDA_TRY(cudaFuncSetAttribute(k_az_outer_inv<A1, TN, TA>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                           (int)smem));
@@ -446,7 +447,8 @@ int launch_outer_inv(nis_csa_plan* pl, float2* slc, double* max_sq, int col0, in
 template <class P, int W>
 int launch_inner(nis_csa_plan* pl, bool inv, int col0, int ncols, int k10, int nk1, cudaStream_t st) {
     const size_t smem = 2 * (size_t)P::N * W * sizeof(float2);   // double-buffered tile
-    static bool attr_done = false;
+    static bool attr_done_dev[64] = {};
+    bool& attr_done = attr_done_dev[nis::current_device() & 63];
     if (!attr_done) {
         NIS_CUDA_TRY(cudaFuncSetAttribute(k_az_inner_tma<P, false, W>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                           (int)smem));
@@ -477,7 +479,8 @@ int launch_range(nis_csa_plan* pl, int row0, int nrows, cudaStream_t st) {
     constexpr int SMROW = P::N + (PAD ? (P::N >> PAD) : 0);
     constexpr int GROUP_ELEMS = SMROW + ((P::NT >= 32 && P::N <= 8192) ? P::N : 0);   // exchange buffer + prefetch buffer
     const size_t smem = (size_t)GROUP_ELEMS * RPB * sizeof(float2);
-    static bool attr_done = false;
+    static bool attr_done_dev[64] = {};
+    bool& attr_done = attr_done_dev[nis::current_device() & 63];
     if (!attr_done) {
         NIS_CUDA_TRY(cudaFuncSetAttribute(k_range<P, PAD, RPB, MINB, PK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr_done = true;
@@ -522,7 +525,8 @@ int launch_az_cluster(nis_csa_plan* pl, const CUtensorMap& map, float2* out, int
                       cudaStream_t st) {
     auto kern = k_az_cluster<P, C, W, INV, INV>;
     const size_t smem = INV ? (size_t)W * (P::N + 2) * sizeof(float2) : (size_t)P::N * W * sizeof(float2);
-    static int n_clusters = 0;
+    static int n_clusters_dev[64] = {};
+    int& n_clusters = n_clusters_dev[nis::current_device() & 63];
     cudaLaunchConfig_t cfg = {};
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;

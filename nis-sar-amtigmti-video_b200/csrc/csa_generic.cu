@@ -357,7 +357,8 @@ int launch_blue(nis_ctx* ctx, const GenLen& g, float2* data, int64_t pitch, int 
                 float scale, double* max_sq, cudaStream_t st) {
     constexpr int SMROW = P::N + (PAD ? (P::N >> PAD) : 0);
     const size_t smem = (size_t)SMROW * sizeof(float2);
-    static bool attr_done = false;
+    static bool attr_done_dev[64] = {};
+    bool& attr_done = attr_done_dev[nis::current_device() & 63];
     if (!attr_done) {
         NIS_CUDA_TRY(cudaFuncSetAttribute(k_row_blue<MODE, P, PAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr_done = true;
@@ -384,7 +385,8 @@ int launch_row(nis_ctx* ctx, const GenLen& g, float2* data, int64_t pitch, int n
         }
     }
     const size_t smem = 2 * (size_t)g.N * sizeof(float2);
-    static bool attr_done = false;
+    static bool attr_done_dev[64] = {};
+    bool& attr_done = attr_done_dev[nis::current_device() & 63];
     if (!attr_done) {
         NIS_CUDA_TRY(cudaFuncSetAttribute(k_row_mixed<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         attr_done = true;

@@ -212,8 +212,15 @@ __global__ void __launch_bounds__(256) k_echo(EchoConst k, EchoTail<SPT> tail, c
     for (int j = 0; j < SPT; ++j) {
         if (n0 + t_lo + j < k.S) {
             float2 x = cmul(acc[j], tail.e[j]);
-            if (k.accumulate) { const float2 o = out[j]; x.x += o.x; x.y += o.y; }
-            out[j] = x;
+            if (k.accumulate == 2) {
+                // several GPUs add their scatterer shards into one owner's rows, possibly over NVLink: fire-and-forget
+                // reductions (RED.ADD.F32), no read-modify-write round trip
+                atomicAdd(&out[j].x, x.x);
+                atomicAdd(&out[j].y, x.y);
+            } else {
+                if (k.accumulate) { const float2 o = out[j]; x.x += o.x; x.y += o.y; }
+                out[j] = x;
+            }
         }
     }
 }

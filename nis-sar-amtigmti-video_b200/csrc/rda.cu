@@ -223,7 +223,8 @@ template <class P, int PAD>
 int launch_rda_range(nis_rda_plan* pl, const float2* in, int64_t pitch, float2* rc_out, cudaStream_t st) {
     constexpr int SMROW = P::N + (PAD ? (P::N >> PAD) : 0);
     const size_t smem = (size_t)SMROW * sizeof(float2);
-    static bool attr_done = false;
+    static bool attr_done_dev[64] = {};
+    bool& attr_done = attr_done_dev[nis::current_device() & 63];
     if (!attr_done) {
         NIS_CUDA_TRY(cudaFuncSetAttribute(k_rda_range<P, PAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr_done = true;
@@ -435,7 +436,8 @@ extern "C" int nis_rda_focus(nis_rda_plan* pl, const nis_c32* phist, int64_t pit
         RUN(launch_transpose(ctx, pl->tbuf, P, pl->work, S, P, st));
     }
     {
-        static bool attr_done = false;
+        static bool attr_done_dev[64] = {};
+    bool& attr_done = attr_done_dev[nis::current_device() & 63];
         if (!attr_done) {
             NIS_CUDA_TRY(cudaFuncSetAttribute(k_rda_rcmc, cudaFuncAttributeMaxDynamicSharedMemorySize, 24576 * 8));
             attr_done = true;

@@ -228,7 +228,8 @@ template <class P, int PAD>
 int launch_tdbp_range(nis_tdbp_plan* pl, const float2* raw, int64_t pitch, float2* rc, int n_pulses, cudaStream_t st) {
     constexpr int SMROW = P::N + (PAD ? (P::N >> PAD) : 0);
     const size_t smem = (size_t)SMROW * sizeof(float2);
-    static bool attr_done = false;
+    static bool attr_done_dev[64] = {};
+    bool& attr_done = attr_done_dev[nis::current_device() & 63];
     if (!attr_done) {
         NIS_CUDA_TRY(cudaFuncSetAttribute(k_tdbp_range<P, PAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr_done = true;

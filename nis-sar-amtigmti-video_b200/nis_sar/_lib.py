@@ -78,6 +78,10 @@ SIGNATURES = {
     "nis_viewer_products": (C.c_int, [_P, _P, _P, C.c_uint64, C.c_double, _P, _P, _P, _P, _P, _P, _P, _P]),
     "nis_region_stats": (C.c_int, [_P, _P, C.c_int64, C.c_int32, C.c_int32, C.c_int32, _P, _P]),
     "nis_region_select": (C.c_int, [_P, _P, C.c_int64, C.c_int32, C.c_int32, _P, C.c_int32, _P, _P]),
+    "nis_peer_alloc": (C.c_int, [C.c_uint64, C.POINTER(_P), _P]),
+    "nis_peer_free": (C.c_int, [_P]),
+    "nis_peer_open": (C.c_int, [_P, C.POINTER(_P)]),
+    "nis_peer_close": (C.c_int, [_P]),
     "nis_power_sum": (C.c_int, [_P, _P, C.c_uint64, _P, _P]),
     "nis_power_max": (C.c_int, [_P, _P, C.c_uint64, _P, _P]),
     "nis_noise_add": (C.c_int, [_P, _P, C.c_uint64, _P, C.c_double, C.c_double, C.c_double, C.c_double, C.c_uint64,

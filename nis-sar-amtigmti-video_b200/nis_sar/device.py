@@ -53,6 +53,8 @@ def echo_accumulate(pos0, vel, rcs, pos_tx, pos_rx, t_slow, *, c, fc, k_rate, t_
     ``device``.  ``vel`` is one xyz triple or a [T,3] array; ``pos_rx`` None selects the monostatic
     delay 2|p - p_tx|/c.  ``pulse_range=(p0, p1)`` restricts the rows that are computed (the pulse
     block of one rank); rows outside are left untouched.  ``spotlight=(vel_sat[P,3], pi l_ant / lambda, t_fast[S])``
+    ``accumulate``: False overwrite, True add, "atomic" add with device-scope-free reductions (``out`` may be another GPU's
+    buffer mapped through ``nis_sar.dist.share_tensor``: the partial echoes of several ranks meet in one buffer).
     selects the run_physics_spotlight model (sar_batch_sim.py:83-169): start-stop corrected delay, sinc^2 pattern,
     amplitude rcs (not its square root), chirp centred on the delay, sample times t_start + n / fs."""
     di = _dev_index(device)
@@ -85,6 +87,7 @@ def echo_accumulate(pos0, vel, rcs, pos_tx, pos_rx, t_slow, *, c, fc, k_rate, t_
             accumulate = False if pulse_range is None else accumulate
         elif out.shape != (P, S) or out.dtype != torch.complex64 or not out.is_contiguous():
             raise NisError("echo_accumulate: out must be a contiguous complex64 [P, S] tensor")
+        acc_mode = 2 if accumulate == "atomic" else (1 if accumulate else 0)
         p0, p1 = (0, P) if pulse_range is None else pulse_range
         prm = _lib.EchoParams(c=c, fc=fc, k_rate=k_rate, t_p=t_p, t_start=float(t_fast[0]),
                               dt_fast=((S / fs) / (S - 1) if S > 1 else 1.0 / fs) if spotlight is None else 1.0 / fs,
@@ -96,12 +99,12 @@ def echo_accumulate(pos0, vel, rcs, pos_tx, pos_rx, t_slow, *, c, fc, k_rate, t_
             if spotlight is not None:
                 rc = lib.nis_echo_spotlight(ctx, C.byref(prm), _ptr(pos0_d), _ptr(vel_d), _ptr(amp_d), _ptr(ptx_d),
                                             _ptr(prx_d), _ptr(ts_d), _ptr(tf_d), T, q0, q1, S, float(spotlight[1]),
-                                            _ptr(out), 1 if accumulate else 0, C.c_void_p(_stream_ptr(di)))
+                                            _ptr(out), acc_mode, C.c_void_p(_stream_ptr(di)))
                 _lib.check(rc, "nis_echo_spotlight")
                 continue
             rc = lib.nis_echo_accumulate(ctx, C.byref(prm), _ptr(pos0_d), _ptr(vel_d), _ptr(amp_d), _ptr(ptx_d),
                                          _ptr(prx_d), _ptr(ts_d), _ptr(tf_d), T, q0, q1, S, _ptr(out),
-                                         1 if accumulate else 0, C.c_void_p(_stream_ptr(di)))
+                                         acc_mode, C.c_void_p(_stream_ptr(di)))
             _lib.check(rc, "nis_echo_accumulate")
         # the fp64 input tensors may be freed right away: torch's allocator only reuses their memory
         # for later work on this same stream

@@ -16,6 +16,7 @@ from __future__ import annotations
 
 from typing import Callable, Sequence
 
+import numpy as np
 import torch
 import torch.distributed as dist
 
@@ -76,6 +77,109 @@ def echo_scatterer_shards(compute: Callable[[int, int], torch.Tensor], num_scatt
         else:
             dist.reduce(_as_real(part), dst=dst, op=dist.ReduceOp.SUM, group=group)
     return part
+
+
+# ------------------------------------------------------------------ peer memory over NVLink / NVSwitch
+class _CudaArray:
+    """``__cuda_array_interface__`` carrier: lets torch view a raw device pointer as a tensor (no copy, no ownership)."""
+
+    def __init__(self, ptr, shape, typestr):
+        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": typestr, "data": (int(ptr), False), "version": 2}
+
+
+_TYPESTR = {torch.complex64: "<c8", torch.float32: "<f4", torch.float64: "<f8", torch.complex128: "<c16"}
+
+
+class SharedBuffer:
+    """One buffer per rank, each mapped into every rank (CUDA IPC): ``local`` is this rank's tensor, ``views[r]`` aliases
+    rank r's buffer.  Kernels launched by this rank load from / reduce into ``views[r]`` directly over NVLink -- the
+    transfer overlaps the arithmetic access by access instead of preceding it as a copy.  Collective: every rank of the
+    group constructs it with the same shape; ``close()`` (collective as well) unmaps and frees."""
+
+    def __init__(self, shape, dtype=torch.complex64, device=None, group=None):
+        import ctypes as C
+        from . import _lib
+        self.group = group
+        rank, n = world(group)
+        self.device = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
+        lib = _lib.load()
+        nbytes = int(np.prod(shape)) * torch.empty((), dtype=dtype).element_size()
+        self._ptr = C.c_void_p()
+        handle = (C.c_uint8 * 64)()
+        with torch.cuda.device(self.device):
+            _lib.check(lib.nis_peer_alloc(nbytes, C.byref(self._ptr), C.cast(handle, C.c_void_p)), "nis_peer_alloc")
+            self.local = torch.as_tensor(_CudaArray(self._ptr.value, shape, _TYPESTR[dtype]), device=self.device)
+            handles = [None] * n
+            if n > 1:
+                dist.all_gather_object(handles, bytes(handle), group=group)
+            self._opened = {}
+            self.views = []
+            for r in range(n):
+                if r == rank:
+                    self.views.append(self.local)
+                    continue
+                p = C.c_void_p()
+                hb = (C.c_uint8 * 64).from_buffer_copy(handles[r])
+                _lib.check(lib.nis_peer_open(C.cast(hb, C.c_void_p), C.byref(p)), "nis_peer_open")
+                self._opened[r] = p
+                self.views.append(torch.as_tensor(_CudaArray(p.value, shape, _TYPESTR[dtype]), device=self.device))
+
+    def close(self):
+        from . import _lib
+        lib = _lib.load()
+        peer_barrier(self.device, self.group)
+        with torch.cuda.device(self.device):
+            for p in self._opened.values():
+                lib.nis_peer_close(p)
+            self._opened = {}
+            self.views = []
+            peer_barrier(self.device, self.group)     # everybody has unmapped before anybody frees
+            if self._ptr:
+                lib.nis_peer_free(self._ptr)
+                self._ptr = None
+            self.local = None
+
+
+def peer_barrier(device, group=None) -> None:
+    """Everything this rank has enqueued is complete and every rank has reached this point."""
+    torch.cuda.synchronize(device)
+    if world(group)[1] > 1:
+        dist.barrier(group=group)
+
+
+def echo_scatterer_shards_p2p(compute_into: Callable[[int, int, int, int, torch.Tensor], None], num_scatterers: int,
+                              shared: SharedBuffer) -> tuple:
+    """Scatterer sharding with the reduction fused into the synthesis kernel (reduce-scatter semantics): rank b owns the
+    pulse block b of ``shared`` (a SharedBuffer of shape [P, S] complex64).  Every rank synthesises ITS scatterers
+    [t0, t1) for ALL pulse blocks and the kernel's epilogue adds each block straight into the owner's HBM with
+    fire-and-forget reductions over NVLink -- ``compute_into(t0, t1, p0, p1, dst)`` must accumulate atomically into rows
+    [p0, p1) of ``dst`` (``dev.echo_accumulate(..., out=dst, pulse_range=(p0, p1), accumulate="atomic")``).  No partial
+    [P, S] echo is materialised and no separate collective runs.  Returns (p0, p1): the fully reduced rows of
+    ``shared.local`` this rank holds."""
+    rank, n = world(shared.group)
+    P = shared.local.shape[0]
+    t0, t1 = block_range(num_scatterers, rank, n)
+    shared.local.zero_()
+    peer_barrier(shared.device, shared.group)
+    for k in range(n):
+        b = (rank + k) % n                      # start with the local block, then walk the ring: spreads the NVLink load
+        p0, p1 = block_range(P, b, n)
+        if p1 > p0 and t1 > t0:
+            compute_into(t0, t1, p0, p1, shared.views[b])
+    peer_barrier(shared.device, shared.group)
+    return block_range(P, rank, n)
+
+
+def pair_products_p2p(shared: SharedBuffer, products: Callable[[torch.Tensor, torch.Tensor], dict]):
+    """HRWS-style chain without the staging copy: every rank has focused its channel into ``shared.local``; the fused
+    DPCA/ATI kernel of rank k then reads channel k+1 directly from rank k+1's HBM over NVLink (8 of its 16 input bytes per
+    pixel), so the exchange overlaps the products instead of preceding them.  Returns the products of the pair (k, k+1),
+    None on the last rank."""
+    rank, n = world(shared.group)
+    peer_barrier(shared.device, shared.group)      # every channel is focused before anyone reads it
+    out = products(shared.local, shared.views[rank + 1]) if rank < n - 1 else None
+    peer_barrier(shared.device, shared.group)      # nobody overwrites its channel while a neighbour still reads it
+    return out
 
 
 # ------------------------------------------------------------------------------------------- CSA

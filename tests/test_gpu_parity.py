@@ -690,3 +690,33 @@ def test_videosar_frames_and_peak_power_noise(api, dev):
     assert abs(np.mean(np.abs(added) ** 2) / want - 1) < 0.03
     noise = api.generate_noise_tensor(clean.shape, dev.peak_power(clean), 20.0, scr_db=15.0, seed=3)
     assert torch.equal(noise, raw - clean) or np.allclose(noise.cpu().numpy(), added, atol=1e-4 * np.sqrt(want))
+
+
+def test_echo_atomic_accumulate_and_shared_buffer_single_rank(api, dev):
+    """The reduction mode used when several GPUs add their scatterer shards into one owner's rows (accumulate="atomic",
+    RED.ADD in the kernel epilogue): two shards added atomically == one launch over all scatterers, and a SharedBuffer
+    (IPC-exportable allocation viewed as a tensor) is an ordinary output buffer on one rank."""
+    import torch
+    from nis_sar import scenes, dist as nd
+    sc = scenes.vehicle_scene(seed=4, num_pulses=96, num_scatterers=600)
+    prm = sc["prm"]
+    kw = dict(c=prm.C, fc=prm.FC, k_rate=prm.k_rate, t_p=prm.T_p, t_start=orc.vehicle_window_start(prm.as_globals()),
+              fs=360e6, n_samples=2048)
+    full = dev.echo_accumulate(sc["pos"], np.zeros(3), sc["rcs"], sc["pos_sat"], None, sc["t_vec"], **kw)
+    sh = nd.SharedBuffer((96, 2048), torch.complex64)
+    try:
+        assert sh.views[0] is sh.local and sh.local.shape == (96, 2048) and sh.local.dtype == torch.complex64
+
+        def into(a, b, p0, p1, dst):
+            dev.echo_accumulate(sc["pos"][a:b], np.zeros(3), sc["rcs"][a:b], sc["pos_sat"], None, sc["t_vec"], out=dst,
+                                pulse_range=(p0, p1), accumulate="atomic", **kw)
+        sh.local.zero_()
+        for a, b in ((0, 250), (250, 600)):
+            for p0, p1 in ((0, 40), (40, 96)):
+                into(a, b, p0, p1, sh.local)
+        torch.cuda.synchronize()
+        assert _rel(sh.local.cpu().numpy(), full.cpu().numpy()) < 1e-6
+        own = nd.echo_scatterer_shards_p2p(into, 600, sh)       # world size 1: degenerates to one shard, one block
+        assert own == (0, 96) and _rel(sh.local.cpu().numpy(), full.cpu().numpy()) < 1e-6
+    finally:
+        sh.close()

@@ -10,6 +10,7 @@ Checks, with N ranks against a one-GPU computation on rank 0:
   3. frame-parallel CSA (config 4 style)                              -> frames identical to a local recompute
   4. one receive channel per rank, ring exchange, DPCA/ATI per pair   -> indices equal to a local recompute
   5. VideoSAR frames (spotlight echo -> TDBP), round robin            -> frames identical to a local recompute
+  1b / 4b: the two exchange steps with the transfer fused into the kernels (peer-mapped HBM over NVLink)
 Prints one JSON line on rank 0."""
 import json
 import os
@@ -52,6 +53,31 @@ def main():
     out["scatterer_shards_rel_l2"] = float(torch.linalg.vector_norm(summed - full) / torch.linalg.vector_norm(full))
     out["scatterer_shards_ms"] = nd.max_over_ranks(ev0.elapsed_time(ev1), device)
 
+    # ---- 1b: the same reduction fused into the synthesis kernel: every rank adds its scatterers' echo straight into the
+    #          owner's pulse block over NVLink (peer-mapped buffers, RED.ADD), no partial echo, no collective
+    shared = nd.SharedBuffer(tuple(full.shape), torch.complex64, device=device)
+
+    def shard_into(a, b, p0, p1, dst):
+        dev.echo_accumulate(sc["pos"][a:b], np.zeros(3), sc["rcs"][a:b], sc["pos_sat"], None, sc["t_vec"], out=dst,
+                            pulse_range=(p0, p1), accumulate="atomic", **kw)
+    try:
+        own = nd.echo_scatterer_shards_p2p(shard_into, len(sc["rcs"]), shared)      # warm-up
+        torch.cuda.synchronize()
+        dist.barrier()
+        ev0.record()
+        own = nd.echo_scatterer_shards_p2p(shard_into, len(sc["rcs"]), shared)
+        ev1.record()
+        torch.cuda.synchronize()
+        blk = shared.local[own[0]:own[1]]
+        ref = full[own[0]:own[1]]
+        err = torch.linalg.vector_norm(blk - ref) / torch.linalg.vector_norm(ref)
+        errs = torch.tensor([float(err)], device=device)
+        dist.all_reduce(errs, op=dist.ReduceOp.MAX)
+        out["scatterer_shards_p2p_rel_l2"] = float(errs.item())
+        out["scatterer_shards_p2p_ms"] = nd.max_over_ranks(ev0.elapsed_time(ev1), device)
+    except Exception as e:   # no peer path on this box: report, the NCCL route above is the fallback
+        out["scatterer_shards_p2p_error"] = str(e)[:200]
+
     raw = torch.zeros_like(full)
 
     def fill(p0, p1, buf):
@@ -86,6 +112,39 @@ def main():
     flag = torch.tensor([ok], device=device)
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
     out["channel_pairs_ok"] = bool(flag.item())
+
+    # ---- 4b: pairing at 4096^2, staging copy (isend / irecv) vs the DPCA/ATI kernel reading the neighbour's HBM over NVLink
+    n4 = 4096
+    p4 = dev.cached_plan(n4, n4, lam=sp.Lambda, kr=sp.k_rate, fs=sp.FS, prf=sp.PRF, vr=sp.V_eff, r_ref=sp.R0,
+                         t_start=sp.t_start_fast, device=device)
+    g4 = torch.Generator(device=device).manual_seed(500 + rank)
+    chan4 = p4.focus(torch.view_as_complex(torch.randn((n4, n4, 2), generator=g4, device=device))).clone()
+    prod = lambda a, b: dev.gmti_fused(a, b, lazy=True)       # all products, no host read-back
+    try:
+        sh4 = nd.SharedBuffer((n4, n4), torch.complex64, device=device)
+        sh4.local.copy_(chan4)
+        for fn_name, fn in (("copy", lambda: nd.pair_products(chan4, prod)), ("p2p", lambda: nd.pair_products_p2p(sh4, prod))):
+            r0 = fn()
+            torch.cuda.synchronize()
+            dist.barrier()
+            ev0.record()
+            for _ in range(5):
+                r0 = fn()
+            ev1.record()
+            torch.cuda.synchronize()
+            out[f"pair4096_{fn_name}_ms"] = nd.max_over_ranks(ev0.elapsed_time(ev1) / 5, device)
+            if r0 is not None:
+                out.setdefault("_pair_results", {})[fn_name] = (r0["det_idx_raw"][:1000].clone(), r0["result_dev"].clone())
+        ok = 1
+        pr = out.pop("_pair_results", None)
+        if pr:
+            ok = int(torch.equal(pr["copy"][0], pr["p2p"][0]) and torch.equal(pr["copy"][1], pr["p2p"][1]))
+        flag = torch.tensor([ok], device=device)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        out["pair4096_p2p_equals_copy"] = bool(flag.item())
+    except Exception as e:
+        out.pop("_pair_results", None)
+        out["pair4096_p2p_error"] = str(e)[:200]
     # ---- 5: VideoSAR frames (spotlight echo -> backprojection), round robin over ranks, timed
     from nis_sar import video, targets as tg
     vp = params.batch_spotlight_preset(fs=60e6, bw=50e6, t_p=2e-6)
