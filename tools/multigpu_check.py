@@ -44,6 +44,7 @@ def main():
     def shard(a, b):
         return dev.echo_accumulate(sc["pos"][a:b], np.zeros(3), sc["rcs"][a:b], sc["pos_sat"], None, sc["t_vec"], **kw)
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    summed = nd.echo_scatterer_shards(shard, len(sc["rcs"]))      # warm-up (NCCL communicator set-up)
     torch.cuda.synchronize()
     dist.barrier()
     ev0.record()
