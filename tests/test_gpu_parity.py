@@ -720,3 +720,37 @@ def test_echo_atomic_accumulate_and_shared_buffer_single_rank(api, dev):
         assert own == (0, 96) and _rel(sh.local.cpu().numpy(), full.cpu().numpy()) < 1e-6
     finally:
         sh.close()
+
+
+def test_abi_error_behaviour_on_device(dev):
+    """Error classes and messages through the C ABI (nothing throws across it; Python raises NisError): unsupported
+    sizes, mismatched shapes, wrong dtypes, bad parameters -- and the library keeps working afterwards."""
+    import torch
+    from nis_sar._lib import NisError
+    prm = params.spaceborne_preset()
+    kw = dict(lam=prm.Lambda, kr=prm.k_rate, fs=prm.FS, prf=prm.PRF, vr=prm.V_eff, r_ref=prm.R0, t_start=prm.t_start_fast)
+    with pytest.raises(NisError, match="not supported"):
+        dev.CsaPlan(3, 100000, **kw)
+    with pytest.raises(NisError, match="non-physical"):
+        dev.CsaPlan(64, 64, **{**kw, "fs": -1.0})
+    plan = dev.CsaPlan(64, 128, **kw)
+    with pytest.raises(NisError, match="plan is 64x128"):
+        plan.focus(torch.zeros((64, 64), dtype=torch.complex64, device="cuda"))
+    with pytest.raises(NisError, match="complex64"):
+        plan.focus(torch.zeros((64, 128), dtype=torch.complex128, device="cuda"))
+    rk = dict(lam=prm.Lambda, t_p=prm.T_p, kr=prm.k_rate, fs=prm.FS, prf=prm.PRF, vr=prm.V_eff, range_grp=prm.R0)
+    assert not dev.RdaPlan.supported(64, 20000, **rk)             # 20000 samples + 6000 taps do not fit a 16384-point FFT
+    with pytest.raises(NisError, match="not supported"):
+        dev.RdaPlan(64, 20000, **rk)
+    with pytest.raises(NisError, match="taps"):
+        dev.TdbpPlan(c=prm.C, fc=prm.FC, k_rate=prm.k_rate, t_p=1e-3, fs=600e6, t_start=0.0, n_samples=1024, scene_size=100.0)
+    with pytest.raises(NisError, match="shape"):
+        dev.gmti_fused(torch.zeros((4, 4), dtype=torch.complex64, device="cuda"),
+                       torch.zeros((4, 5), dtype=torch.complex64, device="cuda"))
+    x = torch.zeros(16, dtype=torch.complex64, device="cuda")
+    with pytest.raises(NisError, match="positive"):
+        dev.add_noise(x, 10.0, k_nu=0.0, ref_power=1.0)
+    # still healthy
+    out = plan.focus(torch.ones((64, 128), dtype=torch.complex64, device="cuda"))
+    assert torch.isfinite(torch.view_as_real(out)).all()
+    plan.close()
