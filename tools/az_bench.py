@@ -1,6 +1,6 @@
 #!/usr/bin/env python
-"""Development tool: time the CSA launch schedules (NIS_CSA_SCHED / NIS_CSA_STRIPS knobs) and check that
-every schedule gives the same image as the whole-frame one.  Usage: python tools/sched_bench.py [sizes...]"""
+"""Development tool: time the azimuth engines of the power-of-two CSA path (NIS_CSA_AZ knob: 0 = two-kernel four-step,
+k = cluster configuration k) and check every engine against engine 0.  Usage: python tools/az_bench.py az | azone N K"""
 import json
 import os
 import sys
@@ -62,33 +62,6 @@ def run_az(n, ids):
     os.environ["NIS_CSA_AZ"] = "0"
 
 
-def run(n, configs):
-    prm = params.spaceborne_preset()
-    x = torch.view_as_complex(torch.randn((n, n, 2), device="cuda"))
-    ref = None
-    for sched, strips in configs:
-        os.environ["NIS_CSA_SCHED"] = str(sched)
-        os.environ["NIS_CSA_STRIPS"] = str(strips)
-        plan = dev.CsaPlan(n, n, lam=prm.Lambda, kr=prm.k_rate, fs=prm.FS, prf=prm.PRF, vr=prm.V_eff, r_ref=prm.R0,
-                           t_start=prm.t_start_fast)
-        out = torch.empty((n, n), dtype=torch.complex64, device="cuda")
-        plan.focus(x, out=out)
-        torch.cuda.synchronize()
-        if ref is None:
-            ref = out.clone()
-            same = True
-        else:
-            same = bool(torch.equal(torch.view_as_real(out), torch.view_as_real(ref)))
-        ms = time_cuda(lambda: plan.focus(x, out=out))
-        g = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(g):
-            plan.focus(x, out=out)
-        ms_g = time_cuda(g.replay)
-        print(json.dumps({"n": n, "sched": sched, "strips": strips, "same": same, "ms": round(ms, 4),
-                          "ms_graph": round(ms_g, 4), "frac48": round(48.0 * n * n / ms_g * 1e-6 / PEAK, 4)}), flush=True)
-        plan.close()
-
-
 if __name__ == "__main__":
     if sys.argv[1:2] == ["azone"]:
         run_az(int(sys.argv[2]), (int(sys.argv[3]),))
@@ -97,7 +70,4 @@ if __name__ == "__main__":
         for n, ids in ((1024, (0, 1)), (2048, (0, 1, 2)), (4096, (0, 1, 2, 3, 4)), (8192, (0, 1, 2, 3)), (16384, (0, 1))):
             run_az(n, ids)
         sys.exit(0)
-    sizes = [int(a) for a in sys.argv[1:]] or [4096, 8192]
-    cfg = [(0, 1), (1, 2), (1, 4), (1, 8), (1, 16), (1, 32), (2, 1), (2, 2), (2, 4)]
-    for n in sizes:
-        run(n, cfg)
+    print("usage: az_bench.py az | azone N CONFIG")
