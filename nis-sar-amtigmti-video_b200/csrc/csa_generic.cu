@@ -35,6 +35,7 @@ enum Mode { AZ_FWD = 0, RANGE = 1, AZ_INV = 2 };
 struct GenDev {   // by-value kernel argument
     int N, npass, M;
     int radix[kMaxPass];
+    uint32_t inv_ns[kMaxPass];   // ceil(2^32 / Ns) of every pass (Ns = product of the earlier radices)
     const float2* twN;
     const float2* chirp;
     const float2* bfft;
@@ -48,7 +49,12 @@ struct GenLen {
     GenDev dev() const {
         GenDev d{};
         d.N = N; d.npass = npass; d.M = M;
-        for (int i = 0; i < kMaxPass; ++i) d.radix[i] = radix[i];
+        uint64_t ns = 1;
+        for (int i = 0; i < kMaxPass; ++i) {
+            d.radix[i] = radix[i];
+            d.inv_ns[i] = (uint32_t)((0x100000000ull + ns - 1) / ns);
+            if (i < npass) ns *= (uint64_t)radix[i];
+        }
         d.twN = twN; d.chirp = chirp; d.bfft = bfft; d.tw_pow2 = tw_pow2;
         return d;
     }
@@ -79,18 +85,24 @@ int bluestein_m(int n) {
 bool length_supported(int n) { return smooth(n) || (n >= 2 && n <= kMaxBluesteinLen && bluestein_m(n) > 0); }
 
 // ----------------------------------------------------------------------------- mixed radix engine
+// Odd radices: the R-point DFT is evaluated through the conjugate-symmetric pairs s_r = v_r + v_(R-r), d_r = v_r - v_(R-r):
+//   X[q], X[R-q] = (v_0 + sum_r cos(2 pi r q / R) s_r) +- (i sum_r w_(rq).y d_r),   r, q = 1 .. (R-1)/2
+// i.e. real-by-complex products only: (R-1)^2 FMAs instead of the (R-1)^2 complex multiplies of the direct sum.
+// inv_ns = ceil(2^32 / Ns): j / Ns == umulhi(j, inv_ns) for every j * Ns < 2^32 (no integer division in the loop).
 template <int R, bool INV>
 __device__ __forceinline__ void mixed_pass(const float2* __restrict__ src, float2* __restrict__ dst, int N, int Ns,
-                                           const float2* __restrict__ twN) {
+                                           uint32_t inv_ns, const float2* __restrict__ twN) {
     const int nb = N / R, stride = N / (Ns * R);
     constexpr bool kPow2 = (R & (R - 1)) == 0;
+    constexpr int H = (R - 1) / 2;
     float2 wr[R];
     if constexpr (!kPow2) {
 #pragma unroll
         for (int m = 0; m < R; ++m) wr[m] = __ldg(twN + m * nb);
     }
     for (int j = threadIdx.x; j < nb; j += blockDim.x) {
-        const int k = j % Ns, base = (j / Ns) * Ns * R + k;
+        const int jq = (Ns == 1) ? j : (int)__umulhi((uint32_t)j, inv_ns);
+        const int k = j - jq * Ns, base = jq * Ns * R + k;
         float2 v[R];
 #pragma unroll
         for (int r = 0; r < R; ++r) {
@@ -107,16 +119,30 @@ __device__ __forceinline__ void mixed_pass(const float2* __restrict__ src, float
 #pragma unroll
             for (int q = 0; q < R; ++q) dst[base + q * Ns] = v[brev(q, L)];
         } else {
+            float2 x0 = v[0];
 #pragma unroll
-            for (int q = 0; q < R; ++q) {
-                float2 acc = v[0];
+            for (int r = 1; r <= H; ++r) {
+                const float2 a = v[r], b = v[R - r];
+                v[r] = make_float2(a.x + b.x, a.y + b.y);          // s_r
+                v[R - r] = make_float2(a.x - b.x, a.y - b.y);      // d_r
+                x0.x += v[r].x;
+                x0.y += v[r].y;
+            }
+            dst[base] = x0;
 #pragma unroll
-                for (int r = 1; r < R; ++r) {
-                    const float2 w = wr[(r * q) % R];
-                    const float2 t = INV ? cmul_conj(v[r], w) : cmul(v[r], w);
-                    acc.x += t.x; acc.y += t.y;
+            for (int q = 1; q <= H; ++q) {
+                float2 A = v[0], B = make_float2(0.f, 0.f);
+#pragma unroll
+                for (int r = 1; r <= H; ++r) {
+                    const float2 w = wr[(r * q) % R];              // (cos, -sin) of 2 pi r q / R
+                    A.x = fmaf(w.x, v[r].x, A.x);
+                    A.y = fmaf(w.x, v[r].y, A.y);
+                    B.x = fmaf(-w.y, v[R - r].y, B.x);             // i w.y d = w.y (-d.y, d.x)
+                    B.y = fmaf(w.y, v[R - r].x, B.y);
                 }
-                dst[base + q * Ns] = acc;
+                const float2 p = make_float2(A.x + B.x, A.y + B.y), m = make_float2(A.x - B.x, A.y - B.y);
+                dst[base + q * Ns] = INV ? m : p;
+                dst[base + (R - q) * Ns] = INV ? p : m;
             }
         }
     }
@@ -130,15 +156,15 @@ __device__ float2* mixed_dft(const GenDev& g, float2* a, float2* b) {
     for (int p = 0; p < g.npass; ++p) {
         const int R = g.radix[p];
         switch (R) {
-            case 2: mixed_pass<2, INV>(a, b, g.N, Ns, g.twN); break;
-            case 3: mixed_pass<3, INV>(a, b, g.N, Ns, g.twN); break;
-            case 4: mixed_pass<4, INV>(a, b, g.N, Ns, g.twN); break;
-            case 5: mixed_pass<5, INV>(a, b, g.N, Ns, g.twN); break;
-            case 7: mixed_pass<7, INV>(a, b, g.N, Ns, g.twN); break;
-            case 8: mixed_pass<8, INV>(a, b, g.N, Ns, g.twN); break;
-            case 11: mixed_pass<11, INV>(a, b, g.N, Ns, g.twN); break;
-            case 13: mixed_pass<13, INV>(a, b, g.N, Ns, g.twN); break;
-            default: mixed_pass<16, INV>(a, b, g.N, Ns, g.twN); break;
+            case 2: mixed_pass<2, INV>(a, b, g.N, Ns, g.inv_ns[p], g.twN); break;
+            case 3: mixed_pass<3, INV>(a, b, g.N, Ns, g.inv_ns[p], g.twN); break;
+            case 4: mixed_pass<4, INV>(a, b, g.N, Ns, g.inv_ns[p], g.twN); break;
+            case 5: mixed_pass<5, INV>(a, b, g.N, Ns, g.inv_ns[p], g.twN); break;
+            case 7: mixed_pass<7, INV>(a, b, g.N, Ns, g.inv_ns[p], g.twN); break;
+            case 8: mixed_pass<8, INV>(a, b, g.N, Ns, g.inv_ns[p], g.twN); break;
+            case 11: mixed_pass<11, INV>(a, b, g.N, Ns, g.inv_ns[p], g.twN); break;
+            case 13: mixed_pass<13, INV>(a, b, g.N, Ns, g.inv_ns[p], g.twN); break;
+            default: mixed_pass<16, INV>(a, b, g.N, Ns, g.inv_ns[p], g.twN); break;
         }
         __syncthreads();
         Ns *= R;
