@@ -422,6 +422,55 @@ def run_gpu_arm(args):
                                        "gsamples_per_s": 256 * 2048 / (vms * 1e-3) / 1e9}
         del vout
 
+    # ------------------------------------------------ the reference's own GPU formulation of the echo engine, same device
+    ref_gpu = None
+    if world == 1:
+        from nis_sar import scenes as nsc2
+        from oracle import sar_oracle_torch as ot
+        asc = nsc2.ati_scene(seed=0, num_pulses=8, num_clutter=5000)          # default clutter scene, 8 of 7200 pulses
+        aprm = asc["prm"]
+        apos = np.concatenate([asc["ship_pos"], asc["clutter_pos"]])
+        arcs = np.concatenate([asc["ship_rcs"], asc["clutter_rcs"]])
+        ag = aprm.as_globals()
+        for _ in range(2):
+            rt, _t0 = ot.echo_bistatic_torch(apos, arcs, asc["t_vec"], asc["pos_tx"], asc["vel_tx"], asc["rx_offsets"][0],
+                                             asc["ship_vel"], ag, device=device)
+        torch.cuda.synchronize(device)
+        t0r = time.perf_counter()
+        rt, _t0 = ot.echo_bistatic_torch(apos, arcs, asc["t_vec"], asc["pos_tx"], asc["vel_tx"], asc["rx_offsets"][0],
+                                         asc["ship_vel"], ag, device=device)
+        torch.cuda.synchronize(device)
+        ref_s = time.perf_counter() - t0r
+        tg_list = [{"position": p_, "rcs": r_} for p_, r_ in zip(apos, arcs)]
+        mine = None
+        for _ in range(3):
+            t0m = time.perf_counter()
+            mine, _t0 = api.run_bistatic_physics_gpu(tg_list, asc["t_vec"], asc["pos_tx"], asc["vel_tx"], asc["rx_offsets"][0],
+                                                     asc["ship_vel"], params=aprm, device=device, return_device=True)
+            torch.cuda.synchronize(device)
+            mine_s = time.perf_counter() - t0m
+        err = float(torch.linalg.vector_norm(mine.to(torch.complex128) - rt) / torch.linalg.vector_norm(rt))
+        upd = float(len(arcs)) * 8 * rt.shape[1]
+        asc2 = nsc2.ati_scene(seed=0, num_pulses=512, num_clutter=5000)     # enough pulses to amortise the host set-up
+        for _ in range(2):
+            t0m = time.perf_counter()
+            m2, _t0 = api.run_bistatic_physics_gpu(tg_list, asc2["t_vec"], asc2["pos_tx"], asc2["vel_tx"],
+                                                   asc2["rx_offsets"][0], asc2["ship_vel"], params=aprm, device=device,
+                                                   return_device=True)
+            torch.cuda.synchronize(device)
+            mine512_s = time.perf_counter() - t0m
+        del m2
+        ref_gpu = {"workload": "default ATI clutter scene, 5035 scatterers x 8 of 7200 pulses x 13200 samples",
+                   "reference_torch_eager_on_this_gpu": {"s": ref_s, "g_updates_per_s": upd / ref_s / 1e9,
+                                                         "what": "oracle/sar_oracle_torch.py: the per-pulse eager torch loop of "
+                                                                 "run_bistatic_physics_gpu (sar_ati_dcpa_sim_csa.py:137-178), fp64"},
+                   "this_library_same_call": {"s": mine_s, "g_updates_per_s": upd / mine_s / 1e9,
+                                              "what": "nis_sar.api.run_bistatic_physics_gpu incl. host list -> device arrays"},
+                   "this_library_512_pulses": {"s": mine512_s, "g_updates_per_s": upd * 64 / mine512_s / 1e9},
+                   "rel_l2_between_them": err}
+        del rt, mine
+        torch.cuda.empty_cache()
+
     # ------------------------------------------------ next-row N1: Range-Doppler focusing of a 4096 x 4096 frame
     rda = None
     if world == 1:
@@ -552,6 +601,8 @@ def run_gpu_arm(args):
         line["ati_frame"] = ati
     if other:
         line["other_configs"] = other
+    if ref_gpu is not None:
+        line["reference_gpu_path"] = ref_gpu
     if video is not None:
         line["videosar_frame"] = video
     if rda is not None:

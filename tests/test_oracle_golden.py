@@ -220,3 +220,18 @@ def test_spotlight_echo_and_tdbp_match_reference():
     for tag, vf in (("mbp", g["v_tgt"]), ("stdbp", np.zeros(3))):
         img = orc.tdbp(raw, g["pos_sat"], g["vel_sat"], t0, n, vf, g["t_vec"], 500.0, G, nx=24, ny=24)
         assert _rel(img, g["img_" + tag]) < 1e-6, tag
+
+
+def test_torch_formulation_of_the_echo_engine_matches_the_oracle():
+    """oracle/sar_oracle_torch.py (the reference's own eager-torch structure, timed on the GPU by bench.py) on the CPU."""
+    from oracle import sar_oracle_torch as ot
+    prm = params.spaceborne_preset(fs=60e6, bw=50e6)
+    sc = scenes.ati_scene(seed=5, num_pulses=12, num_clutter=30, prm=prm, t_int=None)
+    pos = np.concatenate([sc["ship_pos"], sc["clutter_pos"]])
+    rcs = np.concatenate([sc["ship_rcs"], sc["clutter_rcs"]])
+    g = prm.as_globals()
+    want, t0 = orc.echo_bistatic(pos, rcs, sc["t_vec"], sc["pos_tx"], sc["vel_tx"], sc["rx_offsets"][0], sc["ship_vel"], g)
+    got, t0t = ot.echo_bistatic_torch(pos, rcs, sc["t_vec"], sc["pos_tx"], sc["vel_tx"], sc["rx_offsets"][0], sc["ship_vel"], g)
+    assert t0 == t0t and got.shape == want.shape
+    assert _rel(got.numpy(), want) < 1e-7
+    assert np.array_equal(got.numpy() != 0, want != 0)
