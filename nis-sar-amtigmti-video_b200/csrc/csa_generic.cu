@@ -15,6 +15,8 @@
 //   Bluestein    (any length <= 8192): x[n] a[n] -> FFT_M -> x FFT_M(b)/M -> IFFT_M -> x a[k], a[n] =
 //                exp(-i pi n^2 / N), M in {64, 256, 1024, 4096, 16384} >= 2N-1, on the register-resident
 //                power-of-two transforms of fft.cuh.
+#include <stdlib.h>
+
 #include <complex>
 
 #include "csa_internal.cuh"
@@ -40,12 +42,17 @@ struct GenDev {   // by-value kernel argument
     const float2* chirp;
     const float2* bfft;
     const float2* tw_pow2;
+    const float2* bfe;      // pruned Bluestein (N <= M/2, M = 16384): even / odd bins of bfft, w_M^n, 8192-point twiddles
+    const float2* bfo;
+    const float2* twm;
+    const float2* tw_half;
 };
 
 struct GenLen {
     int N = 0, kind = 0 /* 0 mixed, 1 Bluestein */, npass = 0, M = 0;
     int radix[kMaxPass] = {};
     float2 *twN = nullptr, *chirp = nullptr, *bfft = nullptr, *tw_pow2 = nullptr;
+    float2 *bfe = nullptr, *bfo = nullptr, *twm = nullptr, *tw_half = nullptr;
     GenDev dev() const {
         GenDev d{};
         d.N = N; d.npass = npass; d.M = M;
@@ -56,9 +63,13 @@ struct GenLen {
             if (i < npass) ns *= (uint64_t)radix[i];
         }
         d.twN = twN; d.chirp = chirp; d.bfft = bfft; d.tw_pow2 = tw_pow2;
+        d.bfe = bfe; d.bfo = bfo; d.twm = twm; d.tw_half = tw_half;
         return d;
     }
-    void release() { cudaFree(twN); cudaFree(chirp); cudaFree(bfft); cudaFree(tw_pow2); }
+    void release() {
+        cudaFree(twN); cudaFree(chirp); cudaFree(bfft); cudaFree(tw_pow2);
+        cudaFree(bfe); cudaFree(bfo); cudaFree(twm); cudaFree(tw_half);
+    }
 };
 
 bool factorize(int n, int* radix, int* npass) {
@@ -296,12 +307,103 @@ __global__ void __launch_bounds__(P::NT) k_row_blue(GenDev g, float2* __restrict
     if (MODE == AZ_INV && max_sq != nullptr) atomic_max_f64(max_sq, warp_max_f64(mx));
 }
 
+// Pruned Bluestein for N <= H = M/2: the product sequence x a is zero on [N, M) and only outputs [0, N) are wanted, so the
+// M-point circular convolution splits into even / odd spectral bins -- two H-point transforms of u and u w_M^n, two H-point
+// inverses A, B, y[n] = A[n] + w_M^-n B[n] -- on the 16-elements-per-thread plan instead of the 32-element one.  u and A
+// are parked in shared memory (each thread re-reads only its own elements).
+template <class P, int PAD, bool INV>
+__device__ __forceinline__ void bluestein_core_pruned(float2* v, int t, float2* sm, float2* park_u, float2* park_a,
+                                                      const GenDev& g) {
+    constexpr int E = P::E, NT = P::NT;
+#pragma unroll
+    for (int s = 0; s < E; ++s) park_u[t + NT * s] = v[s];
+    transform<P, false, 1, PAD>(v, t, sm, g.tw_half);
+#pragma unroll
+    for (int s = 0; s < E; ++s) {
+        const float2 h = __ldg(g.bfe + t + NT * s);
+        v[s] = INV ? cmul_conj(v[s], h) : cmul(v[s], h);
+    }
+    __syncthreads();
+    transform<P, true, 1, PAD>(v, t, sm, g.tw_half);
+#pragma unroll
+    for (int s = 0; s < E; ++s) {
+        park_a[t + NT * s] = v[s];
+        v[s] = cmul(park_u[t + NT * s], __ldg(g.twm + t + NT * s));
+    }
+    __syncthreads();
+    transform<P, false, 1, PAD>(v, t, sm, g.tw_half);
+#pragma unroll
+    for (int s = 0; s < E; ++s) {
+        const float2 h = __ldg(g.bfo + t + NT * s);
+        v[s] = INV ? cmul_conj(v[s], h) : cmul(v[s], h);
+    }
+    __syncthreads();
+    transform<P, true, 1, PAD>(v, t, sm, g.tw_half);
+#pragma unroll
+    for (int s = 0; s < E; ++s) {
+        const int idx = t + NT * s;
+        float2 y = make_float2(0.f, 0.f);
+        if (idx < g.N) {
+            const float2 c = cmul_conj(v[s], __ldg(g.twm + idx));
+            const float2 a = park_a[idx];
+            y = make_float2(a.x + c.x, a.y + c.y);
+            const float2 ch = __ldg(g.chirp + idx);
+            y = INV ? cmul_conj(y, ch) : cmul(y, ch);
+        }
+        v[s] = y;
+    }
+    __syncthreads();
+}
+
+// azimuth transforms (AZ_FWD / AZ_INV) of rows whose length takes the pruned Bluestein core
+template <int MODE, class P, int PAD>
+__global__ void __launch_bounds__(P::NT) k_row_blue_pruned(GenDev g, float2* __restrict__ data, int64_t pitch, int n_rows,
+                                                           float scale, double* __restrict__ max_sq) {
+    extern __shared__ float2 sm[];
+    constexpr int E = P::E, NT = P::NT, H = P::N;
+    constexpr int SMROW = H + (PAD ? (H >> PAD) : 0);
+    float2* const park_u = sm + SMROW;
+    float2* const park_a = park_u + H;
+    const int t = threadIdx.x;
+    double mx = 0.0;
+    for (int row = blockIdx.x; row < n_rows; row += gridDim.x) {
+        float2* p = data + (int64_t)row * pitch;
+        float2 v[E];
+#pragma unroll
+        for (int s = 0; s < E; ++s) {
+            const int idx = t + NT * s;
+            float2 x = make_float2(0.f, 0.f);
+            if (idx < g.N) {
+                const float2 a = __ldg(g.chirp + idx);
+                x = (MODE == AZ_INV) ? cmul_conj(p[idx], a) : cmul(p[idx], a);
+            }
+            v[s] = x;
+        }
+        if (MODE == AZ_INV) bluestein_core_pruned<P, PAD, true>(v, t, sm, park_u, park_a, g);
+        else bluestein_core_pruned<P, PAD, false>(v, t, sm, park_u, park_a, g);
+#pragma unroll
+        for (int s = 0; s < E; ++s) {
+            const int idx = t + NT * s;
+            if (idx < g.N) {
+                float2 x = v[s];
+                if (MODE == AZ_INV) {
+                    x.x *= scale; x.y *= scale;
+                    if (max_sq != nullptr) mx = fmax(mx, sq_mag_f64(x));
+                }
+                p[idx] = x;
+            }
+        }
+    }
+    if (MODE == AZ_INV && max_sq != nullptr) atomic_max_f64(max_sq, warp_max_f64(mx));
+}
+
 // --------------------------------------------------------------------------------------- host side
 using P64 = Plan<64, 8, 8, 8, 1>;
 using P256 = Plan<256, 16, 16, 16, 1>;
 using P1024 = Plan<1024, 16, 16, 8, 8>;
 using P4096 = Plan<4096, 16, 16, 16, 16>;
 using P16384 = Plan<16384, 32, 32, 32, 16>;
+using P8192H = Plan<8192, 16, 16, 8, 8, 8>;
 
 void host_fft(std::vector<std::complex<double>>& a) {   // in-place radix-2, forward
     const size_t n = a.size();
@@ -369,6 +471,20 @@ int build_length(int n, GenLen* g) {
     int rc;
     if ((rc = upload(chirp, &g->chirp)) != NIS_OK) return rc;
     if ((rc = upload(bf, &g->bfft)) != NIS_OK) return rc;
+    if (M == 16384 && n <= 8192) {
+        const int H = M / 2;
+        std::vector<float2> be(H), bo(H), tm(H);
+        for (int k = 0; k < H; ++k) {
+            be[k] = bf[2 * k];
+            bo[k] = bf[2 * k + 1];
+            const double a = -2.0 * pi * (double)k / (double)M;
+            tm[k] = make_float2((float)cos(a), (float)sin(a));
+        }
+        if ((rc = upload(be, &g->bfe)) != NIS_OK) return rc;
+        if ((rc = upload(bo, &g->bfo)) != NIS_OK) return rc;
+        if ((rc = upload(tm, &g->twm)) != NIS_OK) return rc;
+        if ((rc = upload_pow2_twiddles<P8192H>(&g->tw_half)) != NIS_OK) return rc;
+    }
     switch (M) {
         case 64: return upload_pow2_twiddles<P64>(&g->tw_pow2);
         case 256: return upload_pow2_twiddles<P256>(&g->tw_pow2);
@@ -401,6 +517,23 @@ int launch_blue(nis_ctx* ctx, const GenLen& g, float2* data, int64_t pitch, int 
 template <int MODE>
 int launch_row(nis_ctx* ctx, const GenLen& g, float2* data, int64_t pitch, int n_rows, const RowCoef* coef,
                float scale, double* max_sq, cudaStream_t st) {
+    if (g.kind == 1 && g.bfe != nullptr && MODE != RANGE && !getenv("NIS_BLUE_NOPRUNE")) {
+        constexpr int PAD = 4;
+        constexpr int SMROW = P8192H::N + (P8192H::N >> PAD);
+        const size_t smem = (size_t)(SMROW + 2 * P8192H::N) * sizeof(float2);
+        static bool attr_done_dev[64] = {};
+        bool& attr_done = attr_done_dev[nis::current_device() & 63];
+        if (!attr_done) {
+            NIS_CUDA_TRY(cudaFuncSetAttribute(k_row_blue_pruned<MODE, P8192H, PAD>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                              (int)smem));
+            attr_done = true;
+        }
+        int grid = ctx->num_sms;
+        if (grid > n_rows) grid = n_rows;
+        k_row_blue_pruned<MODE, P8192H, PAD><<<grid, P8192H::NT, smem, st>>>(g.dev(), data, pitch, n_rows, scale, max_sq);
+        NIS_LAUNCH_CHECK(ctx);
+        return NIS_OK;
+    }
     if (g.kind == 1) {
         switch (g.M) {
             case 64: return launch_blue<MODE, P64, 3>(ctx, g, data, pitch, n_rows, coef, scale, max_sq, st);
