@@ -755,3 +755,31 @@ def test_abi_error_behaviour_on_device(dev):
     out = plan.focus(torch.ones((64, 128), dtype=torch.complex64, device="cuda"))
     assert torch.isfinite(torch.view_as_real(out)).all()
     plan.close()
+
+
+def test_tdbp_pulse_blocks_and_odd_pulse_counts(api, dev):
+    """Backprojection of a CPI whose pulse count is not a multiple of the kernel's unroll factor, and split into pulse
+    blocks that accumulate into one image (how a CPI can be divided across calls or GPUs): both equal the oracle."""
+    import torch
+    from nis_sar import scenes, targets as tg
+    prm = params.batch_spotlight_preset(fs=60e6, bw=50e6, t_p=2e-6)
+    G = _batch_globals(prm)
+    n_p = 43
+    t_vec = (np.arange(n_p) - (n_p - 1) / 2) / prm.PRF + 0.1
+    pos_sat, vel_sat = scenes.orbit_trajectory(prm, t_vec, along="x")
+    base = tg.generate_destroyer(center_pos=(0, 0, 0))[::4]
+    l_ant = prm.Lambda * prm.R0 / 500.0
+    raw, t0, n, vt = api.run_physics_spotlight(base, t_vec, pos_sat, vel_sat, 10.0, 15.0, l_ant, params=prm)
+    ref = orc.tdbp(raw.cpu().numpy().astype(np.complex128), pos_sat, vel_sat, t0, n, vt, t_vec, 300.0, G, nx=17, ny=23)
+    plan = dev.TdbpPlan(c=prm.C, fc=prm.FC, k_rate=prm.k_rate, t_p=prm.T_p, fs=prm.FS, t_start=t0, n_samples=n,
+                        scene_size=300.0, nx=17, ny=23)
+    rc = plan.range_compress(raw)
+    full = plan.backproject(rc, pos_sat, vel_sat, t_vec, vt)
+    assert full.shape == (23, 17)
+    assert _rel(full.cpu().numpy(), ref) < TOL_L2
+    parts = torch.zeros_like(full)
+    for p0, p1 in ((0, 5), (5, 6), (6, 30), (30, 43)):
+        plan.backproject(rc, pos_sat, vel_sat, t_vec, vt, pulse_range=(p0, p1), out=parts, accumulate=True)
+    assert _rel(parts.cpu().numpy(), ref) < TOL_L2
+    assert _rel(parts.cpu().numpy(), full.cpu().numpy()) < 1e-6
+    plan.close()
