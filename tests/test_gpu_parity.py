@@ -783,3 +783,35 @@ def test_tdbp_pulse_blocks_and_odd_pulse_counts(api, dev):
     assert _rel(parts.cpu().numpy(), ref) < TOL_L2
     assert _rel(parts.cpu().numpy(), full.cpu().numpy()) < 1e-6
     plan.close()
+
+
+def test_rda_and_viewer_device_tensor_paths(api, dev):
+    """Device-resident hand-offs: sar_focus_rda on a complex64 CUDA tensor with return_device=True (the echo never leaves
+    HBM), RdaPlan.focus on row-strided input, SARData on CUDA tensors -- all equal to the host-array paths."""
+    import torch
+    from nis_sar import viewer
+    prm = params.spaceborne_preset(fs=60e6, bw=50e6).replace(T_p=2e-6)
+    args = (prm.Lambda, prm.T_p, prm.k_rate, prm.FS, prm.PRF, prm.V_eff, prm.R0)
+    rng = np.random.default_rng(12)
+    x = (rng.standard_normal((512, 256)) + 1j * rng.standard_normal((512, 256))).astype(np.complex64)   # [ranges, pulses]
+    host = api.sar_focus_rda(x, *args, returns="satellite")
+    xd = torch.from_numpy(x).cuda()
+    devr = api.sar_focus_rda(xd, *args, returns="satellite", return_device=True)
+    assert devr[0].is_cuda and devr[0].shape == (256, 512) and devr[3].shape == (512, 256)
+    assert np.allclose(devr[0].cpu().numpy(), host[0], rtol=0, atol=1e-6 * np.abs(host[0]).max())
+    assert _rel(devr[5].cpu().numpy(), host[5]) < 1e-6
+    # row-strided pulse-major input straight into the plan
+    wide = torch.zeros((256, 600), dtype=torch.complex64, device="cuda")
+    wide[:, :512] = xd.transpose(0, 1)
+    plan = dev.cached_rda_plan(256, 512, lam=prm.Lambda, t_p=prm.T_p, kr=prm.k_rate, fs=prm.FS, prf=prm.PRF, vr=prm.V_eff,
+                               range_grp=prm.R0)
+    out = plan.focus(wide[:, :512])
+    assert np.allclose(out["image_mag"].cpu().numpy(), host[0], rtol=0, atol=1e-6 * np.abs(host[0]).max())
+    # viewer on device tensors ([N_cross, N_range] orientation, like the numpy path)
+    s1 = (rng.standard_normal((40, 60)) + 1j * rng.standard_normal((40, 60))).astype(np.complex64)
+    s2 = (s1 * np.exp(0.2j)).astype(np.complex64)
+    a = viewer.SARData(s1, s2)
+    b = viewer.SARData(torch.from_numpy(s1).cuda(), torch.from_numpy(s2).cuda())
+    for m in viewer.MODES:
+        assert np.array_equal(a.get(m), b.get(m)), m
+    assert abs(b.balance() + 0.2) < 1e-5          # angle(mean(s1 conj(s1 e^{0.2j}))) = -0.2
