@@ -589,7 +589,8 @@ int az_cluster_setup(nis_csa_plan* pl) {
 
 struct AzSplit { int n, a1, a2; };
 const AzSplit kAzSplits[] = {{64, 4, 16},     {128, 8, 16},    {256, 16, 16},   {512, 8, 64},    {1024, 16, 64},
-                             {2048, 8, 256},  {4096, 16, 256}, {8192, 16, 512}, {16384, 16, 1024}};
+                             {2048, 8, 256},  {4096, 16, 256}, {8192, 16, 512}, {16384, 16, 1024},
+                             {32768, 32, 1024}};   // sar_vehicle_sim.py focuses 32768 pulses (:43)
 
 struct AzClusterCfg { int n_az, id; int (*setup)(nis_csa_plan*); };
 const AzClusterCfg kAzCluster[] = {
@@ -629,6 +630,8 @@ int setup_az_four_step(nis_csa_plan* pl) {
                 pl->outer_inv_mag = launch_outer_inv_mag<4>; break;
         case 8: pl->outer_fwd = launch_outer_fwd<8>; pl->outer_inv = launch_outer_inv<8, 16, 16>;
                 pl->outer_inv_mag = launch_outer_inv_mag<8>; break;
+        case 32: pl->outer_fwd = launch_outer_fwd<32>; pl->outer_inv = launch_outer_inv<32, 16, 16>;
+                 pl->outer_inv_mag = launch_outer_inv_mag<32>; break;
         default: pl->outer_fwd = launch_outer_fwd<16>; pl->outer_inv = launch_outer_inv<16, 16, 16>;
                  pl->outer_inv_mag = launch_outer_inv_mag<16>;
                  if (const char* v = getenv("NIS_OUTER_INV")) {   // tuning knob (development only)
@@ -790,7 +793,7 @@ extern "C" int nis_csa_plan_create(nis_ctx* ctx, int32_t n_az, int32_t n_rg, con
     NIS_REQUIRE(ctx && prm && out, "nis_csa_plan_create: null argument");
     const int cls = nis_csa_size_class(n_az, n_rg);
     if (!cls) {
-        set_error("nis_csa_plan_create: size %d x %d not supported (per axis: power of two 64..16384, or any length "
+        set_error("nis_csa_plan_create: size %d x %d not supported (azimuth: power of two 64..32768, range: power of two 64..16384; or per axis any length "
                   "<= 14000 whose prime factors are <= 13, or any length <= 8192)", n_az, n_rg);
         return NIS_ERR_UNSUPPORTED;
     }

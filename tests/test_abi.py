@@ -54,6 +54,7 @@ def test_size_classes():
     assert lib.nis_csa_size_class(4096, 4096) == 1
     assert lib.nis_csa_size_class(8192, 8192) == 1
     assert lib.nis_csa_size_class(64, 16384) == 1
+    assert lib.nis_csa_size_class(32768, 2048) == 1       # the aperture sar_vehicle_sim.py focuses (:43)
     assert lib.nis_csa_size_class(48, 4096) == 2          # general-size path (mixed radix)
     assert lib.nis_csa_size_class(7199, 13200) == 2       # the reference's default scene
     assert lib.nis_csa_size_class(8209, 4096) == 0        # prime > 8192: no engine

@@ -162,7 +162,7 @@ def test_csa_random_input_vs_oracle(api, n_az, n_rg):
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("n_az,az_cfg", [(1024, 1), (2048, 1), (2048, 2), (4096, 0), (4096, 1), (4096, 2), (4096, 3),
-                                         (4096, 4), (8192, 1), (8192, 2), (8192, 3), (16384, 1)])
+                                         (4096, 4), (8192, 1), (8192, 2), (8192, 3), (16384, 1), (32768, 0)])
 def test_csa_azimuth_engines_vs_oracle(api, dev, n_az, az_cfg, monkeypatch):
     """Every azimuth engine of the power-of-two path -- the two-kernel four-step (0) and each thread-block-cluster
     configuration (cluster size x per-CTA transform length x tile width) -- against the oracle, selected with the
@@ -468,11 +468,13 @@ def test_rda_golden_reference_vectors(api, tag):
 
 
 @pytest.mark.parametrize("n_ranges,n_pulses,t_p", [(1024, 512, 2e-6), (2048, 2048, 5e-6), (1000, 360, 3e-6),
-                                                   (4096, 256, 1e-5), (520, 4096, 1e-6), (8192, 64, 1e-5), (13200, 45, 1e-5)])
+                                                   (4096, 256, 1e-5), (520, 4096, 1e-6), (8192, 64, 1e-5), (13200, 45, 1e-5),
+                                                   (256, 32768, 1e-6)])
 def test_rda_vs_oracle(api, n_ranges, n_pulses, t_p):
     """Larger frames against the numpy oracle: matched filters of 61 ... 6001 taps (FFT lengths 1024 ... 16384),
     four-step and row-DFT azimuth engines, migration of several range cells at the band edge; 8192 samples take the pruned
-    16384-point range compression (two 8192-point transforms each way), 13200 the unpruned one."""
+    16384-point range compression (two 8192-point transforms each way), 13200 the unpruned one; 32768 pulses is the aperture
+    sar_vehicle_sim.py focuses (:43): radix-32 outer azimuth stage."""
     prm = params.spaceborne_preset(fs=60e6 if t_p < 1e-5 else 600e6, bw=50e6).replace(T_p=t_p)
     rng = np.random.default_rng(n_ranges + n_pulses)
     x = (rng.standard_normal((n_ranges, n_pulses)) + 1j * rng.standard_normal((n_ranges, n_pulses))).astype(np.complex64)

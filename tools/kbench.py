@@ -55,6 +55,22 @@ def csa_stages(n_az, n_rg, iters=10):
     print(json.dumps(rec), flush=True)
 
 
+def rda_vehicle(iters=5):
+    """sar_vehicle_sim.py's own frame: 32768 pulses x 2048 samples, 1 us / 300 MHz chirp sampled at 360 MHz (361 taps)."""
+    prm = params.airborne_vehicle_preset()
+    n_pulses, n_ranges = 32768, 2048
+    plan = dev.RdaPlan(n_pulses, n_ranges, lam=prm.Lambda, t_p=prm.T_p, kr=prm.k_rate, fs=360e6, prf=prm.PRF, vr=prm.V_sat,
+                       range_grp=prm.R0)
+    x = torch.view_as_complex(torch.randn((n_pulses, n_ranges, 2), device="cuda"))
+    ms = time_cuda(lambda: plan.focus(x), iters)
+    ms_all = time_cuda(lambda: plan.focus(x, want=plan.EXPORTS), iters)
+    px = n_pulses * n_ranges
+    print(json.dumps({"what": "rda_vehicle_frame", "n_pulses": n_pulses, "n_ranges": n_ranges, "ms_image_only": ms,
+                      "Mpixel_per_s": px / ms * 1e-3, "frac_60B": 60.0 * px / ms * 1e-6 / PEAK, "ms_with_4_exports": ms_all}),
+          flush=True)
+    plan.close()
+
+
 def rda(n_pulses, n_ranges, iters=10, t_p=10e-6):
     """Range-Doppler focusing.  Algorithmic bytes per pixel: range compression 16 + azimuth DFT 16 + RCMC/azimuth
     compression 16 + inverse DFT to magnitude 12 = 60 (image only; each exported map adds 8)."""
@@ -143,6 +159,8 @@ if __name__ == "__main__":
             csa_stages(int(a), int(b))
         elif k == "tdbp":
             tdbp(*(int(v) for v in arg.split("x"))) if arg else tdbp()
+        elif k == "rda_vehicle":
+            rda_vehicle()
         elif k == "rda":
             a, b = arg.split("x")
             rda(int(a), int(b))
