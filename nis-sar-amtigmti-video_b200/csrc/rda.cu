@@ -76,6 +76,48 @@ __global__ void __launch_bounds__(P::NT) k_rda_range(const float2* __restrict__ 
     }
 }
 
+// Overlap-save variant for filters too long for one block (the satellite scripts compress 13200-sample pulses with a
+// 12001-tap filter: 19200 > 16384): block b produces outputs [b B, (b+1) B), B = M - L + 1, from the M inputs that end at its
+// last output (zero outside the pulse); the first L - 1 samples of every block's circular convolution are discarded.
+template <class P, int PAD>
+__global__ void __launch_bounds__(P::NT) k_rda_range_blocked(const float2* __restrict__ in, int64_t in_pitch,
+                                                             float2* __restrict__ work, int64_t work_pitch,
+                                                             float2* __restrict__ rc_out, int n_rows, int N, int s0, int L,
+                                                             int n_blocks, const float2* __restrict__ Hf,
+                                                             const float* __restrict__ win, const float2* __restrict__ tw) {
+    extern __shared__ float2 sm[];
+    constexpr int E = P::E, NT = P::NT, M = P::N;
+    const int B = M - L + 1;
+    const int t = threadIdx.x;
+    const int total = n_rows * n_blocks;
+    for (int job = blockIdx.x; job < total; job += gridDim.x) {
+        const int row = job / n_blocks, o0 = (job % n_blocks) * B;
+        const int in0 = o0 + s0 - (L - 1);
+        const float2* p = in + (int64_t)row * in_pitch;
+        float2 v[E];
+#pragma unroll
+        for (int s = 0; s < E; ++s) {
+            const int xi = in0 + t + NT * s;
+            v[s] = (xi >= 0 && xi < N) ? p[xi] : make_float2(0.f, 0.f);
+        }
+        transform<P, false, 1, PAD>(v, t, sm, tw);
+#pragma unroll
+        for (int s = 0; s < E; ++s) v[s] = cmul_pk(v[s], __ldg(Hf + t + NT * s));
+        __syncthreads();
+        transform<P, true, 1, PAD>(v, t, sm, tw);
+        const float w = win[row];
+#pragma unroll
+        for (int s = 0; s < E; ++s) {
+            const int j = t + NT * s, o = o0 + j - (L - 1);
+            if (j >= L - 1 && o < N) {
+                if (rc_out != nullptr) rc_out[(int64_t)row * N + o] = v[s];
+                work[(int64_t)row * work_pitch + o] = make_float2(v[s].x * w, v[s].y * w);
+            }
+        }
+        __syncthreads();
+    }
+}
+
 // Pruned variant for N <= M/2 (the common case: the pulse is at most half of the padded length).  The upper half of the
 // input is zero, so the M-point spectrum splits into two H = M/2-point transforms of x[n] and x[n] w_M^n (even / odd
 // bins), and the M-point inverse into y[n] = A[n mod H] +- w_M^-(n mod H) B[n mod H] with A, B the H-point inverses of the
@@ -307,6 +349,28 @@ int launch_rda_range(nis_rda_plan* pl, const float2* in, int64_t pitch, float2* 
 }
 
 template <class P, int PAD>
+int launch_rda_range_blocked(nis_rda_plan* pl, const float2* in, int64_t pitch, float2* rc_out, cudaStream_t st) {
+    constexpr int SMROW = P::N + (PAD ? (P::N >> PAD) : 0);
+    const size_t smem = (size_t)SMROW * sizeof(float2);
+    static bool attr_done_dev[64] = {};
+    bool& attr_done = attr_done_dev[nis::current_device() & 63];
+    if (!attr_done) {
+        NIS_CUDA_TRY(cudaFuncSetAttribute(k_rda_range_blocked<P, PAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_done = true;
+    }
+    const int B = P::N - pl->taps + 1, n_blocks = (pl->S + B - 1) / B;
+    int per_sm = 1;
+    NIS_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_rda_range_blocked<P, PAD>, P::NT, smem));
+    const int jobs = pl->P * n_blocks;
+    int grid = pl->ctx->num_sms * (per_sm < 1 ? 1 : per_sm);
+    if (grid > jobs) grid = jobs;
+    k_rda_range_blocked<P, PAD><<<grid, P::NT, smem, st>>>(in, pitch, pl->work, pl->S, rc_out, pl->P, pl->S, pl->s0, pl->taps,
+                                                            n_blocks, pl->Hf, pl->win, pl->tw);
+    NIS_LAUNCH_CHECK(pl->ctx);
+    return NIS_OK;
+}
+
+template <class P, int PAD>
 int launch_rda_range_pruned(nis_rda_plan* pl, const float2* in, int64_t pitch, float2* rc_out, cudaStream_t st) {
     constexpr int SMROW = P::N + (PAD ? (P::N >> PAD) : 0);
     const size_t smem = (size_t)(SMROW + P::N) * sizeof(float2);
@@ -338,7 +402,8 @@ int upload_tw(float2** dev) {
 bool rda_sizes_ok(int P, int S, const nis_rda_params& prm, int* M_out) {
     if (P < 2 || S < 2 || S > 24576) return false;
     const int taps = mf_taps(prm);
-    const int M = conv_fft_len(S, taps);
+    int M = conv_fft_len(S, taps);
+    if (M == 0 && taps >= 1 && taps <= 14337) M = 16384;   // overlap-save blocks of >= 2048 outputs
     if (taps < 1 || M == 0) return false;
     if (M_out) *M_out = M;
     return (az_engine_supported(P, S)) || (rowdft_supported(P));
@@ -377,8 +442,8 @@ extern "C" int nis_rda_plan_create(nis_ctx* ctx, int32_t P, int32_t S, const nis
                 "nis_rda_plan_create: non-physical parameters");
     int M = 0;
     if (!rda_sizes_ok(P, S, *prm, &M)) {
-        set_error("nis_rda_plan_create: %d pulses x %d samples with a %d-tap matched filter is not supported (samples + "
-                  "taps/2 <= 16384; pulses: power of two 64..32768 with samples %% 32 == 0, or any length the row-DFT "
+        set_error("nis_rda_plan_create: %d pulses x %d samples with a %d-tap matched filter is not supported (taps <= "
+                  "14337, samples <= 24576; pulses: power of two 64..32768 with samples %% 32 == 0, or any length the row-DFT "
                   "engine takes)", P, S, mf_taps(*prm));
         return NIS_ERR_UNSUPPORTED;
     }
@@ -443,7 +508,8 @@ extern "C" int nis_rda_plan_create(nis_ctx* ctx, int32_t P, int32_t S, const nis
     }
     // measured: the pruned form wins only where the unpruned one needs the 32-elements-per-thread plan (M = 16384: 1.30 ->
     // 1.09 ms at 8192 rows); at M = 8192 its 256-thread CTAs run four dependent transforms per row and lose (0.22 -> 0.45 ms)
-    const bool prune = (2 * S <= M) && M == 16384 && !getenv("NIS_RDA_NOPRUNE");
+    const bool blocked = conv_fft_len(S, pl->taps) == 0;   // the filter does not fit one block with the pulse
+    const bool prune = !blocked && (2 * S <= M) && M == 16384 && !getenv("NIS_RDA_NOPRUNE");
     if (prune) {
         const int H = M / 2;
         std::vector<float2> hf(M), he(H), ho(H), twm(H);
@@ -462,7 +528,10 @@ extern "C" int nis_rda_plan_create(nis_ctx* ctx, int32_t P, int32_t S, const nis
         CUDA_FAIL_IF(cudaMemcpy(pl->HfO, ho.data(), H * sizeof(float2), cudaMemcpyHostToDevice));
         CUDA_FAIL_IF(cudaMemcpy(pl->twM, twm.data(), H * sizeof(float2), cudaMemcpyHostToDevice));
     }
-    if (prune) {
+    if (blocked) {
+        pl->range_fn = launch_rda_range_blocked<P16384, 5>;
+        FAIL_IF(upload_tw<P16384>(&pl->tw));
+    } else if (prune) {
         pl->range_fn = launch_rda_range_pruned<P8192, 4>;
         FAIL_IF(upload_tw<P8192>(&pl->tw));
     } else

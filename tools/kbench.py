@@ -161,9 +161,9 @@ if __name__ == "__main__":
             tdbp(*(int(v) for v in arg.split("x"))) if arg else tdbp()
         elif k == "rda_vehicle":
             rda_vehicle()
-        elif k == "rda":
-            a, b = arg.split("x")
-            rda(int(a), int(b))
+        elif k == "rda":       # rda:PULSESxSAMPLES[xPULSE_WIDTH_US]
+            parts = arg.split("x")
+            rda(int(parts[0]), int(parts[1]), t_p=float(parts[2]) * 1e-6 if len(parts) > 2 else 10e-6)
         elif k == "gmti":
             gmti(int(arg))
         elif k == "echo":
