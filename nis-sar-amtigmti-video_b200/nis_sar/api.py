@@ -219,6 +219,19 @@ def calculate_snr_db(r_slant, rcs, wavelength, bandwidth, t_int, p_tx=None, ant_
     return 10 * np.log10(numerator / denominator), gain_db
 
 
+def calculate_raw_snr_db(r_slant, rcs, wavelength, bandwidth, ant_l, p_tx=1000.0, ant_w=0.5, t_sys=290.0, nf_db=5.0,
+                         loss_db=3.0):
+    """Single-pulse (un-integrated) radar-equation SNR of sar_batch_sim.py:53-63 (its module constants as defaults)."""
+    ant_area = ant_l * ant_w
+    effective_area = ant_area * 0.6
+    gain = 4 * np.pi * effective_area / (wavelength ** 2)
+    nf = 10 ** (nf_db / 10)
+    loss = 10 ** (loss_db / 10)
+    numerator = p_tx * (gain ** 2) * (wavelength ** 2) * rcs
+    denominator = ((4 * np.pi) ** 3) * (r_slant ** 4) * K_BOLTZ * t_sys * bandwidth * loss * nf
+    return 10 * np.log10(numerator / denominator)
+
+
 def _draw_seed(seed):
     # the reference draws from numpy's global generator; so does the default seed, which keeps np.random.seed() meaningful
     return int(np.random.randint(0, 2 ** 31 - 1)) * 2654435761 + 12345 if seed is None else int(seed)

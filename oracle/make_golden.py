@@ -197,6 +197,10 @@ def golden_noise():
             np.random.seed(11)
             out[f"{key}_noisy_nu{nu}"] = noise_fn(raw, 17.0, 10.0, nu)
     out["raw"] = raw
+    raw_fn = ref_extract.batch_snr_function()
+    bargs = np.array([[6.1e5, 5000.0, 0.031, 5.0e8, 37.9], [6.1e5, 5.0, 0.031, 5.0e8, 9.5]])
+    out["batch_snr_args"] = bargs
+    out["batch_snr"] = np.array([raw_fn(*a) for a in bargs])
     np.savez_compressed(os.path.join(OUT, "noise.npz"), **out)
 
 

@@ -172,3 +172,10 @@ def batch_functions(g: dict):
     ns.update({k: g[k] for k in ("C", "R0", "FC", "T_P", "K_RATE", "FS", "Lambda")})
     f = _extract("sar_batch_sim.py", ("run_physics_spotlight", "tdbp_gpu"), ns)
     return _quiet(f["run_physics_spotlight"]), _quiet(f["tdbp_gpu"])
+
+
+def batch_snr_function():
+    """``calculate_raw_snr_db`` of sar_batch_sim.py:53-63 with its module constants."""
+    ns = {"np": np}
+    ns.update(_constants("sar_batch_sim.py", ("P_TX", "ANT_WIDTH", "T_SYS", "NF_DB", "LOSS_DB", "K_BOLTZ")))
+    return _extract("sar_batch_sim.py", ("calculate_raw_snr_db",), ns)["calculate_raw_snr_db"]

@@ -195,6 +195,8 @@ def test_api_snr_matches_reference():
     for key in ("satellite", "vehicle"):
         for a, r in zip(g[f"{key}_snr_args"], g[f"{key}_snr"]):
             assert np.array_equal(np.array(api.calculate_snr_db(*a, preset=key)), r)
+    for a, r in zip(g["batch_snr_args"], g["batch_snr"]):
+        assert api.calculate_raw_snr_db(*a) == r               # sar_batch_sim.py:53-63
 
 
 # ------------------------------------------------------------------------------------------ viewer data layer (N3)
