@@ -743,9 +743,11 @@ def test_abi_error_behaviour_on_device(dev):
     with pytest.raises(NisError, match="complex64"):
         plan.focus(torch.zeros((64, 128), dtype=torch.complex128, device="cuda"))
     rk = dict(lam=prm.Lambda, t_p=prm.T_p, kr=prm.k_rate, fs=prm.FS, prf=prm.PRF, vr=prm.V_eff, range_grp=prm.R0)
-    assert not dev.RdaPlan.supported(64, 20000, **rk)             # 20000 samples + 6000 taps do not fit a 16384-point FFT
+    assert dev.RdaPlan.supported(64, 20000, **rk)                 # long filter + long pulse: overlap-save blocks
+    assert not dev.RdaPlan.supported(64, 30000, **rk)             # a 30000-sample row does not fit the RCMC row buffer
+    assert not dev.RdaPlan.supported(64, 4096, **{**rk, "t_p": 3e-5})   # 18001 taps: no block left for outputs
     with pytest.raises(NisError, match="not supported"):
-        dev.RdaPlan(64, 20000, **rk)
+        dev.RdaPlan(64, 30000, **rk)
     with pytest.raises(NisError, match="taps"):
         dev.TdbpPlan(c=prm.C, fc=prm.FC, k_rate=prm.k_rate, t_p=1e-3, fs=600e6, t_start=0.0, n_samples=1024, scene_size=100.0)
     with pytest.raises(NisError, match="shape"):
