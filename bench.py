@@ -422,6 +422,37 @@ def run_gpu_arm(args):
                                        "gsamples_per_s": 256 * 2048 / (vms * 1e-3) / 1e9}
         del vout
 
+    # ------------------------------------------------ DPCA/ATI stage alone, beside the reference's seven numpy passes
+    gmti_line = None
+    if world == 1:
+        from oracle import sar_oracle as orc3
+        ng = 4096
+        ga = torch.view_as_complex(torch.randn((ng, ng, 2), device=device))
+        gb = torch.view_as_complex(torch.randn((ng, ng, 2), device=device))
+        for _ in range(3):
+            dev.gmti_fused(ga, gb, lazy=True)
+        torch.cuda.synchronize(device)
+        eg0, eg1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        cur = torch.cuda.current_stream(device)
+        eg0.record(cur)
+        for _ in range(20):
+            dev.gmti_fused(ga, gb, lazy=True)
+        eg1.record(cur)
+        torch.cuda.synchronize(device)
+        g_ms = eg0.elapsed_time(eg1) / 20
+        hs = 2048
+        h1 = ga[:hs, :hs].cpu().numpy().astype(np.complex128)
+        h2 = gb[:hs, :hs].cpu().numpy().astype(np.complex128)
+        tg0 = time.perf_counter()
+        orc3.gmti_products(h1, h2)
+        g_cpu = time.perf_counter() - tg0
+        gmti_line = {"workload": "4096 x 4096 channel pair, all products + detection list (49 B per pixel pair)",
+                     "ms": g_ms, "mpixel_pairs_per_s": ng * ng / (g_ms * 1e-3) / 1e6,
+                     "achieved_GBps": 49.0 * ng * ng / (g_ms * 1e-3) / 1e9,
+                     "cpu_port": {"mpixel_pairs_per_s": hs * hs / g_cpu / 1e6, "cores": 1,
+                                  "sample": f"the inline numpy block (sar_ati_dcpa_sim_csa.py:414-419, :447-449) on a 2048 x 2048 pair, {g_cpu:.1f} s"}}
+        del ga, gb
+
     # ------------------------------------------------ the reference's own GPU formulation of the echo engine, same device
     ref_gpu = None
     if world == 1:
@@ -583,6 +614,7 @@ def run_gpu_arm(args):
         "gpu_launches": int(launches),
         "roofline": {"bound": "hbm", "kernel": f"csa:{dom}", "achieved": dom_gbs, "peak": peak_gbs, "unit": "GB/s",
                      "frac": dom_gbs / peak_gbs, "traffic": traffic, "peak_source": peak_src,
+                     "frac_of_nameplate_8TBps": dom_gbs / 8000.0,
                      "algorithmic_bytes_per_launch": STAGE_ALGO_BYTES_PER_PIXEL * pixels,
                      "launch_ms": stage[dom],
                      "csa_whole": {"achieved": csa_gbs, "frac": csa_gbs / peak_gbs,
@@ -599,6 +631,9 @@ def run_gpu_arm(args):
     if ati is not None:
         ati["frac_of_hbm_peak"] = ati["achieved_GBps"] / peak_gbs
         line["ati_frame"] = ati
+    if gmti_line is not None:
+        gmti_line["frac_of_hbm_peak"] = gmti_line["achieved_GBps"] / peak_gbs
+        line["gmti_stage"] = gmti_line
     if other:
         line["other_configs"] = other
     if ref_gpu is not None:
