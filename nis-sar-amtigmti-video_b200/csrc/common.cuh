@@ -134,6 +134,16 @@ __host__ __device__ __forceinline__ float2 cmul_conj_pk(float2 a, float2 b) {   
     return cmul_conj(a, b);
 #endif
 }
+// s * a - b with a real s: one step of a three-term recurrence on a complex sequence (one FFMA2)
+__host__ __device__ __forceinline__ float2 cfms_pk(float s, float2 a, float2 b) {
+#ifdef __CUDA_ARCH__
+    unsigned long long r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(pk2(s, s)), "l"(pk2(a.x, a.y)), "l"(pk2(-b.x, -b.y)));
+    return upk2(r);
+#else
+    return make_float2(fmaf(s, a.x, -b.x), fmaf(s, a.y, -b.y));
+#endif
+}
 __host__ __device__ __forceinline__ float2 cscale_pk(float2 a, float s) {   // a * real s
 #ifdef __CUDA_ARCH__
     unsigned long long r;
