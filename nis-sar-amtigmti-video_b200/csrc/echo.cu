@@ -59,6 +59,7 @@ __global__ void __launch_bounds__(256) k_echo(EchoConst k, EchoTail<SPT> tail, c
     constexpr int CH = 256 * SPT;
     constexpr int HALF = SPT / 2;
     __shared__ uint4 rec[256];
+    __shared__ float2 recv[256];   // cis(per-sample phase step) of each kept scatterer at the chunk centre
     __shared__ int warp_cnt[8];
 
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
@@ -71,6 +72,7 @@ __global__ void __launch_bounds__(256) k_echo(EchoConst k, EchoTail<SPT> tail, c
     // per-thread constants of the common quadratic term: A mt^2 and 2 A mt (mod 1)
     const uint32_t k1 = frac32(k.a_turns * (double)mt * (double)mt);
     const uint32_t k2 = frac32(2.0 * k.a_turns * (double)mt);
+    const float2 vk2 = cis_u32(k2);   // this thread's share of the phase step: cis(delta_t) = cis(s.y) cis(k2)
 
     const double ti = t_slow[pulse];
     const double tx0 = pos_tx[3 * pulse], tx1 = pos_tx[3 * pulse + 1], tx2 = pos_tx[3 * pulse + 2];
@@ -154,7 +156,10 @@ __global__ void __launch_bounds__(256) k_echo(EchoConst k, EchoTail<SPT> tail, c
             if (w < wid) off += cw;
             total += cw;
         }
-        if (keep) rec[off] = r;
+        if (keep) {
+            rec[off] = r;
+            recv[off] = cis_u32(r.y);
+        }
         __syncthreads();
 
         // ------------------------------------------------ inner loop: every thread, every kept scatterer
@@ -164,11 +169,8 @@ __global__ void __launch_bounds__(256) k_echo(EchoConst k, EchoTail<SPT> tail, c
             const int lo = (int)(s.w & 0xffffu), hi = (int)(s.w >> 16);
             if (t_lo >= hi || t_hi <= lo) continue;
             const uint32_t phi = s.x + s.y * (uint32_t)mt + k1;
-            const uint32_t dlt = s.y + k2;
-            const float a = __uint_as_float(s.z);
-            float2 u = cis_u32(phi);
-            u.x *= a; u.y *= a;
-            const float2 v = cis_u32(dlt);
+            const float2 u = cscale_pk(cis_u32(phi), __uint_as_float(s.z));
+            const float2 v = cmul_pk(recv[q], vk2);
             // the samples of one scatterer are a geometric sequence u v^k, and any such sequence obeys the three-term
             // recurrence p[k+1] = 2 cos(delta) p[k] - p[k-1] (v + 1/v = 2 cos delta): TWO FMAs per new complex term instead
             // of the four of a complex multiply.  Two chains run outward from the centre sample (forward f, backward b),
@@ -176,8 +178,8 @@ __global__ void __launch_bounds__(256) k_echo(EchoConst k, EchoTail<SPT> tail, c
             // an error of the coefficient by at most k^2 / 2 over k steps; k <= SPT/2 here (<= 3e-5 relative, reached only
             // where the chirp's instantaneous frequency is near zero).
             const float c2 = 2.0f * v.x;
-            float2 f0 = u, f1 = cmul(u, v);
-            float2 b0 = cmul_conj(u, v), b1 = cfms_pk(c2, b0, u);
+            float2 f0 = u, f1 = cmul_pk(u, v);
+            float2 b0 = cmul_conj_pk(u, v), b1 = cfms_pk(c2, b0, u);
             if (t_lo >= lo && t_hi <= hi) {
 #pragma unroll
                 for (int i = 0; i < HALF; i += 2) {
