@@ -51,7 +51,8 @@ __device__ __forceinline__ bool gate(const double* __restrict__ t_fast, int n, d
 
 // SPOT: the spotlight model is a separate instantiation, so that the stripmap engines keep their register budget
 template <int SPT, bool SPOT>
-__global__ void __launch_bounds__(256) k_echo(EchoConst k, EchoTail<SPT> tail, const double* __restrict__ pos0,
+// resident CTAs per SM: 3 at 16 samples per thread (<= 85 registers), 4 at 8 (<= 64); measured -- one CTA fewer costs 12-25 %
+__global__ void __launch_bounds__(256, SPOT ? 1 : (SPT == 16 ? 3 : 4)) k_echo(EchoConst k, EchoTail<SPT> tail, const double* __restrict__ pos0,
                                               const double* __restrict__ vel, const double* __restrict__ amp,
                                               const double* __restrict__ pos_tx, const double* __restrict__ pos_rx,
                                               const double* __restrict__ t_slow, const double* __restrict__ t_fast,
