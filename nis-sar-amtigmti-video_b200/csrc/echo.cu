@@ -51,8 +51,9 @@ __device__ __forceinline__ bool gate(const double* __restrict__ t_fast, int n, d
 
 // SPOT: the spotlight model is a separate instantiation, so that the stripmap engines keep their register budget
 template <int SPT, bool SPOT>
-// resident CTAs per SM: 3 at 16 samples per thread (<= 85 registers), 4 at 8 (<= 64); measured -- one CTA fewer costs 12-25 %
-__global__ void __launch_bounds__(256, SPOT ? 1 : (SPT == 16 ? 3 : 4)) k_echo(EchoConst k, EchoTail<SPT> tail, const double* __restrict__ pos0,
+// four resident CTAs per SM (<= 64 registers; 24 bytes of spills at 16 samples per thread): measured -- 3 CTAs at 75
+// registers are 7 % slower on sparse scenes and equal on dense ones, 2 CTAs at 94 registers 12-25 % slower
+__global__ void __launch_bounds__(256, SPOT ? 1 : 4) k_echo(EchoConst k, EchoTail<SPT> tail, const double* __restrict__ pos0,
                                               const double* __restrict__ vel, const double* __restrict__ amp,
                                               const double* __restrict__ pos_tx, const double* __restrict__ pos_rx,
                                               const double* __restrict__ t_slow, const double* __restrict__ t_fast,
