@@ -402,10 +402,9 @@ def run_gpu_arm(args):
         torch.cuda.empty_cache()
         # configs[2]: dense vehicle scene, 1e5 scatterers, airborne geometry (S = 2048); a 256-pulse block of the 32768
         from nis_sar import scenes as nsc
-        from oracle import sar_oracle as orc2
         vs = nsc.vehicle_scene(seed=0, num_pulses=256, num_scatterers=100000)
         vpr = vs["prm"]
-        vkw = dict(c=vpr.C, fc=vpr.FC, k_rate=vpr.k_rate, t_p=vpr.T_p, t_start=orc2.vehicle_window_start(vpr.as_globals()),
+        vkw = dict(c=vpr.C, fc=vpr.FC, k_rate=vpr.k_rate, t_p=vpr.T_p, t_start=(2 * vpr.R0 / vpr.C) - (2048 / 360e6) / 2,   # sar_vehicle_sim.py:89
                    fs=360e6, n_samples=2048, device=device)
         vargs = (vs["pos"], np.zeros(3), vs["rcs"], vs["pos_sat"], None, vs["t_vec"])
         vout = dev.echo_accumulate(*vargs, **vkw)
