@@ -820,3 +820,47 @@ def test_rda_and_viewer_device_tensor_paths(api, dev):
     for m in viewer.MODES:
         assert np.array_equal(a.get(m), b.get(m)), m
     assert abs(b.balance() + 0.2) < 1e-5          # angle(mean(s1 conj(s1 e^{0.2j}))) = -0.2
+
+
+def test_full_size_properties_of_the_widened_rows(api, dev):
+    """Size-independent properties at the sizes the reference actually runs (the oracle would take minutes there):
+    RDA 8192 x 8192 with a 6001-tap filter -- the complex exports are linear in the input and the image of a scaled input
+    scales; TDBP of a full 2500-pulse x 22004-sample CPI on 512 x 512 pixels -- linear in the echo, and the destroyer
+    focuses at the scene centre when the pixels move with it (mBP) but smears when they do not (StdBP)."""
+    import torch
+    from nis_sar import scenes, targets as tg
+    # ---- RDA
+    prm = params.spaceborne_preset().replace(T_p=10e-6)
+    n = 8192
+    plan = dev.RdaPlan(n, n, lam=prm.Lambda, t_p=prm.T_p, kr=prm.k_rate, fs=prm.FS, prf=prm.PRF, vr=prm.V_eff, range_grp=prm.R0)
+    g = torch.Generator(device="cuda").manual_seed(3)
+    a = torch.view_as_complex(torch.randn((n, n, 2), generator=g, device="cuda"))
+    b = torch.view_as_complex(torch.randn((n, n, 2), generator=g, device="cuda"))
+    ra = plan.focus(a, want=("range_doppler_filtered",))
+    fa, ia = ra["range_doppler_filtered"].clone(), ra["image_mag"].clone()
+    fb = plan.focus(b, want=("range_doppler_filtered",))["range_doppler_filtered"].clone()
+    fab = plan.focus(a + 2.0 * b, want=("range_doppler_filtered",))["range_doppler_filtered"]
+    err = float(torch.linalg.vector_norm(fab - (fa + 2.0 * fb)) / torch.linalg.vector_norm(fab))
+    assert err < 1e-5, err
+    i3 = plan.focus(3.0 * a)["image_mag"]
+    assert float(torch.linalg.vector_norm(i3 - 3.0 * ia) / torch.linalg.vector_norm(i3)) < 1e-6
+    plan.close()
+    del a, b, fa, fb, fab, ia, i3
+    torch.cuda.empty_cache()
+    # ---- spotlight echo + TDBP at the reference's own frame size
+    vp = params.batch_spotlight_preset()
+    n_p = 2500
+    t_vec = (np.arange(n_p) - (n_p - 1) / 2) / vp.PRF
+    pos_sat, vel_sat = scenes.orbit_trajectory(vp, t_vec, along="x")
+    ship = tg.generate_destroyer(center_pos=(0, 0, 0))
+    l_ant = vp.Lambda * vp.R0 / 500.0
+    raw, t0, ns, vt = api.run_physics_spotlight(ship, t_vec, pos_sat, vel_sat, 45.0, 15.0, l_ant, params=vp)
+    assert raw.shape == (2500, 22004)
+    mbp = api.tdbp_gpu(raw, pos_sat, vel_sat, t0, ns, vt, t_vec, 500.0, params=vp, return_device=True)
+    std = api.tdbp_gpu(raw, pos_sat, vel_sat, t0, ns, np.zeros(3), t_vec, 500.0, params=vp, return_device=True)
+    both = api.tdbp_gpu(2.0 * raw, pos_sat, vel_sat, t0, ns, vt, t_vec, 500.0, params=vp, return_device=True)
+    assert float(torch.linalg.vector_norm(both - 2.0 * mbp) / torch.linalg.vector_norm(both)) < 1e-6
+    m, s = mbp.abs(), std.abs()
+    pk = np.unravel_index(int(torch.argmax(m)), m.shape)
+    assert abs(pk[0] - 256) < 120 and abs(pk[1] - 256) < 120            # the 155 m hull spans ~160 of the 512 pixels
+    assert float(m.max()) > 1.5 * float(s.max())                          # motion-compensated focusing is sharper
