@@ -170,14 +170,18 @@ def echo_scatterer_shards_p2p(compute_into: Callable[[int, int, int, int, torch.
     return block_range(P, rank, n)
 
 
-def pair_products_p2p(shared: SharedBuffer, products: Callable[[torch.Tensor, torch.Tensor], dict]):
+def pair_products_p2p(shared: SharedBuffer, products: Callable[[torch.Tensor, torch.Tensor], dict],
+                      first: torch.Tensor | None = None):
     """HRWS-style chain without the staging copy: every rank has focused its channel into ``shared.local``; the fused
     DPCA/ATI kernel of rank k then reads channel k+1 directly from rank k+1's HBM over NVLink (8 of its 16 input bytes per
     pixel), so the exchange overlaps the products instead of preceding them.  Returns the products of the pair (k, k+1),
-    None on the last rank."""
+    None on the last rank.  ``first`` replaces ``shared.local`` as the pair's first image when the two members of a pair
+    are focused from different pulse windows of a channel (the one-pulse DPCA shift, sar_ati_dcpa_sim_csa.py:402-403:
+    rank k keeps focus(raw_k[1:]) private and publishes focus(raw_k[:-1]) for rank k-1)."""
     rank, n = world(shared.group)
     peer_barrier(shared.device, shared.group)      # every channel is focused before anyone reads it
-    out = products(shared.local, shared.views[rank + 1]) if rank < n - 1 else None
+    a = shared.local if first is None else first
+    out = products(a, shared.views[rank + 1]) if rank < n - 1 else None
     peer_barrier(shared.device, shared.group)      # nobody overwrites its channel while a neighbour still reads it
     return out
 

@@ -107,6 +107,16 @@ def ati_scene(seed: int = 0, num_pulses: int = 7200, num_clutter: int = 5000,
     }
 
 
+def hrws_scene(n_channels: int = 8, **kw):
+    """Config 5 (HRWS-N fast-mover scene): the two-channel scene above with ``n_channels`` receive phase centres at
+    (k - (N-1)/2) d_rx along the velocity vector, so that every adjacent pair (k, k+1) has the DPCA geometry of
+    sar_ati_dcpa_sim_csa.py:42, :184-196 and is co-registered by the same one-pulse shift (:402-403)."""
+    sc = ati_scene(**kw)
+    d = sc["prm"].d_rx
+    sc["rx_offsets"] = tuple((k - (n_channels - 1) / 2) * d for k in range(n_channels))
+    return sc
+
+
 def stripmap_scene(num_pulses: int, num_samples: int, n_side: int = 9, half_extent: float = 1000.0):
     """Config 2: sar_satellite_sim.py geometry (orbit along +x) with a point-target grid, the
     receive window sized so that S = ``num_samples`` at fs = 600 MHz."""

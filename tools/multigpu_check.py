@@ -11,6 +11,8 @@ Checks, with N ranks against a one-GPU computation on rank 0:
   4. one receive channel per rank, ring exchange, DPCA/ATI per pair   -> indices equal to a local recompute
   5. VideoSAR frames (spotlight echo -> TDBP), round robin            -> frames identical to a local recompute
   1b / 4b: the two exchange steps with the transfer fused into the kernels (peer-mapped HBM over NVLink)
+  6. HRWS-N fast-mover scene (config 5): echo -> CSA per channel per rank, pairs over NVLink -> equal to a local
+     recompute; ATI phase of the mover and clutter cancellation per pair
 Prints one JSON line on rank 0."""
 import json
 import os
@@ -170,6 +172,54 @@ def main():
     counts = torch.tensor([len(mine_v)], device=device)
     dist.all_reduce(counts)
     out["video_frames_total"] = int(counts.item())
+    # ---- 6: HRWS-N fast-mover scene (config 5): channel k on rank k (echo -> one-pulse DPCA shift -> CSA), pair (k, k+1)
+    #         formed by the DPCA/ATI kernel reading rank k+1's image over NVLink
+    from nis_sar import api
+    hp = params.spaceborne_preset(fs=100e6, bw=80e6).replace(n_samples=2048, window_s=2048 / 100e6)
+    hs = scenes.hrws_scene(world, seed=17, num_pulses=1025, num_clutter=400, prm=hp, t_int=None)
+    ship, clut = (hs["ship_pos"], hs["ship_rcs"]), (hs["clutter_pos"], hs["clutter_rcs"])
+
+    def channel(k):
+        a, _ = api.run_bistatic_physics_gpu(tg.arrays_to_targets(*ship), hs["t_vec"], hs["pos_tx"], hs["vel_tx"],
+                                            hs["rx_offsets"][k], hs["ship_vel"], params=hp, device=device, return_device=True)
+        b, _ = api.run_bistatic_physics_gpu(tg.arrays_to_targets(*clut), hs["t_vec"], hs["pos_tx"], hs["vel_tx"],
+                                            hs["rx_offsets"][k], hs["clutter_vel"], params=hp, device=device, return_device=True)
+        return a + b
+
+    def focus(raw):
+        return api.sar_focus_csa(raw, hp.Lambda, hp.T_p, hp.k_rate, hp.FS, hp.PRF, hp.V_eff, hp.R0, hp.t_start_fast,
+                                 device=device, return_device=True)[0].clone()
+    try:
+        raw_k = channel(rank)
+        lead = focus(raw_k[1:].contiguous())                   # slc1 of pair (k, k+1)
+        shh = nd.SharedBuffer(tuple(lead.shape), torch.complex64, device=device)
+        shh.local.copy_(focus(raw_k[:-1].contiguous()))        # slc2 of pair (k-1, k), read by rank k-1
+        prod_h = lambda a, b: dev.gmti_fused(a, b, want=("ati_phase", "ati_phase_masked", "dpca_mag"))
+        res = nd.pair_products_p2p(shh, prod_h, first=lead)
+        ok, stats = 1, torch.zeros(5, device=device, dtype=torch.float64)
+        if res is not None:
+            ref = prod_h(lead, focus(channel(rank + 1)[:-1].contiguous()))
+            ok = int(torch.equal(res["det_idx"], ref["det_idx"]) and res["peak_idx"] == ref["peak_idx"]
+                     and torch.equal(res["dpca_mag"], ref["dpca_mag"]))
+            mag = lead.abs()
+            dp = res["dpca_mag"]
+            mover = int(torch.argmax(dp))                       # the ship survives the subtraction
+            clutter_px = int(torch.argmax(torch.where(dp < 0.05 * dp.max(), mag, torch.zeros_like(mag))))
+            stats = torch.tensor([float(res["ati_phase"].flatten()[mover]),
+                                  20 * np.log10(float(dp.flatten()[clutter_px]) / float(mag.flatten()[clutter_px])),
+                                  float(len(res["det_idx"])), float(dp.flatten()[mover] / mag.flatten()[mover]),
+                                  float(mag.flatten()[mover] / mag.max())], device=device, dtype=torch.float64)
+        flag = torch.tensor([ok], device=device)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        out["hrws_pairs_equal_local_recompute"] = bool(flag.item())
+        allst = [torch.zeros_like(stats) for _ in range(world)]
+        dist.all_gather(allst, stats)
+        out["hrws_mover_ati_phase_rad_per_pair"] = [round(float(s[0]), 4) for s in allst[:-1]]
+        out["hrws_clutter_cancellation_db_per_pair"] = [round(float(s[1]), 1) for s in allst[:-1]]
+        out["hrws_detections_per_pair"] = [int(s[2]) for s in allst[:-1]]
+        out["hrws_mover_dpca_over_slc_and_rel_mag"] = [[round(float(s[3]), 3), round(float(s[4]), 4)] for s in allst[:-1]]
+    except Exception as e:
+        out["hrws_error"] = str(e)[:300]
     if rank == 0:
         print(json.dumps(out))
     dist.destroy_process_group()
