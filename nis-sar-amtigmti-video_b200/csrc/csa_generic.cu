@@ -21,6 +21,7 @@
 
 #include "csa_internal.cuh"
 #include "fft.cuh"
+#include "mixed_ct.cuh"
 
 using namespace nis;
 using namespace nis::fft;
@@ -53,6 +54,7 @@ struct GenLen {
     int radix[kMaxPass] = {};
     float2 *twN = nullptr, *chirp = nullptr, *bfft = nullptr, *tw_pow2 = nullptr;
     float2 *bfe = nullptr, *bfo = nullptr, *twm = nullptr, *tw_half = nullptr;
+    float2* ct_tw = nullptr;   // per-pass tables of the compile-time plan (mixed_ct.cuh), when the length has one
     GenDev dev() const {
         GenDev d{};
         d.N = N; d.npass = npass; d.M = M;
@@ -68,7 +70,7 @@ struct GenLen {
     }
     void release() {
         cudaFree(twN); cudaFree(chirp); cudaFree(bfft); cudaFree(tw_pow2);
-        cudaFree(bfe); cudaFree(bfo); cudaFree(twm); cudaFree(tw_half);
+        cudaFree(bfe); cudaFree(bfo); cudaFree(twm); cudaFree(tw_half); cudaFree(ct_tw);
     }
 };
 
@@ -439,6 +441,30 @@ int upload_pow2_twiddles(float2** dev) {
     return upload(h, dev);
 }
 
+template <class MP>
+int upload_ct_tables(float2** dev) {
+    std::vector<float2> h(MP::TW_LEN);
+    mixedct::build_tables<MP>(h.data());
+    return upload(h, dev);
+}
+
+template <int MODE, class MP>
+int launch_mixed_ct(nis_ctx* ctx, const GenLen& g, float2* data, int64_t pitch, int n_rows, const RowCoef* coef,
+                    float scale, double* max_sq, cudaStream_t st) {
+    static bool attr_done_dev[64] = {};
+    bool& attr_done = attr_done_dev[nis::current_device() & 63];
+    if (!attr_done) {
+        NIS_CUDA_TRY(cudaFuncSetAttribute(mixedct::k_row_mixed_ct<MODE, MP>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          (int)MP::smem_bytes));
+        attr_done = true;
+    }
+    int grid = ctx->num_sms;
+    if (grid > n_rows) grid = n_rows;
+    mixedct::k_row_mixed_ct<MODE, MP><<<grid, MP::NT, MP::smem_bytes, st>>>(data, pitch, n_rows, coef, g.ct_tw, scale, max_sq);
+    NIS_LAUNCH_CHECK(ctx);
+    return NIS_OK;
+}
+
 int build_length(int n, GenLen* g) {
     g->N = n;
     const double pi = 3.14159265358979323846264338327950288;
@@ -450,6 +476,10 @@ int build_length(int n, GenLen* g) {
             const double a = -2.0 * pi * (double)m / (double)n;
             tw[m] = make_float2((float)cos(a), (float)sin(a));
         }
+        int rc = NIS_OK;
+        if (n == mixedct::MP13200::N) rc = upload_ct_tables<mixedct::MP13200>(&g->ct_tw);
+        if (n == mixedct::MP7200::N) rc = upload_ct_tables<mixedct::MP7200>(&g->ct_tw);
+        if (rc != NIS_OK) return rc;
         return upload(tw, &g->twN);
     }
     g->kind = 1;
@@ -542,6 +572,12 @@ int launch_row(nis_ctx* ctx, const GenLen& g, float2* data, int64_t pitch, int n
             case 4096: return launch_blue<MODE, P4096, 4>(ctx, g, data, pitch, n_rows, coef, scale, max_sq, st);
             default: return launch_blue<MODE, P16384, 5>(ctx, g, data, pitch, n_rows, coef, scale, max_sq, st);
         }
+    }
+    if (g.ct_tw != nullptr && !getenv("NIS_MIXED_RUNTIME")) {
+        if (g.N == mixedct::MP13200::N)
+            return launch_mixed_ct<MODE, mixedct::MP13200>(ctx, g, data, pitch, n_rows, coef, scale, max_sq, st);
+        if (g.N == mixedct::MP7200::N)
+            return launch_mixed_ct<MODE, mixedct::MP7200>(ctx, g, data, pitch, n_rows, coef, scale, max_sq, st);
     }
     const size_t smem = 2 * (size_t)g.N * sizeof(float2);
     static bool attr_done_dev[64] = {};

@@ -374,10 +374,12 @@ def test_csa_general_sizes_golden(api, tag):
     assert np.allclose(cax, g[f"{tag}_cax"], rtol=1e-13, atol=1e-9)
 
 
-@pytest.mark.parametrize("n_az,n_rg", [(63, 1320), (255, 660), (360, 1000), (719, 1320), (97, 4097), (1000, 24)])
+@pytest.mark.parametrize("n_az,n_rg", [(63, 1320), (255, 660), (360, 1000), (719, 1320), (97, 4097), (1000, 24),
+                                       (150, 13200), (7200, 40), (301, 7200)])
 def test_csa_general_sizes_vs_oracle(api, n_az, n_rg):
     """Shapes of the reduced default scene (P-1 pulses x 22 us * fs samples) and mixed engine pairs:
-    63 = 7.3.3, 1320 = 8.3.5.11, 255 = 3.5.17 (Bluestein), 719 prime, 4097 = 17.241 (Bluestein 16384)."""
+    63 = 7.3.3, 1320 = 8.3.5.11, 255 = 3.5.17 (Bluestein), 719 prime, 4097 = 17.241 (Bluestein 16384); 13200 and 7200 run
+    on the compile-time plans of mixed_ct.cuh (range chain and both azimuth directions; 150 rows > one row per CTA)."""
     prm = params.spaceborne_preset()
     rng = np.random.default_rng(n_az + 7 * n_rg)
     x = (rng.standard_normal((n_az, n_rg)) + 1j * rng.standard_normal((n_az, n_rg))).astype(np.complex64)
