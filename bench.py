@@ -397,8 +397,39 @@ def run_gpu_arm(args):
         other["default_ati_scene"] = {"workload": "configs[0] shape: 2 channels x CSA 7199 x 13200 (general-size path: mixed radix "
                                                   "13200, Bluestein 7199) + fused DPCA/ATI detection",
                                       "ms_per_frame": dms, "mpixels_per_s": 2 * na * nr / (dms * 1e-3) / 1e6}
+        # the whole of `python sar_ati_dcpa_sim_csa.py` at its own sizes (:184-197, :402-419): destroyer moving at 15 m/s
+        # + 5000 clutter scatterers, 7200 pulses x 13200 samples, two phase centres -> shift -> CSA x2 -> DPCA/ATI
+        del chd
+        from nis_sar import scenes as nsc0
+        ds = nsc0.ati_scene(seed=0)
+        dkw = dict(c=prm.C, fc=prm.FC, k_rate=prm.k_rate, t_p=prm.T_p, t_start=prm.t_start_fast, fs=prm.FS,
+                   n_samples=nr, device=device)
+        vd = ds["vel_tx"] / np.sqrt(np.sum(ds["vel_tx"] ** 2, axis=1))[:, None]
+        rawd = torch.empty((na + 1, nr), dtype=torch.complex64, device=device)
+
+        def default_scene_full():
+            for off, slc, mx in ((ds["rx_offsets"][0], sd1, mxd), (ds["rx_offsets"][1], sd2, None)):
+                prx = ds["pos_tx"] + vd * off
+                dev.echo_accumulate(ds["ship_pos"], ds["ship_vel"], ds["ship_rcs"], ds["pos_tx"], prx, ds["t_vec"], out=rawd, **dkw)
+                dev.echo_accumulate(ds["clutter_pos"], ds["clutter_vel"], ds["clutter_rcs"], ds["pos_tx"], prx, ds["t_vec"],
+                                    out=rawd, accumulate=True, **dkw)
+                pd.focus(rawd[1:] if mx is not None else rawd[:-1], out=slc, max_sq=mx)
+            return dev.gmti_fused(sd1, sd2, max_sq=mxd, want=("ati_phase_masked", "dpca_mag"))
+        res_d = default_scene_full()
+        torch.cuda.synchronize(device)
+        tw0 = time.perf_counter()
+        res_d = default_scene_full()      # reads det_count / peak_idx back: host-synchronous
+        torch.cuda.synchronize(device)
+        tw1 = time.perf_counter()
+        n_up = 2.0 * (len(ds["ship_rcs"]) + len(ds["clutter_rcs"])) * (na + 1) * nr
+        other["default_scene_full_run"] = {
+            "workload": "sar_ati_dcpa_sim_csa.py at its own sizes: 35 moving + 5000 clutter scatterers x 7200 pulses x 13200 samples x "
+                        "2 phase centres (echo) -> pulse shift -> CSA 7199 x 13200 x 2 -> DPCA/ATI + detections; host scene arrays "
+                        "in, detection list out",
+            "s_wall": tw1 - tw0, "scatterer_sample_updates": n_up, "g_updates_per_s": n_up / (tw1 - tw0) / 1e9,
+            "detections": int(res_d["det_count"])}
         pd.close()
-        del chd, sd1, sd2
+        del rawd, sd1, sd2
         torch.cuda.empty_cache()
         # configs[2]: dense vehicle scene, 1e5 scatterers, airborne geometry (S = 2048); a 256-pulse block of the 32768
         from nis_sar import scenes as nsc

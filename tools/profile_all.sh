@@ -14,5 +14,6 @@ ncu $FULL -k regex:k_az_inner -c 1 -o gpurun_out/prof_azinner_$TAG python tools/
 ncu $FULL -k regex:k_echo -c 1 -o gpurun_out/prof_echo_$TAG python tools/kbench.py echo:stripmap8192 > /dev/null 2>&1
 ncu $FULL -k regex:"k_rda_range|k_rda_rcmc" -c 2 -o gpurun_out/prof_rda_$TAG python tools/kbench.py rda:4096x4096 > /dev/null 2>&1
 ncu $FULL -k regex:"k_tdbp" -c 3 -o gpurun_out/prof_tdbp_$TAG python tools/kbench.py tdbp:2500x512 > /dev/null 2>&1
+ncu $FULL -k regex:"k_row_mixed_ct|k_row_blue_pruned" -c 3 -o gpurun_out/prof_general_$TAG python tools/one_csa.py 7199x13200 1 > /dev/null 2>&1
 ncu $FULL -k regex:"k_gmti_products" -c 1 -o gpurun_out/prof_gmti_$TAG python tools/kbench.py gmti:4096 > /dev/null 2>&1
 ls -la gpurun_out/*_$TAG.* | awk '{print $5, $9}'
