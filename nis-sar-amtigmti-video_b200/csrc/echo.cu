@@ -18,6 +18,7 @@
 //    fast sincos (u = amp cis(phi_t), v = cis(delta_t)) and then runs the phasor recurrence
 //    p <- p v outward from the centre sample: 1 complex multiply + 1 complex add per sample.
 #include <math.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -58,7 +59,8 @@ __global__ void __launch_bounds__(256, SPOT ? 1 : 4) k_echo(EchoConst k, EchoTai
                                               const double* __restrict__ pos_tx, const double* __restrict__ pos_rx,
                                               const double* __restrict__ t_slow, const double* __restrict__ t_fast,
                                               float2* __restrict__ raw) {
-    constexpr int CH = 256 * SPT;
+    const int NTH = blockDim.x;        // 32 .. 256 threads: the launcher balances the chunks over the sample window
+    const int CH = NTH * SPT;
     constexpr int HALF = SPT / 2;
     __shared__ uint4 rec[256];
     __shared__ float2 recv[256];   // cis(per-sample phase step) of each kept scatterer at the chunk centre
@@ -88,7 +90,9 @@ __global__ void __launch_bounds__(256, SPOT ? 1 : 4) k_echo(EchoConst k, EchoTai
 #pragma unroll
     for (int j = 0; j < SPT; ++j) acc[j] = make_float2(0.f, 0.f);
 
-    for (int b0 = 0; b0 < k.T; b0 += 256) {
+    if (tid < 8) warp_cnt[tid] = 0;    // warps a narrower CTA does not have
+    __syncthreads();
+    for (int b0 = 0; b0 < k.T; b0 += NTH) {
         // ------------------------------------------------ prologue: one scatterer per thread, fp64
         const int b = b0 + tid;
         bool keep = false;
@@ -238,6 +242,17 @@ __global__ void __launch_bounds__(256, SPOT ? 1 : 4) k_echo(EchoConst k, EchoTai
     }
 }
 
+// Chunks of equal width over the window: as few CTAs per pulse as 256 threads x SPT samples allow, each with just the
+// warps it needs (13200 samples at 16 per thread: 4 CTAs of 224 threads instead of 4 x 256 with a quarter of them idle).
+struct EchoShape { int chunks, threads; };
+inline EchoShape echo_shape(int S, int spt) {
+    EchoShape e;
+    e.chunks = (S + 256 * spt - 1) / (256 * spt);
+    const int per = (S + e.chunks - 1) / e.chunks;
+    e.threads = ((per + spt - 1) / spt + 31) / 32 * 32;
+    return e;
+}
+
 template <int SPT>
 int launch_echo(nis_ctx* ctx, const EchoConst& k, const double* pos0, const double* vel, const double* amp,
                 const double* pos_tx, const double* pos_rx, const double* t_slow, const double* t_fast, float2* raw,
@@ -250,10 +265,10 @@ int launch_echo(nis_ctx* ctx, const EchoConst& k, const double* pos0, const doub
         ph -= floor(ph);
         tail.e[j] = make_float2((float)cos(two_pi * ph), (float)sin(two_pi * ph));
     }
-    constexpr int CH = 256 * SPT;
-    dim3 grid((k.S + CH - 1) / CH, n_pulses);
-    if (k.spotlight) k_echo<SPT, true><<<grid, 256, 0, st>>>(k, tail, pos0, vel, amp, pos_tx, pos_rx, t_slow, t_fast, raw);
-    else k_echo<SPT, false><<<grid, 256, 0, st>>>(k, tail, pos0, vel, amp, pos_tx, pos_rx, t_slow, t_fast, raw);
+    const EchoShape sh = echo_shape(k.S, SPT);
+    dim3 grid(sh.chunks, n_pulses);
+    if (k.spotlight) k_echo<SPT, true><<<grid, sh.threads, 0, st>>>(k, tail, pos0, vel, amp, pos_tx, pos_rx, t_slow, t_fast, raw);
+    else k_echo<SPT, false><<<grid, sh.threads, 0, st>>>(k, tail, pos0, vel, amp, pos_tx, pos_rx, t_slow, t_fast, raw);
     NIS_LAUNCH_CHECK(ctx);
     return NIS_OK;
 }
@@ -281,8 +296,11 @@ static int echo_common(nis_ctx* ctx, const nis_echo_params* prm, const double* t
     float2* r = reinterpret_cast<float2*>(raw);
     // chunk = 256*SPT samples: take the wider chunk unless it wastes > 12 % of its threads past S, or the
     // caller knows that the chirps cover only part of the window (samples_per_thread hint)
-    const int waste16 = ((S + 4095) / 4096) * 4096 - S;
-    const bool wide = prm->samples_per_thread == 16 || (prm->samples_per_thread != 8 && waste16 * 8 <= S);
+    const EchoShape s16 = echo_shape(S, 16);
+    const int waste16 = s16.chunks * s16.threads * 16 - S;
+    int want = prm->samples_per_thread;
+    if (const char* e = getenv("NIS_ECHO_SPT")) want = atoi(e);
+    const bool wide = want == 16 || (want != 8 && waste16 * 8 <= S);
     if (wide)
         return launch_echo<16>(ctx, k, tgt_pos0, tgt_vel, tgt_amp, pos_tx, pos_rx, t_slow, t_fast, r, P1 - P0, st);
     return launch_echo<8>(ctx, k, tgt_pos0, tgt_vel, tgt_amp, pos_tx, pos_rx, t_slow, t_fast, r, P1 - P0, st);

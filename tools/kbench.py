@@ -128,8 +128,8 @@ def echo(kind):
         prm = sc["prm"]
         kw = dict(c=prm.C, fc=prm.FC, k_rate=prm.k_rate, t_p=prm.T_p, t_start=prm.t_start_fast, fs=600e6, n_samples=8192)
         args = (sc["pos"], np.zeros(3), sc["rcs"], sc["pos_sat"], None, sc["t_vec"])
-    elif kind == "ati_default_256p":
-        sc = scenes.ati_scene(seed=0, num_pulses=256, num_clutter=5000)
+    elif kind.startswith("ati_default_"):
+        sc = scenes.ati_scene(seed=0, num_pulses=int(kind[len("ati_default_"):-1]), num_clutter=5000, t_int=None)
         prm = sc["prm"]
         kw = dict(c=prm.C, fc=prm.FC, k_rate=prm.k_rate, t_p=prm.T_p, t_start=prm.t_start_fast, fs=prm.FS, n_samples=13200)
         vhat = sc["vel_tx"] / np.linalg.norm(sc["vel_tx"], axis=1)[:, None]
