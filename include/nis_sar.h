@@ -80,8 +80,9 @@ typedef struct {
     double t_start;  /* t_fast[0] (s) */
     double dt_fast;  /* nominal fast-time step: t_fast[n] ~= t_start + n * dt_fast */
     int32_t per_target_velocity; /* 0: tgt_vel is one xyz triple; 1: tgt_vel is [T*3] */
-    int32_t samples_per_thread;  /* 0: library chooses; 8 or 16: chunk = 256 * this many samples per CTA.
-                                  * 8 suits scenes whose chirps cover well under the whole window */
+    int32_t samples_per_thread;  /* 0: library chooses; 8 or 16: samples per thread.  A CTA (<= 256 threads) covers one of
+                                  * ceil(S / (256 * this)) equal chunks of the window; 8 suits scenes whose chirps
+                                  * cover well under the whole window */
 } nis_echo_params;
 
 /* Spotlight engine, run_physics_spotlight (sar_batch_sim.py:83-169): start-stop corrected delay -- the receive position is

@@ -124,44 +124,47 @@ __global__ void __launch_bounds__(P::NT) k_rda_range_blocked(const float2* __res
 // even / odd products: four H-point transforms on the 16-elements-per-thread plan instead of two M-point ones on the
 // 32-elements-per-thread plan (8192^2 frame, 6001 taps: 1.30 -> 1.09 ms).  HfE / HfO: even / odd bins of the filter
 // spectrum / M; twM[n] = w_M^n.  A is parked in shared memory (each thread re-reads only its own elements).
-template <class P, int PAD>
+// GPARK (M = 32768, H = 16384: the satellite scripts' 13200-sample pulses and 12001-tap filter need 19200 points, which
+// overlap-save on 16384-point blocks pays with four blocks = eight 16384-point transforms per row; this form takes four):
+// the row buffer leaves no shared memory for A, which is parked in a per-CTA global scratch line instead -- 128 KB per CTA,
+// written and re-read by the same thread, resident in L2.
+template <class P, int PAD, bool GPARK>
 __global__ void __launch_bounds__(P::NT) k_rda_range_pruned(const float2* __restrict__ in, int64_t in_pitch,
                                                             float2* __restrict__ work, int64_t work_pitch,
                                                             float2* __restrict__ rc_out, int n_rows, int N, int s0,
                                                             const float2* __restrict__ HfE, const float2* __restrict__ HfO,
                                                             const float2* __restrict__ twM, const float* __restrict__ win,
-                                                            const float2* __restrict__ tw) {
+                                                            const float2* __restrict__ tw, float2* __restrict__ gpark) {
     extern __shared__ float2 sm[];
     constexpr int E = P::E, NT = P::NT, H = P::N;
     constexpr int SMROW = H + (PAD ? (H >> PAD) : 0);
-    float2* const park = sm + SMROW;
+    float2* const park = GPARK ? gpark + (size_t)blockIdx.x * H : sm + SMROW;
     const int t = threadIdx.x;
     for (int row = blockIdx.x; row < n_rows; row += gridDim.x) {
         const float2* p = in + (int64_t)row * in_pitch;
         float2 v[E];
+        // even bins, then odd bins: one copy of the two transforms in the instruction stream (the 32-element plan is large)
+#pragma unroll 1
+        for (int br = 0; br < 2; ++br) {
+            const float2* __restrict__ hf = br ? HfO : HfE;
 #pragma unroll
-        for (int s = 0; s < E; ++s) {
-            const int idx = t + NT * s;
-            v[s] = idx < N ? p[idx] : make_float2(0.f, 0.f);
+            for (int s = 0; s < E; ++s) {
+                const int idx = t + NT * s;
+                float2 x = idx < N ? p[idx] : make_float2(0.f, 0.f);
+                if (br) x = cmul_pk(x, __ldg(twM + idx));
+                v[s] = x;
+            }
+            transform<P, false, 1, PAD>(v, t, sm, tw);
+#pragma unroll
+            for (int s = 0; s < E; ++s) v[s] = cmul_pk(v[s], __ldg(hf + t + NT * s));
+            __syncthreads();
+            transform<P, true, 1, PAD>(v, t, sm, tw);
+            if (br == 0) {
+#pragma unroll
+                for (int s = 0; s < E; ++s) park[t + NT * s] = v[s];
+                __syncthreads();
+            }
         }
-        transform<P, false, 1, PAD>(v, t, sm, tw);
-#pragma unroll
-        for (int s = 0; s < E; ++s) v[s] = cmul_pk(v[s], __ldg(HfE + t + NT * s));
-        __syncthreads();
-        transform<P, true, 1, PAD>(v, t, sm, tw);
-#pragma unroll
-        for (int s = 0; s < E; ++s) park[t + NT * s] = v[s];
-#pragma unroll
-        for (int s = 0; s < E; ++s) {
-            const int idx = t + NT * s;
-            v[s] = idx < N ? cmul_pk(p[idx], __ldg(twM + idx)) : make_float2(0.f, 0.f);
-        }
-        __syncthreads();
-        transform<P, false, 1, PAD>(v, t, sm, tw);
-#pragma unroll
-        for (int s = 0; s < E; ++s) v[s] = cmul_pk(v[s], __ldg(HfO + t + NT * s));
-        __syncthreads();
-        transform<P, true, 1, PAD>(v, t, sm, tw);
         const float w = win[row];
 #pragma unroll
         for (int s = 0; s < E; ++s) {
@@ -301,6 +304,16 @@ int mf_taps(const nis_rda_params& prm) {
     return (int)floor(prm.t_p / step) + 1;
 }
 
+// One zero-padded 32768-point block, evaluated as four 16384-point transforms: possible when the pulse fits the lower half
+// and the 'same' window stays free of wrap-around; worth it when overlap-save on 16384-point blocks would need > 2 blocks.
+bool wide_pruned_ok(int n, int taps) {
+    if (getenv("NIS_RDA_NOWIDE")) return false;
+    if (taps < 1 || n > 16384 || taps > 32768 || n + taps - 1 - (taps - 1) / 2 > 32768) return false;
+    if (taps > 14337) return true;
+    const int B = 16384 - taps + 1;
+    return (n + B - 1) / B > 2;
+}
+
 int conv_fft_len(int n, int taps) {   // smallest supported M that keeps the 'same' window free of wrap-around
     const int need = n + taps - 1 - (taps - 1) / 2;
     const int ms[] = {256, 1024, 2048, 4096, 8192, 16384};
@@ -319,6 +332,8 @@ struct nis_rda_plan {
     RowDft* dft = nullptr;            // row-DFT engine (other P): needs the transposed buffer
     float2 *work = nullptr, *tbuf = nullptr, *Hf = nullptr, *tw = nullptr;
     float2 *HfE = nullptr, *HfO = nullptr, *twM = nullptr;   // pruned range compression (N <= M/2)
+    float2* gpark = nullptr;                                  // M = 32768: one 16384-point scratch line per CTA
+    int gpark_lines = 0;
     float* win = nullptr;
     RdaRow* rows = nullptr;
     double q0 = 0;
@@ -370,22 +385,23 @@ int launch_rda_range_blocked(nis_rda_plan* pl, const float2* in, int64_t pitch, 
     return NIS_OK;
 }
 
-template <class P, int PAD>
+template <class P, int PAD, bool GPARK>
 int launch_rda_range_pruned(nis_rda_plan* pl, const float2* in, int64_t pitch, float2* rc_out, cudaStream_t st) {
     constexpr int SMROW = P::N + (PAD ? (P::N >> PAD) : 0);
-    const size_t smem = (size_t)(SMROW + P::N) * sizeof(float2);
+    const size_t smem = (size_t)(SMROW + (GPARK ? 0 : P::N)) * sizeof(float2);
     static bool attr_done_dev[64] = {};
     bool& attr_done = attr_done_dev[nis::current_device() & 63];
     if (!attr_done) {
-        NIS_CUDA_TRY(cudaFuncSetAttribute(k_rda_range_pruned<P, PAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        NIS_CUDA_TRY(cudaFuncSetAttribute(k_rda_range_pruned<P, PAD, GPARK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr_done = true;
     }
     int per_sm = 1;
-    NIS_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_rda_range_pruned<P, PAD>, P::NT, smem));
+    NIS_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_rda_range_pruned<P, PAD, GPARK>, P::NT, smem));
     int grid = pl->ctx->num_sms * (per_sm < 1 ? 1 : per_sm);
     if (grid > pl->P) grid = pl->P;
-    k_rda_range_pruned<P, PAD><<<grid, P::NT, smem, st>>>(in, pitch, pl->work, pl->S, rc_out, pl->P, pl->S, pl->s0, pl->HfE,
-                                                           pl->HfO, pl->twM, pl->win, pl->tw);
+    if (GPARK && grid > pl->gpark_lines) grid = pl->gpark_lines;
+    k_rda_range_pruned<P, PAD, GPARK><<<grid, P::NT, smem, st>>>(in, pitch, pl->work, pl->S, rc_out, pl->P, pl->S, pl->s0,
+                                                                  pl->HfE, pl->HfO, pl->twM, pl->win, pl->tw, pl->gpark);
     NIS_LAUNCH_CHECK(pl->ctx);
     return NIS_OK;
 }
@@ -403,6 +419,7 @@ bool rda_sizes_ok(int P, int S, const nis_rda_params& prm, int* M_out) {
     if (P < 2 || S < 2 || S > 24576) return false;
     const int taps = mf_taps(prm);
     int M = conv_fft_len(S, taps);
+    if (M == 0 && wide_pruned_ok(S, taps)) M = 32768;       // one 32768-point block in the pruned form (S <= 16384)
     if (M == 0 && taps >= 1 && taps <= 14337) M = 16384;   // overlap-save blocks of >= 2048 outputs
     if (taps < 1 || M == 0) return false;
     if (M_out) *M_out = M;
@@ -427,6 +444,7 @@ extern "C" int nis_rda_plan_destroy(nis_rda_plan* pl) {
     cudaFree(pl->tbuf);
     cudaFree(pl->Hf);
     cudaFree(pl->HfE);
+    cudaFree(pl->gpark);
     cudaFree(pl->HfO);
     cudaFree(pl->twM);
     cudaFree(pl->tw);
@@ -508,8 +526,9 @@ extern "C" int nis_rda_plan_create(nis_ctx* ctx, int32_t P, int32_t S, const nis
     }
     // measured: the pruned form wins only where the unpruned one needs the 32-elements-per-thread plan (M = 16384: 1.30 ->
     // 1.09 ms at 8192 rows); at M = 8192 its 256-thread CTAs run four dependent transforms per row and lose (0.22 -> 0.45 ms)
-    const bool blocked = conv_fft_len(S, pl->taps) == 0;   // the filter does not fit one block with the pulse
-    const bool prune = !blocked && (2 * S <= M) && M == 16384 && !getenv("NIS_RDA_NOPRUNE");
+    const bool wide = M == 32768;
+    const bool blocked = !wide && conv_fft_len(S, pl->taps) == 0;   // the filter does not fit one block with the pulse
+    const bool prune = wide || (!blocked && (2 * S <= M) && M == 16384 && !getenv("NIS_RDA_NOPRUNE"));
     if (prune) {
         const int H = M / 2;
         std::vector<float2> hf(M), he(H), ho(H), twm(H);
@@ -531,8 +550,13 @@ extern "C" int nis_rda_plan_create(nis_ctx* ctx, int32_t P, int32_t S, const nis
     if (blocked) {
         pl->range_fn = launch_rda_range_blocked<P16384, 5>;
         FAIL_IF(upload_tw<P16384>(&pl->tw));
+    } else if (wide) {
+        pl->gpark_lines = ctx->num_sms;
+        CUDA_FAIL_IF(cudaMalloc(&pl->gpark, (size_t)pl->gpark_lines * 16384 * sizeof(float2)));
+        pl->range_fn = launch_rda_range_pruned<P16384, 5, true>;
+        FAIL_IF(upload_tw<P16384>(&pl->tw));
     } else if (prune) {
-        pl->range_fn = launch_rda_range_pruned<P8192, 4>;
+        pl->range_fn = launch_rda_range_pruned<P8192, 4, false>;
         FAIL_IF(upload_tw<P8192>(&pl->tw));
     } else
     switch (M) {
