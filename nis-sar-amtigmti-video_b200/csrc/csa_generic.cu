@@ -319,28 +319,27 @@ __device__ __forceinline__ void bluestein_core_pruned(float2* v, int t, float2* 
     constexpr int E = P::E, NT = P::NT;
 #pragma unroll
     for (int s = 0; s < E; ++s) park_u[t + NT * s] = v[s];
-    transform<P, false, 1, PAD>(v, t, sm, g.tw_half);
+    // even bins, then odd bins, as a rolled loop: one copy of the two transforms in the instruction stream
+#pragma unroll 1
+    for (int br = 0; br < 2; ++br) {
+        const float2* __restrict__ bf = br ? g.bfo : g.bfe;
+        transform<P, false, 1, PAD>(v, t, sm, g.tw_half);
 #pragma unroll
-    for (int s = 0; s < E; ++s) {
-        const float2 h = __ldg(g.bfe + t + NT * s);
-        v[s] = INV ? cmul_conj(v[s], h) : cmul(v[s], h);
-    }
-    __syncthreads();
-    transform<P, true, 1, PAD>(v, t, sm, g.tw_half);
+        for (int s = 0; s < E; ++s) {
+            const float2 h = __ldg(bf + t + NT * s);
+            v[s] = INV ? cmul_conj(v[s], h) : cmul(v[s], h);
+        }
+        __syncthreads();
+        transform<P, true, 1, PAD>(v, t, sm, g.tw_half);
+        if (br == 0) {
 #pragma unroll
-    for (int s = 0; s < E; ++s) {
-        park_a[t + NT * s] = v[s];
-        v[s] = cmul(park_u[t + NT * s], __ldg(g.twm + t + NT * s));
+            for (int s = 0; s < E; ++s) {
+                park_a[t + NT * s] = v[s];
+                v[s] = cmul(park_u[t + NT * s], __ldg(g.twm + t + NT * s));
+            }
+            __syncthreads();
+        }
     }
-    __syncthreads();
-    transform<P, false, 1, PAD>(v, t, sm, g.tw_half);
-#pragma unroll
-    for (int s = 0; s < E; ++s) {
-        const float2 h = __ldg(g.bfo + t + NT * s);
-        v[s] = INV ? cmul_conj(v[s], h) : cmul(v[s], h);
-    }
-    __syncthreads();
-    transform<P, true, 1, PAD>(v, t, sm, g.tw_half);
 #pragma unroll
     for (int s = 0; s < E; ++s) {
         const int idx = t + NT * s;
