@@ -51,7 +51,8 @@ __device__ __forceinline__ bool gate(const double* __restrict__ t_fast, int n, d
 }
 
 // SPOT: the spotlight model is a separate instantiation, so that the stripmap engines keep their register budget
-template <int SPT, bool SPOT>
+// W256: the CTA has all 256 threads (chunk width and tile size are compile-time constants)
+template <int SPT, bool SPOT, bool W256>
 // four resident CTAs per SM (<= 64 registers; 24 bytes of spills at 16 samples per thread): measured -- 3 CTAs at 75
 // registers are 7 % slower on sparse scenes and equal on dense ones, 2 CTAs at 94 registers 12-25 % slower
 __global__ void __launch_bounds__(256, SPOT ? 1 : 4) k_echo(EchoConst k, EchoTail<SPT> tail, const double* __restrict__ pos0,
@@ -59,7 +60,7 @@ __global__ void __launch_bounds__(256, SPOT ? 1 : 4) k_echo(EchoConst k, EchoTai
                                               const double* __restrict__ pos_tx, const double* __restrict__ pos_rx,
                                               const double* __restrict__ t_slow, const double* __restrict__ t_fast,
                                               float2* __restrict__ raw) {
-    const int NTH = blockDim.x;        // 32 .. 256 threads: the launcher balances the chunks over the sample window
+    const int NTH = W256 ? 256 : blockDim.x;   // 32 .. 256 threads: the launcher balances the chunks over the sample window
     const int CH = NTH * SPT;
     constexpr int HALF = SPT / 2;
     __shared__ uint4 rec[256];
@@ -90,8 +91,10 @@ __global__ void __launch_bounds__(256, SPOT ? 1 : 4) k_echo(EchoConst k, EchoTai
 #pragma unroll
     for (int j = 0; j < SPT; ++j) acc[j] = make_float2(0.f, 0.f);
 
-    if (tid < 8) warp_cnt[tid] = 0;    // warps a narrower CTA does not have
-    __syncthreads();
+    if (!W256) {
+        if (tid < 8) warp_cnt[tid] = 0;    // warps a narrower CTA does not have
+        __syncthreads();
+    }
     for (int b0 = 0; b0 < k.T; b0 += NTH) {
         // ------------------------------------------------ prologue: one scatterer per thread, fp64
         const int b = b0 + tid;
@@ -267,8 +270,9 @@ int launch_echo(nis_ctx* ctx, const EchoConst& k, const double* pos0, const doub
     }
     const EchoShape sh = echo_shape(k.S, SPT);
     dim3 grid(sh.chunks, n_pulses);
-    if (k.spotlight) k_echo<SPT, true><<<grid, sh.threads, 0, st>>>(k, tail, pos0, vel, amp, pos_tx, pos_rx, t_slow, t_fast, raw);
-    else k_echo<SPT, false><<<grid, sh.threads, 0, st>>>(k, tail, pos0, vel, amp, pos_tx, pos_rx, t_slow, t_fast, raw);
+    if (k.spotlight) k_echo<SPT, true, false><<<grid, sh.threads, 0, st>>>(k, tail, pos0, vel, amp, pos_tx, pos_rx, t_slow, t_fast, raw);
+    else if (sh.threads == 256) k_echo<SPT, false, true><<<grid, 256, 0, st>>>(k, tail, pos0, vel, amp, pos_tx, pos_rx, t_slow, t_fast, raw);
+    else k_echo<SPT, false, false><<<grid, sh.threads, 0, st>>>(k, tail, pos0, vel, amp, pos_tx, pos_rx, t_slow, t_fast, raw);
     NIS_LAUNCH_CHECK(ctx);
     return NIS_OK;
 }
@@ -300,7 +304,10 @@ static int echo_common(nis_ctx* ctx, const nis_echo_params* prm, const double* t
     const int waste16 = s16.chunks * s16.threads * 16 - S;
     int want = prm->samples_per_thread;
     if (const char* e = getenv("NIS_ECHO_SPT")) want = atoi(e);
-    const bool wide = want == 16 || (want != 8 && waste16 * 8 <= S);
+    // ... and unless the wider chunk leaves the GPU short of threads (few pulses x few chunks: 1e5 scatterers on a 256-pulse
+    // block of 2048-sample rows ran 18 -> 26 ms with 128-thread CTAs)
+    const bool fills = (int64_t)(P1 - P0) * s16.chunks * s16.threads >= (int64_t)ctx->num_sms * 1024;
+    const bool wide = want == 16 || (want != 8 && waste16 * 8 <= S && fills);
     if (wide)
         return launch_echo<16>(ctx, k, tgt_pos0, tgt_vel, tgt_amp, pos_tx, pos_rx, t_slow, t_fast, r, P1 - P0, st);
     return launch_echo<8>(ctx, k, tgt_pos0, tgt_vel, tgt_amp, pos_tx, pos_rx, t_slow, t_fast, r, P1 - P0, st);

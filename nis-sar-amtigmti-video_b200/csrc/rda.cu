@@ -461,7 +461,7 @@ extern "C" int nis_rda_plan_create(nis_ctx* ctx, int32_t P, int32_t S, const nis
     int M = 0;
     if (!rda_sizes_ok(P, S, *prm, &M)) {
         set_error("nis_rda_plan_create: %d pulses x %d samples with a %d-tap matched filter is not supported (taps <= "
-                  "14337, samples <= 24576; pulses: power of two 64..32768 with samples %% 32 == 0, or any length the row-DFT "
+                  "14337, or <= 32768 with samples <= 16384 and samples + taps / 2 <= 32768; samples <= 24576; pulses: power of two 64..32768 with samples %% 32 == 0, or any length the row-DFT "
                   "engine takes)", P, S, mf_taps(*prm));
         return NIS_ERR_UNSUPPORTED;
     }

@@ -471,13 +471,16 @@ def test_rda_golden_reference_vectors(api, tag):
 
 @pytest.mark.parametrize("n_ranges,n_pulses,t_p", [(1024, 512, 2e-6), (2048, 2048, 5e-6), (1000, 360, 3e-6),
                                                    (4096, 256, 1e-5), (520, 4096, 1e-6), (8192, 64, 1e-5), (13200, 45, 1e-5),
-                                                   (256, 32768, 1e-6), (13200, 48, 2e-5), (5000, 64, 2e-5)])
+                                                   (256, 32768, 1e-6), (13200, 48, 2e-5), (5000, 64, 2e-5),
+                                                   (4096, 40, 3e-5)])
 def test_rda_vs_oracle(api, n_ranges, n_pulses, t_p):
     """Larger frames against the numpy oracle: matched filters of 61 ... 6001 taps (FFT lengths 1024 ... 16384),
     four-step and row-DFT azimuth engines, migration of several range cells at the band edge; 8192 samples take the pruned
     16384-point range compression (two 8192-point transforms each way), 13200 the unpruned one; 32768 pulses is the aperture
     sar_vehicle_sim.py focuses (:43): radix-32 outer azimuth stage; T_p = 20 us at 600 MHz is the satellite scripts' own
-    12001-tap filter on their 13200-sample window (overlap-save blocks: the filter does not fit one 16384-point block)."""
+    12001-tap filter on their 13200-sample window (the filter does not fit one 16384-point block with the pulse: one
+    32768-point block in the pruned form; 5000 samples keep the two-block overlap-save kernel; 18001 taps on 4096 samples is
+    a filter no 16384-point block could hold)."""
     prm = params.spaceborne_preset(fs=60e6 if t_p < 1e-5 else 600e6, bw=50e6).replace(T_p=t_p)
     rng = np.random.default_rng(n_ranges + n_pulses)
     x = (rng.standard_normal((n_ranges, n_pulses)) + 1j * rng.standard_normal((n_ranges, n_pulses))).astype(np.complex64)
@@ -747,7 +750,9 @@ def test_abi_error_behaviour_on_device(dev):
     rk = dict(lam=prm.Lambda, t_p=prm.T_p, kr=prm.k_rate, fs=prm.FS, prf=prm.PRF, vr=prm.V_eff, range_grp=prm.R0)
     assert dev.RdaPlan.supported(64, 20000, **rk)                 # long filter + long pulse: overlap-save blocks
     assert not dev.RdaPlan.supported(64, 30000, **rk)             # a 30000-sample row does not fit the RCMC row buffer
-    assert not dev.RdaPlan.supported(64, 4096, **{**rk, "t_p": 3e-5})   # 18001 taps: no block left for outputs
+    assert dev.RdaPlan.supported(64, 4096, **{**rk, "t_p": 3e-5})       # 18001 taps: one 32768-point block (pruned form)
+    assert not dev.RdaPlan.supported(64, 20000, **{**rk, "t_p": 3e-5})  # ... which needs the pulse in its lower half
+    assert not dev.RdaPlan.supported(64, 4096, **{**rk, "t_p": 6e-5})   # 36001 taps: longer than any block
     with pytest.raises(NisError, match="not supported"):
         dev.RdaPlan(64, 30000, **rk)
     with pytest.raises(NisError, match="taps"):
