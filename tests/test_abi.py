@@ -83,6 +83,12 @@ def test_scene_builders_are_seeded():
     assert abs(np.linalg.norm(s["pos_tx"][1]) - s["prm"].R0) < 1e-3
     pos, rcs = scenes.dense_vehicle_scene(1, 500)
     assert pos.shape == (500, 3) and rcs.shape == (500,)
+    # HRWS-N: phase centres (k - (N-1)/2) d_rx; N = 2 is the reference's own pair (sar_ati_dcpa_sim_csa.py:184-196)
+    h8 = scenes.hrws_scene(8, seed=4, num_pulses=16, num_clutter=10)
+    d = h8["prm"].d_rx
+    assert np.allclose(h8["rx_offsets"], [(k - 3.5) * d for k in range(8)], rtol=0, atol=1e-12)
+    assert np.allclose(np.diff(h8["rx_offsets"]), d) and np.array_equal(h8["clutter_pos"], a["clutter_pos"])
+    assert scenes.hrws_scene(2, seed=4, num_pulses=16, num_clutter=10)["rx_offsets"] == a["rx_offsets"]
 
 
 def test_bench_reference_arm_prints_the_contract_line():
