@@ -167,7 +167,10 @@ typedef struct {
     double range_grp;  /* range_grp_m */
 } nis_rda_params;
 
-/* 1 if an (n_pulses, n_ranges) frame with this matched-filter length can be focused */
+/* 1 if an (n_pulses, n_ranges) frame with this matched-filter length (taps = int(t_p * fs) + 1) can be focused:
+ * n_ranges <= 24576; taps <= 14337 (one or several 16384-point blocks), or taps <= 32768 with n_ranges <= 16384 and
+ * n_ranges + taps / 2 <= 32768 (one 32768-point block); n_pulses a power of two 64..32768 with n_ranges % 32 == 0, or any length
+ * the row-DFT engines take (prime factors <= 13 up to 14000, anything else up to 8192). */
 NIS_API int nis_rda_supported(int32_t n_pulses, int32_t n_ranges, const nis_rda_params* prm);
 NIS_API int nis_rda_plan_create(nis_ctx* ctx, int32_t n_pulses, int32_t n_ranges, const nis_rda_params* prm,
                         nis_rda_plan** out);
