@@ -91,6 +91,19 @@ def test_scene_builders_are_seeded():
     assert scenes.hrws_scene(2, seed=4, num_pulses=16, num_clutter=10)["rx_offsets"] == a["rx_offsets"]
 
 
+def test_videosar_timeline_matches_sar_batch_sim():
+    """The sliding-CPI frame loop of sar_batch_sim.py (:244-252, :303-306) at its own constants (PRF 5000, 5 s, 10 fps,
+    0.5 s CPI): 25000 pulses, frames every 500 pulses, 2500-pulse CPIs, and only 46 of the 50 requested frames fit."""
+    from nis_sar import video
+    prm = params.batch_spotlight_preset()
+    t_all, step, cpi, nfr = video.batch_timeline(prm)
+    assert (len(t_all), step, cpi, nfr) == (25000, 500, 2500, 50)
+    assert t_all[0] == -2.5 and t_all[-1] == 2.5
+    wins = video.cpi_windows(len(t_all), step, cpi, nfr)
+    assert len(wins) == 46 and wins[0] == (0, 2500) and wins[-1] == (22500, 25000)
+    assert video.cpi_windows(100, 10, 101, 5) == [] and video.cpi_windows(100, 10, 100, 5) == [(0, 100)]
+
+
 def test_bench_reference_arm_prints_the_contract_line():
     """`bench.py --impl reference` (the CPU arm the driver runs beside the GPU arm): one JSON line with the contract's keys,
     the reference-arm additions, and the same metric / unit / config as the GPU arm."""
