@@ -91,6 +91,21 @@ def test_scene_builders_are_seeded():
     assert scenes.hrws_scene(2, seed=4, num_pulses=16, num_clutter=10)["rx_offsets"] == a["rx_offsets"]
 
 
+def test_fft_engine_index_arithmetic_on_the_host():
+    """fft.cuh's pass functions are __host__ __device__: csrc/hosttest runs the exact scatter / gather / twiddle index
+    arithmetic of every power-of-two plan the kernels instantiate (padded and strided shared-memory layouts included) on the
+    CPU, threads one after another between the barriers, against a double-precision DFT."""
+    import shutil
+    import subprocess
+    if shutil.which("nvcc") is None:
+        pytest.skip("nvcc not on PATH")
+    csrc = os.path.join(ROOT, "nis-sar-amtigmti-video_b200", "csrc")
+    subprocess.run(["make", "-C", csrc, "hosttest"], check=True, capture_output=True, timeout=300)
+    out = subprocess.run([os.path.join(csrc, "..", "lib", "test_fft_host")], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0 and out.stdout.strip().endswith("all ok"), out.stdout[-2000:]
+    assert out.stdout.count("fwd") >= 20            # one line per plan
+
+
 def test_videosar_timeline_matches_sar_batch_sim():
     """The sliding-CPI frame loop of sar_batch_sim.py (:244-252, :303-306) at its own constants (PRF 5000, 5 s, 10 fps,
     0.5 s CPI): 25000 pulses, frames every 500 pulses, 2500-pulse CPIs, and only 46 of the 50 requested frames fit."""
