@@ -103,7 +103,7 @@ def test_fft_engine_index_arithmetic_on_the_host():
     subprocess.run(["make", "-C", csrc, "hosttest"], check=True, capture_output=True, timeout=300)
     out = subprocess.run([os.path.join(csrc, "..", "lib", "test_fft_host")], capture_output=True, text=True, timeout=300)
     assert out.returncode == 0 and out.stdout.strip().endswith("all ok"), out.stdout[-2000:]
-    assert out.stdout.count("fwd") >= 20            # one line per plan
+    assert out.stdout.count("fwd") >= 19            # one line per plan
 
 
 def test_videosar_timeline_matches_sar_batch_sim():
