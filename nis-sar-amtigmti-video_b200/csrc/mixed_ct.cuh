@@ -55,7 +55,7 @@ struct Root {   // exp(-2 pi i M / R), argument folded into (-pi, pi]
 };
 
 template <int B, int E, class F>
-__device__ __forceinline__ void static_for(F&& f) {
+__host__ __device__ __forceinline__ void static_for(F&& f) {
     if constexpr (B < E) {
         f(std::integral_constant<int, B>{});
         static_for<B + 1, E>(f);
@@ -64,7 +64,7 @@ __device__ __forceinline__ void static_for(F&& f) {
 
 // ---- small DFTs, in place, natural order.  STRIDE lets the prime-factor map run sub-transforms on strided registers.
 template <int R, bool INV, int STRIDE>
-__device__ __forceinline__ void dft_odd(float2* v) {
+__host__ __device__ __forceinline__ void dft_odd(float2* v) {
     constexpr int H = (R - 1) / 2;
     float2 s[H + 1], d[H + 1];
     float2 x0 = v[0];
@@ -96,7 +96,7 @@ __device__ __forceinline__ void dft_odd(float2* v) {
 }
 
 template <int R, bool INV, int STRIDE>
-__device__ __forceinline__ void dft_pow2(float2* v) {
+__host__ __device__ __forceinline__ void dft_pow2(float2* v) {
     if constexpr (R == 2) {
         const float2 a = v[0], b = v[STRIDE];
         v[0] = make_float2(a.x + b.x, a.y + b.y);
@@ -116,7 +116,7 @@ constexpr bool is_pow2(int r) { return (r & (r - 1)) == 0; }
 constexpr int pow2_part(int r) { return r & (-r); }
 
 template <int R, bool INV, int STRIDE = 1>
-__device__ __forceinline__ void dft_small(float2* v) {
+__host__ __device__ __forceinline__ void dft_small(float2* v) {
     if constexpr (is_pow2(R)) {
         dft_pow2<R, INV, STRIDE>(v);
     } else if constexpr (R % 2 == 1) {
@@ -179,13 +179,14 @@ void build_tables(float2* h) {   // host: [pass 1 | pass 2 | pass 3], each [r - 
 // ---- passes.  R = radix, NS = product of the earlier radices, NB = N / R butterflies, IT per thread.
 template <class MP, int R, int NS, bool POW>
 struct Pass {
+    static constexpr int R_ = R, NS_ = NS;
     static constexpr int NB = MP::N / R, IT = (NB + MP::NT - 1) / MP::NT;
     static constexpr bool FULL = (NB % MP::NT) == 0;
-    __device__ static __forceinline__ bool active(int j) { return FULL || j < NB; }
+    __host__ __device__ static __forceinline__ bool active(int j) { return FULL || j < NB; }
 
     // v[r] *= w^(k r) (CONJ: conjugated)
     template <bool CONJ>
-    __device__ static __forceinline__ void twiddle(float2* v, const float2* __restrict__ tw, int k) {
+    __host__ __device__ static __forceinline__ void twiddle(float2* v, const float2* __restrict__ tw, int k) {
         if constexpr (NS > 1 && !POW) {
 #pragma unroll
             for (int r = 1; r < R; ++r) {
@@ -208,20 +209,20 @@ struct Pass {
             for (int r = 1; r < R; ++r) v[r] = CONJ ? cmul_conj(v[r], w[r]) : cmul(v[r], w[r]);
         }
     }
-    __device__ static __forceinline__ void gather(float2* v, const float2* sm, int j) {
+    __host__ __device__ static __forceinline__ void gather(float2* v, const float2* sm, int j) {
 #pragma unroll
         for (int r = 0; r < R; ++r) v[r] = sm[j + r * NB];
     }
-    __device__ static __forceinline__ void spread(const float2* v, float2* sm, int j) {
+    __host__ __device__ static __forceinline__ void spread(const float2* v, float2* sm, int j) {
 #pragma unroll
         for (int r = 0; r < R; ++r) sm[j + r * NB] = v[r];
     }
-    __device__ static __forceinline__ void gather_t(float2* v, const float2* sm, int j, int k) {
+    __host__ __device__ static __forceinline__ void gather_t(float2* v, const float2* sm, int j, int k) {
         const int base = (j - k) * R + k;
 #pragma unroll
         for (int q = 0; q < R; ++q) v[q] = sm[base + q * NS];
     }
-    __device__ static __forceinline__ void spread_t(const float2* v, float2* sm, int j, int k) {
+    __host__ __device__ static __forceinline__ void spread_t(const float2* v, float2* sm, int j, int k) {
         const int base = (j - k) * R + k;
 #pragma unroll
         for (int q = 0; q < R; ++q) sm[base + q * NS] = v[q];

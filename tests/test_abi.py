@@ -92,8 +92,8 @@ def test_scene_builders_are_seeded():
 
 
 def test_fft_engine_index_arithmetic_on_the_host():
-    """fft.cuh's pass functions are __host__ __device__: csrc/hosttest runs the exact scatter / gather / twiddle index
-    arithmetic of every power-of-two plan the kernels instantiate (padded and strided shared-memory layouts included) on the
+    """fft.cuh's and mixed_ct.cuh's pass functions are __host__ __device__: csrc/hosttest runs the exact scatter / gather /
+    twiddle index arithmetic of every plan the kernels instantiate (padded and strided shared-memory layouts included) on the
     CPU, threads one after another between the barriers, against a double-precision DFT."""
     import shutil
     import subprocess
@@ -104,6 +104,11 @@ def test_fft_engine_index_arithmetic_on_the_host():
     out = subprocess.run([os.path.join(csrc, "..", "lib", "test_fft_host")], capture_output=True, text=True, timeout=300)
     assert out.returncode == 0 and out.stdout.strip().endswith("all ok"), out.stdout[-2000:]
     assert out.stdout.count("fwd") >= 19            # one line per plan
+    # mixed_ct.cuh (13200 = 11.10.10.12, 7200 = 9.10.10.8): small DFTs, twiddle tables (full and powers-of-w^k), forward passes
+    # 0..3 and the transposed inverse passes 3..0 in the order k_row_mixed_ct runs them
+    out = subprocess.run([os.path.join(csrc, "..", "lib", "test_mixed_host")], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0 and out.stdout.strip().endswith("all ok"), out.stdout[-2000:]
+    assert "MP13200" in out.stdout and "MP7200" in out.stdout
 
 
 def test_videosar_timeline_matches_sar_batch_sim():
