@@ -156,8 +156,6 @@ __host__ __device__ __forceinline__ void pass_scatter(const float2* v, int t, fl
 #pragma unroll
         for (int q = 0; q < R; ++q) {
             // Ns == 1: base = j R is a multiple of R, q < R <= 2^PAD never carries into the padded digit
-            constexpr int dummy = 0;
-            (void)dummy;
             const int off = (Ns == 1) ? q : padoff<PADSHIFT>(q * Ns);
             p[off * SMS] = v[b + brev(q, LR) * B];
         }
