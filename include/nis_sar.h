@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define NIS_SAR_ABI_VERSION 1
+#define NIS_SAR_ABI_VERSION 2
 
 #if defined(__GNUC__)
 #define NIS_API __attribute__((visibility("default")))
@@ -53,7 +53,11 @@ typedef void* nis_stream; /* cudaStream_t */
 NIS_API int nis_version(void);
 /* copies the calling thread's last error message (NUL terminated) and returns its length */
 NIS_API size_t nis_last_error(char* buf, size_t cap);
-/* one context per device; owns scratch used by nis_gmti_fused */
+/* one context per device.  Calls on one ctx may be issued from several streams (and host threads) at once: the only
+ * library-owned scratch (pulse tables of nis_tdbp_backproject, histograms of nis_region_select) is kept per stream, is
+ * never freed while the ctx lives (a captured CUDA graph may replay with its address) and refuses to grow while its
+ * stream is capturing -- run the call once outside the capture first.  Every entry point expects the ctx's device to be
+ * the calling thread's current CUDA device (plan / ctx creation switch to it themselves and restore the caller's). */
 NIS_API int nis_ctx_create(int device, nis_ctx** out);
 NIS_API int nis_ctx_destroy(nis_ctx* ctx);
 /* number of kernels this library has launched on ctx since creation (bench.py "gpu_launches") */
@@ -218,7 +222,17 @@ NIS_API int nis_tdbp_backproject(nis_tdbp_plan* plan, const nis_c32* rc, const d
  *   phase_masked = mask ? phase : 0; det_idx = ascending flat indices with mask set;
  *   peak = first index attaining max|slc1|.
  * Any output pointer may be NULL (that product is not materialised).
+ * One pass over the pair: products, detection flags and the compaction of the flagged indices happen in the same kernel
+ * (per-tile counts chained by a decoupled look-back), preceded only by a pass over slc1 for max|slc1| when the caller
+ * does not pass max_mag_sq_in.
+ * Buffers: every pointer aligned to its element size (8 B complex, 4 B float / index).  When additionally the complex
+ * buffers are 16-byte, the float maps 8-byte and the mask 2-byte aligned -- true for any whole allocation -- the kernel
+ * moves two pixels per access; views at odd element offsets take an element-wise variant of the same kernel.
+ * n_pix < 2^32 - 1 (flat indices and det_count are 32-bit: every BASELINE size fits).
+ * workspace: dev, caller-owned, nis_gmti_workspace_bytes(n_pix) bytes (8 bytes per 2048 pixels + 16), 8-byte aligned,
+ * contents irrelevant on entry; it must not be shared by two calls that may run concurrently.
  */
+NIS_API uint64_t nis_gmti_workspace_bytes(uint64_t n_pix);
 typedef struct {
     uint32_t det_count;   /* number of detected pixels (may exceed det_cap: list is truncated) */
     uint32_t peak_idx;    /* flat index of the first maximum of |slc1| */
@@ -231,7 +245,8 @@ NIS_API int nis_gmti_fused(nis_ctx* ctx, const nis_c32* slc1, const nis_c32* slc
                    float* slc1_mag, uint8_t* mag_mask, float* ati_phase_masked,
                    uint32_t* det_idx, uint32_t det_cap,
                    const double* max_mag_sq_in /* dev, optional: max |slc1|^2 from nis_csa_focus */,
-                   nis_gmti_result* result /* dev */, nis_stream stream);
+                   void* workspace /* dev */, uint64_t workspace_bytes,
+                   nis_gmti_result* result /* dev, 16 bytes, written by the call */, nis_stream stream);
 /* viewer auto-balance (sar_ati_dcpa_viewer_csa.py:249-250): sum slc1 conj(slc2) in fp64;
  * out: dev [2] doubles (re, im) of the SUM (angle of the mean == angle of the sum) */
 NIS_API int nis_gmti_balance_sum(nis_ctx* ctx, const nis_c32* slc1, const nis_c32* slc2, uint64_t n_pix,
@@ -277,6 +292,26 @@ NIS_API int nis_peer_alloc(uint64_t bytes, void** ptr, uint8_t* handle64);
 NIS_API int nis_peer_free(void* ptr);
 NIS_API int nis_peer_open(const uint8_t* handle64, void** ptr);
 NIS_API int nis_peer_close(void* ptr);
+
+/* 1 when `device` performs atomics on `peer`'s memory natively over their link (cudaDevP2PAttrNativeAtomicSupported):
+ * the precondition of accumulate = 2 into a peer-mapped buffer (system-scope RED.ADD); 0 -> use nis_echo_reduce. */
+NIS_API int nis_peer_native_atomics(int32_t device, int32_t peer);
+
+/* ------------------------------------------------------------------ collectives (the path's two exchange steps, NCCL)
+ * One process per GPU; the 128-byte id is created by rank 0 (nis_comm_unique_id) and distributed over the caller's own
+ * control plane (torch.distributed, MPI, a file ...).  nis_comm_init binds to the calling thread's current device.
+ * NCCL is resolved at run time from the host process (libnccl.so.2); without it these return NIS_ERR_UNSUPPORTED.
+ *   nis_echo_reduce   raw[n_samples] complex64 summed in place across ranks -- the reduction of scatterer-sharded echo
+ *                     synthesis (config 3): root = -1 all-reduce, else reduce to `root`.  Sum order differs from the
+ *                     one-GPU run: results agree to fp32 rounding, not bit-wise.
+ *   nis_slc_exchange  ring shift for DPCA/ATI channel pairing (one receive channel per rank): rank k sends its focused
+ *                     image to rank k-1 and receives channel k+1 into slc_next (NULL on the last rank). */
+typedef struct nis_comm nis_comm;
+NIS_API int nis_comm_unique_id(uint8_t* id128);
+NIS_API int nis_comm_init(int32_t rank, int32_t nranks, const uint8_t* id128, nis_comm** out);
+NIS_API int nis_comm_destroy(nis_comm* comm);
+NIS_API int nis_echo_reduce(nis_comm* comm, nis_c32* raw, uint64_t n_samples, int32_t root, nis_stream stream);
+NIS_API int nis_slc_exchange(nis_comm* comm, const nis_c32* slc_local, nis_c32* slc_next, uint64_t n_pix, nis_stream stream);
 
 /* ------------------------------------------------------------------ buffer format helpers
  * The reference's arrays are complex128; these convert on the device so that host<->device copies

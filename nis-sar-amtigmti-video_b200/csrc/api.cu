@@ -19,17 +19,27 @@ void set_error(const char* fmt, ...) {
 
 using namespace nis;
 
-int nis_ctx::ensure_scratch(size_t bytes) {
-    if (bytes <= scratch_bytes) return NIS_OK;
-    if (scratch) cudaFree(scratch);
-    scratch = nullptr;
-    scratch_bytes = 0;
-    size_t want = bytes + (bytes >> 2);
-    if (cudaMalloc(&scratch, want) != cudaSuccess) {
-        set_error("scratch allocation of %zu bytes failed: %s", want, cudaGetErrorString(cudaGetLastError()));
-        return NIS_ERR_NOMEM;
+int nis_ctx::stream_scratch(cudaStream_t st, size_t bytes, void** out) {
+    std::lock_guard<std::mutex> lock(mu);
+    Scratch& s = scratch[st];
+    if (bytes > s.bytes) {
+        cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+        if (cudaStreamIsCapturing(st, &cap) == cudaSuccess && cap != cudaStreamCaptureStatusNone) {
+            set_error("workspace of %zu bytes needed while the stream is capturing: run the call once outside the capture "
+                      "first (allocation is not captured)", bytes);
+            return NIS_ERR_INVALID;
+        }
+        const size_t want = bytes + (bytes >> 2);
+        void* p = nullptr;
+        if (cudaMalloc(&p, want) != cudaSuccess) {
+            set_error("scratch allocation of %zu bytes failed: %s", want, cudaGetErrorString(cudaGetLastError()));
+            return NIS_ERR_NOMEM;
+        }
+        if (s.ptr) retired.push_back(s.ptr);   // a captured graph may still replay with the old address
+        s.ptr = p;
+        s.bytes = want;
     }
-    scratch_bytes = want;
+    *out = s.ptr;
     return NIS_OK;
 }
 
@@ -55,7 +65,6 @@ extern "C" int nis_ctx_create(int device, nis_ctx** out) {
         return NIS_ERR_CUDA;
     }
     NIS_REQUIRE(device >= 0 && device < count, "nis_ctx_create: device %d out of range (0..%d)", device, count - 1);
-    NIS_CUDA_TRY(cudaSetDevice(device));
     cudaDeviceProp prop;
     NIS_CUDA_TRY(cudaGetDeviceProperties(&prop, device));
     if (prop.major != 10) {
@@ -72,7 +81,12 @@ extern "C" int nis_ctx_create(int device, nis_ctx** out) {
 
 extern "C" int nis_ctx_destroy(nis_ctx* ctx) {
     if (!ctx) return NIS_OK;
-    if (ctx->scratch) cudaFree(ctx->scratch);
+    {
+        DeviceGuard guard(ctx->device);
+        for (auto& kv : ctx->scratch)
+            if (kv.second.ptr) cudaFree(kv.second.ptr);
+        for (void* p : ctx->retired) cudaFree(p);
+    }
     delete ctx;
     return NIS_OK;
 }

@@ -4,7 +4,10 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <map>
+#include <mutex>
 #include <string>
+#include <vector>
 
 #include "../../include/nis_sar.h"
 
@@ -52,11 +55,32 @@ struct nis_ctx {
     int device = 0;
     int num_sms = nis::kNumSMsB200;
     uint64_t launches = 0;
-    // scratch for the GMTI detection pipeline (grown on demand)
-    void* scratch = nullptr;
-    size_t scratch_bytes = 0;
-    int ensure_scratch(size_t bytes);
+    // Small library-owned workspaces (pulse tables of the backprojector, histograms of the order-statistics select) are
+    // kept PER STREAM: two calls in flight on different streams of one device never share bytes.  A buffer that has to
+    // grow is retired, not freed (a captured CUDA graph may still hold its address), and growth is refused while the
+    // stream is capturing.  Large workspaces (nis_gmti_fused) belong to the caller.
+    struct Scratch { void* ptr = nullptr; size_t bytes = 0; };
+    std::mutex mu;
+    std::map<cudaStream_t, Scratch> scratch;
+    std::vector<void*> retired;
+    int stream_scratch(cudaStream_t st, size_t bytes, void** out);
 };
+
+namespace nis {
+// cudaSetDevice for the lifetime of a C entry point; the caller's current device is restored on return
+struct DeviceGuard {
+    int prev = -1;
+    bool switched = false;
+    explicit DeviceGuard(int device) {
+        if (cudaGetDevice(&prev) == cudaSuccess && prev != device) switched = cudaSetDevice(device) == cudaSuccess;
+    }
+    ~DeviceGuard() {
+        if (switched) cudaSetDevice(prev);
+    }
+    DeviceGuard(const DeviceGuard&) = delete;
+    DeviceGuard& operator=(const DeviceGuard&) = delete;
+};
+}  // namespace nis
 
 namespace nis {
 

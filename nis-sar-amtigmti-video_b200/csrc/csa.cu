@@ -799,7 +799,7 @@ extern "C" int nis_csa_plan_create(nis_ctx* ctx, int32_t n_az, int32_t n_rg, con
     }
     NIS_REQUIRE(prm->fs > 0 && prm->prf > 0 && prm->vr > 0 && prm->kr != 0 && prm->lambda > 0 && prm->c > 0,
                 "nis_csa_plan_create: non-physical parameters");
-    NIS_CUDA_TRY(cudaSetDevice(ctx->device));
+    DeviceGuard device_guard(ctx->device);   // the caller's current device is restored on return
     nis_csa_plan* pl = new nis_csa_plan();
     pl->ctx = ctx;
     pl->n_az = n_az;
@@ -830,7 +830,11 @@ extern "C" int nis_csa_plan_create(nis_ctx* ctx, int32_t n_az, int32_t n_rg, con
     {
         std::vector<RowCoef> h = build_row_coefs(n_az, n_rg, *prm, pl->A1, pl->A2);
         FAIL_IF(cudaMalloc(&pl->coef, n_az * sizeof(RowCoef)) == cudaSuccess ? NIS_OK : NIS_ERR_NOMEM);
-        NIS_CUDA_TRY(cudaMemcpy(pl->coef, h.data(), n_az * sizeof(RowCoef), cudaMemcpyHostToDevice));
+        if (cudaMemcpy(pl->coef, h.data(), n_az * sizeof(RowCoef), cudaMemcpyHostToDevice) != cudaSuccess) {
+            set_error("nis_csa_plan_create: upload of the phase coefficients failed: %s", cudaGetErrorString(cudaGetLastError()));
+            nis_csa_plan_destroy(pl);
+            return NIS_ERR_CUDA;
+        }
     }
     if (cls == 2) {
         FAIL_IF(generic_create(pl));

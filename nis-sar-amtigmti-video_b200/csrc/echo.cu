@@ -234,9 +234,11 @@ __global__ void __launch_bounds__(256, SPOT ? 1 : 4) k_echo(EchoConst k, EchoTai
             float2 x = cmul(acc[j], tail.e[j]);
             if (k.accumulate == 2) {
                 // several GPUs add their scatterer shards into one owner's rows, possibly over NVLink: fire-and-forget
-                // reductions (RED.ADD.F32), no read-modify-write round trip
-                atomicAdd(&out[j].x, x.x);
-                atomicAdd(&out[j].y, x.y);
+                // reductions (RED.E.ADD.F32 ... .SYS), no read-modify-write round trip.  SYSTEM scope: concurrent updates of one
+                // address by several devices are only defined for .sys atomics, and only where the link performs them natively
+                // (nis_peer_native_atomics; the Python layer falls back to the NCCL reduce otherwise)
+                atomicAdd_system(&out[j].x, x.x);
+                atomicAdd_system(&out[j].y, x.y);
             } else {
                 if (k.accumulate) { const float2 o = out[j]; x.x += o.x; x.y += o.y; }
                 out[j] = x;

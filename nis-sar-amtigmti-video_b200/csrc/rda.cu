@@ -465,7 +465,7 @@ extern "C" int nis_rda_plan_create(nis_ctx* ctx, int32_t P, int32_t S, const nis
                   "engine takes)", P, S, mf_taps(*prm));
         return NIS_ERR_UNSUPPORTED;
     }
-    NIS_CUDA_TRY(cudaSetDevice(ctx->device));
+    DeviceGuard device_guard(ctx->device);   // the caller's current device is restored on return
     nis_rda_plan* pl = new nis_rda_plan();
     pl->ctx = ctx;
     pl->P = P;

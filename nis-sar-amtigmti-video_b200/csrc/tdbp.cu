@@ -282,7 +282,7 @@ extern "C" int nis_tdbp_plan_create(nis_ctx* ctx, const nis_tdbp_params* prm, ni
                 "nis_tdbp_plan_create: non-physical parameters");
     const int L = (int)(prm->t_p * prm->fs);   // int(T_P * FS) taps (:177)
     NIS_REQUIRE(L >= 1 && L <= 12288, "nis_tdbp_plan_create: %d reference-chirp taps (supported: 1..12288)", L);
-    NIS_CUDA_TRY(cudaSetDevice(ctx->device));
+    DeviceGuard device_guard(ctx->device);   // the caller's current device is restored on return
     nis_tdbp_plan* pl = new nis_tdbp_plan();
     pl->ctx = ctx;
     pl->prm = *prm;
@@ -371,9 +371,10 @@ extern "C" int nis_tdbp_backproject(nis_tdbp_plan* pl, const nis_c32* rc, const 
     k.nx = p.nx; k.ny = p.ny; k.n_pulses = n_pulses; k.W = p.n_samples;
     const int n_pix = p.nx * p.ny;
     cudaStream_t st = (cudaStream_t)stream;
-    int rc2 = pl->ctx->ensure_scratch((size_t)n_pulses * 6 * sizeof(double));
+    void* tab_raw = nullptr;
+    int rc2 = pl->ctx->stream_scratch(st, (size_t)n_pulses * 6 * sizeof(double), &tab_raw);   // per stream, never freed under a graph
     if (rc2 != NIS_OK) return rc2;
-    double* tab = reinterpret_cast<double*>(pl->ctx->scratch);
+    double* tab = reinterpret_cast<double*>(tab_raw);
     k_tdbp_pulse_table<<<(n_pulses + 127) / 128, 128, 0, st>>>(k, pos_plat, vel_plat, t_pulses, n_pulses, tab);
     NIS_LAUNCH_CHECK(pl->ctx);
     k_tdbp<<<(n_pix + 63) / 64, 64, 0, st>>>(k, reinterpret_cast<const float2*>(rc), tab, pl->xs, pl->ys, p_begin, p_end,

@@ -207,10 +207,11 @@ extern "C" int nis_region_select(nis_ctx* ctx, const float* map, int64_t pitch, 
     }
     cudaStream_t st = (cudaStream_t)stream;
     const size_t hist_bytes = (size_t)kMaxRanks * 2048 * sizeof(unsigned long long);
-    int rc = ctx->ensure_scratch(hist_bytes + sizeof(init));
+    void* ws = nullptr;
+    int rc = ctx->stream_scratch(st, hist_bytes + sizeof(init), &ws);   // per stream, never freed under a graph
     if (rc != NIS_OK) return rc;
-    unsigned long long* hist = reinterpret_cast<unsigned long long*>(ctx->scratch);
-    SelectState* state = reinterpret_cast<SelectState*>(reinterpret_cast<char*>(ctx->scratch) + hist_bytes);
+    unsigned long long* hist = reinterpret_cast<unsigned long long*>(ws);
+    SelectState* state = reinterpret_cast<SelectState*>(reinterpret_cast<char*>(ws) + hist_bytes);
     NIS_CUDA_TRY(cudaMemsetAsync(hist, 0, hist_bytes, st));
     NIS_CUDA_TRY(cudaMemcpyAsync(state, init, sizeof(init), cudaMemcpyHostToDevice, st));
     const int shifts[3] = {21, 10, 0}, bits[3] = {11, 11, 10};

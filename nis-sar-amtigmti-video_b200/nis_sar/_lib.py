@@ -82,12 +82,19 @@ SIGNATURES = {
     "nis_peer_free": (C.c_int, [_P]),
     "nis_peer_open": (C.c_int, [_P, C.POINTER(_P)]),
     "nis_peer_close": (C.c_int, [_P]),
+    "nis_peer_native_atomics": (C.c_int, [C.c_int32, C.c_int32]),
+    "nis_comm_unique_id": (C.c_int, [_P]),
+    "nis_comm_init": (C.c_int, [C.c_int32, C.c_int32, _P, C.POINTER(_P)]),
+    "nis_comm_destroy": (C.c_int, [_P]),
+    "nis_echo_reduce": (C.c_int, [_P, _P, C.c_uint64, C.c_int32, _P]),
+    "nis_slc_exchange": (C.c_int, [_P, _P, _P, C.c_uint64, _P]),
     "nis_power_sum": (C.c_int, [_P, _P, C.c_uint64, _P, _P]),
     "nis_power_max": (C.c_int, [_P, _P, C.c_uint64, _P, _P]),
     "nis_noise_add": (C.c_int, [_P, _P, C.c_uint64, _P, C.c_double, C.c_double, C.c_double, C.c_double, C.c_uint64,
                                 C.c_int32, _P]),
+    "nis_gmti_workspace_bytes": (C.c_uint64, [C.c_uint64]),
     "nis_gmti_fused": (C.c_int, [_P, _P, _P, C.c_uint64, C.c_double, C.c_double,
-                                 _P, _P, _P, _P, _P, _P, _P, _P, C.c_uint32, _P, _P, _P]),
+                                 _P, _P, _P, _P, _P, _P, _P, _P, C.c_uint32, _P, _P, C.c_uint64, _P, _P]),
     "nis_gmti_balance_sum": (C.c_int, [_P, _P, _P, C.c_uint64, _P, _P]),
     "nis_narrow_c128_to_c32": (C.c_int, [_P, _P, _P, C.c_uint64, _P]),
     "nis_widen_c32_to_c128": (C.c_int, [_P, _P, _P, C.c_uint64, _P]),
@@ -130,17 +137,19 @@ def check(rc: int, what: str):
 _ctx = {}
 
 
+_ctx_lock = threading.Lock()
+
+
 def context(device_index: int):
-    """One nis_ctx per device, created on first use."""
-    with _lock:
+    """One nis_ctx per device, created on first use (the lock is held across the creation: two threads asking for the
+    same device get the same context)."""
+    lib = load()
+    with _ctx_lock:
         h = _ctx.get(device_index)
-    if h is None:
-        lib = load()
-        out = _P()
-        check(lib.nis_ctx_create(int(device_index), C.byref(out)), "nis_ctx_create")
-        with _lock:
-            _ctx[device_index] = out
-        h = out
+        if h is None:
+            out = _P()
+            check(lib.nis_ctx_create(int(device_index), C.byref(out)), "nis_ctx_create")
+            _ctx[device_index] = h = out
     return h
 
 

@@ -20,6 +20,7 @@ import numpy as np
 import torch
 
 from . import device as dev
+from . import hostio
 from .params import RadarParams, spaceborne_preset
 from .targets import targets_to_arrays
 
@@ -43,12 +44,36 @@ def _params(prm):
     return _default_params if _default_params is not None else spaceborne_preset()
 
 
-def _to_host_c128(t: torch.Tensor) -> np.ndarray:
-    """Device complex64 -> host complex128 numpy: widened on the device, one D2H copy into pinned memory."""
-    wide = dev.widen_c32(t)
-    host = torch.empty(wide.shape, dtype=torch.complex128, pin_memory=True)
-    host.copy_(wide, non_blocking=False)
-    return host.numpy()
+def _to_host_c128(t: torch.Tensor, out=None) -> np.ndarray:
+    """Device complex64 -> host complex128 numpy (``nis_sar.hostio``: widened on the device chunk by chunk, every chunk's
+    D2H copy overlapping the next chunk's widening, into ``out`` or a pinned block of the per-device pool)."""
+    return hostio.to_host_c128(t, out=out)
+
+
+def _to_host_c128_fortran(t: torch.Tensor, out=None) -> np.ndarray:
+    """The same values as an F-contiguous [rows, cols] array: the reference's ``img.T`` (sar_ati_dcpa_sim_csa.py:396) is a
+    view of a C-ordered [n_az, n_rg] buffer, and callers see that in ``.flags`` / ``.strides`` and in how ``np.savez``
+    (:457-461) lays the file out.  The corner turn back runs on the device (one 16 B/pixel pass, hidden behind PCIe)."""
+    return hostio.to_host_c128(dev.transpose_c32(t.contiguous()), out=None if out is None else out.T).T
+
+
+def _upload_c32(a, device) -> torch.Tensor:
+    """numpy complex (any layout) or torch tensor -> contiguous complex64 CUDA tensor of the same logical shape.  An
+    F-ordered 2-D numpy array (what sar_focus_csa returns) is uploaded through its C-ordered transpose and turned on the
+    device instead of being re-strided on the host."""
+    if torch.is_tensor(a):
+        x = a if a.is_cuda else a.to(device)
+        return x.contiguous() if x.dtype == torch.complex64 else dev.narrow_c128(x.to(torch.complex128).contiguous())
+    h = np.asarray(a)
+    turn = h.ndim == 2 and h.flags.f_contiguous and not h.flags.c_contiguous
+    if turn:
+        h = h.T
+    h = np.ascontiguousarray(h)
+    if h.dtype == np.complex64:
+        x = torch.from_numpy(h).to(device)
+    else:
+        x = dev.narrow_c128(torch.from_numpy(h.astype(np.complex128, copy=False)).to(device))
+    return dev.transpose_c32(x) if turn else x
 
 
 # ------------------------------------------------------------------------------------------ echo
@@ -167,12 +192,18 @@ def tdbp_gpu(raw_t, pos_plat, vel_plat, t_start, num_samples, vel_focus, t_pulse
 
 # ------------------------------------------------------------------------------------------- CSA
 def sar_focus_csa(phist, center_wavelength_m, pulse_width_sec, chirp_rate_hzpsec, sample_rate_hz, prf_hz,
-                  platform_speed_mps, range_ref_m, t_start_fast, *, device=None, return_device=False):
+                  platform_speed_mps, range_ref_m, t_start_fast, *, device=None, return_device=False, order="C",
+                  out=None):
     """Chirp Scaling focusing (sar_ati_dcpa_sim_csa.py:202-396).  ``phist`` is [N_az, N_rg]: a numpy
     complex array (any complex dtype) or a complex64 CUDA tensor.  Returns (img, range_axis,
     cross_range_axis) with img of shape [N_rg, N_az] -- the array the reference returns as ``img.T`` --
-    as complex128 numpy (C-contiguous; the reference's is the F-contiguous view of the same values).
+    as complex128 numpy.  ``order="C"`` (default here): C-contiguous, the layout the device holds and every later
+    stage wants; ``order="F"`` (what ``install()`` selects): the F-contiguous view semantics of the reference's
+    ``img.T`` (:396), same values, same ``.flags`` / ``.strides``.  ``out``: optional complex128 array of that shape and
+    order to receive the image (page-locked memory from ``nis_sar.hostio.pinned_empty`` avoids the staging copy).
     ``pulse_width_sec`` is unused, as in the reference."""
+    if order not in ("C", "F"):
+        raise dev.NisError("sar_focus_csa: order must be 'C' or 'F'")
     device = device or _default_device
     if torch.is_tensor(phist):
         x = phist if phist.dtype == torch.complex64 else dev.narrow_c128(phist.to(torch.complex128).contiguous())
@@ -190,7 +221,9 @@ def sar_focus_csa(phist, center_wavelength_m, pulse_width_sec, chirp_rate_hzpsec
                            r_ref=float(range_ref_m), t_start=float(t_start_fast), device=x.device)
     slc = plan.focus(x)
     rax, cax = plan.axes()
-    return (slc if return_device else _to_host_c128(slc)), rax, cax
+    if return_device:
+        return slc, rax, cax
+    return (_to_host_c128_fortran(slc, out) if order == "F" else _to_host_c128(slc, out)), rax, cax
 
 
 # ------------------------------------------------------------------------------------- noise / SNR
@@ -324,15 +357,7 @@ def gmti_products(slc1, slc2, thresh=0.05, cal_phase=0.0, *, device=None, return
     detected-pixel list (sar_ati_dcpa_sim_csa.py:414-419, :447-449).  Inputs [N_rg, N_az] complex."""
     device = device or _default_device
 
-    def up(a):
-        if torch.is_tensor(a):
-            return a.contiguous() if a.dtype == torch.complex64 else dev.narrow_c128(a.to(torch.complex128).contiguous())
-        h = np.ascontiguousarray(a)
-        if h.dtype == np.complex64:
-            return torch.from_numpy(h).to(device)
-        return dev.narrow_c128(torch.from_numpy(h.astype(np.complex128, copy=False)).to(device))
-
-    out = dev.gmti_fused(up(slc1), up(slc2), thresh, cal_phase)
+    out = dev.gmti_fused(_upload_c32(slc1, device), _upload_c32(slc2, device), thresh, cal_phase)
     if return_device:
         return out
     res = {}
@@ -362,13 +387,22 @@ def save_ati_dpca_npz(fname, slc1, slc2, range_axis, cross_range):
 
 # --------------------------------------------------------------------------------------- install
 _ENTRY_POINTS = ("run_bistatic_physics_gpu", "sar_focus_csa", "run_physics_engine", "run_moving_physics",
-                 "run_custom_physics")   # sar_focus_rda: install(ns, names=("sar_focus_rda",)) with functools.partial(returns=...)
+                 "run_custom_physics")
+_INSTALLABLE = _ENTRY_POINTS + ("sar_focus_rda", "add_ocean_noise", "calculate_snr_db", "run_physics_spotlight", "tdbp_gpu",
+                                "generate_noise_tensor", "calculate_raw_snr_db")
 
 
-def install(namespace: dict, names=_ENTRY_POINTS):
-    """Patch the reference's entry points inside ``namespace`` (a simulator module's ``globals()``)
-    with the CUDA implementations.  The replacements read ``C, R0, FC, BW, T_p, FS`` from that
-    namespace on every call, exactly like the functions they replace."""
+def install(namespace: dict, names=_ENTRY_POINTS, *, rda_returns="satellite", snr_preset="satellite"):
+    """Patch the reference's entry points inside ``namespace`` (a simulator module's ``globals()``) with the CUDA
+    implementations -- the drop-in mechanism INTEGRATION.md describes.  Replacements of functions that read radar
+    constants from their module (``C, R0, FC, BW, T_p, FS``: sar_ati_dcpa_sim_csa.py:111-115, :159-168) read them from
+    ``namespace`` on every call, exactly like the functions they replace; functions that take everything as arguments
+    are installed as they are.  ``sar_focus_csa`` is installed with ``order="F"`` (the reference's ``img.T`` view
+    semantics, :396).  ``rda_returns`` picks which copy of ``sar_focus_rda`` is being replaced ("satellite": 7-tuple,
+    "vehicle": 8-tuple, "moving": 3-tuple); ``snr_preset`` the radar constants of ``calculate_snr_db``."""
+    import functools
+    import inspect
+
     def live_params():
         base = spaceborne_preset()
         kw = {k: float(namespace[k]) for k in ("C", "R0", "FC", "BW", "T_p") if k in namespace}
@@ -376,15 +410,23 @@ def install(namespace: dict, names=_ENTRY_POINTS):
             kw["FS"] = float(namespace["FS"])
         return base.replace(**kw)
 
-    def _wrap(fn):
+    def with_live_params(fn):
+        @functools.wraps(fn)
         def patched(*a, **k):
             k.setdefault("params", live_params())
             return fn(*a, **k)
-        patched.__name__ = fn.__name__
-        patched.__doc__ = fn.__doc__
         return patched
 
     g = globals()
+    fixed = {"sar_focus_csa": {"order": "F"}, "sar_focus_rda": {"returns": rda_returns},
+             "calculate_snr_db": {"preset": snr_preset}}
     for n in names:
-        namespace[n] = g[n] if n == "sar_focus_csa" else _wrap(g[n])
+        if n not in _INSTALLABLE:
+            raise dev.NisError(f"install: {n!r} is not a replaceable entry point (known: {', '.join(_INSTALLABLE)})")
+        fn = g[n]
+        if n in fixed:
+            fn = functools.wraps(fn)(functools.partial(fn, **fixed[n]))
+        if "params" in inspect.signature(g[n]).parameters:
+            fn = with_live_params(fn)
+        namespace[n] = fn
     return namespace

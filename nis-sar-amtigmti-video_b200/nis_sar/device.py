@@ -60,8 +60,8 @@ def echo_accumulate(pos0, vel, rcs, pos_tx, pos_rx, t_slow, *, c, fc, k_rate, t_
     di = _dev_index(device)
     dev = torch.device("cuda", di)
     lib = _lib.load()
-    ctx = _lib.context(di)
     with torch.cuda.device(di):
+        ctx = _lib.context(di)
         pos0_d = _f64(np.asarray(pos0).reshape(-1, 3) if not torch.is_tensor(pos0) else pos0.cpu().numpy().reshape(-1, 3), dev)
         T = pos0_d.shape[0]
         vel_np = np.asarray(vel.cpu().numpy() if torch.is_tensor(vel) else vel, dtype=np.float64)
@@ -345,9 +345,10 @@ def add_noise(x, snr_db, scr_db=10.0, k_nu=1.0, seed=0, ref_power=None, accumula
     if x.dtype != torch.complex64 or not x.is_contiguous():
         raise NisError("add_noise: x must be a contiguous complex64 CUDA tensor")
     di = x.device.index
-    lib, ctx = _lib.load(), _lib.context(di)
+    lib = _lib.load()
     n = x.numel()
     with torch.cuda.device(di):
+        ctx = _lib.context(di)
         st = C.c_void_p(_stream_ptr(di))
         pdev, pval = None, 0.0
         if ref_power is None:
@@ -410,11 +411,16 @@ def gmti_fused(slc1, slc2, thresh_frac=0.05, cal_phase=0.0, want=GMTI_PRODUCTS, 
         pmask = alloc("ati_phase_masked", torch.float32)
         cap = n if det_cap is None else int(det_cap)
         det = torch.empty((max(cap, 1),), dtype=torch.int32, device=dev)
-        res = torch.zeros((16,), dtype=torch.uint8, device=dev)
-        rc = _lib.load().nis_gmti_fused(_lib.context(di), _ptr(slc1), _ptr(slc2), n, float(thresh_frac),
-                                        float(cal_phase), _ptr(interf), _ptr(phase), _ptr(diff), _ptr(dmag),
-                                        _ptr(mag1), _ptr(mask), _ptr(pmask), _ptr(det), cap, _ptr(max_sq), _ptr(res),
-                                        C.c_void_p(_stream_ptr(di)))
+        lib = _lib.load()
+        # per-call workspace and result record from torch's stream-ordered allocator (nothing is zero-filled here: the
+        # library initialises both); concurrent calls on other streams get their own
+        ws_bytes = int(lib.nis_gmti_workspace_bytes(n))
+        ws = torch.empty(((ws_bytes + 7) // 8,), dtype=torch.int64, device=dev)
+        res = torch.empty((2,), dtype=torch.int64, device=dev).view(torch.uint8)
+        rc = lib.nis_gmti_fused(_lib.context(di), _ptr(slc1), _ptr(slc2), n, float(thresh_frac),
+                                float(cal_phase), _ptr(interf), _ptr(phase), _ptr(diff), _ptr(dmag),
+                                _ptr(mag1), _ptr(mask), _ptr(pmask), _ptr(det), cap, _ptr(max_sq), _ptr(ws), ws_bytes,
+                                _ptr(res), C.c_void_p(_stream_ptr(di)))
         _lib.check(rc, "nis_gmti_fused")
         if lazy:            # no host synchronisation: the caller reads the 16-byte record / index list later
             if "mag_mask" in outs:

@@ -63,20 +63,89 @@ def echo_pulse_blocks(compute: Callable[[int, int, torch.Tensor], None], raw: to
 
 
 def echo_scatterer_shards(compute: Callable[[int, int], torch.Tensor], num_scatterers: int, dst: int | None = None,
-                          group=None) -> torch.Tensor:
+                          group=None, comm: "CComm | None" = None) -> torch.Tensor:
     """Scatterer sharding (config 3: 1e5 scatterers): rank r synthesises the partial echo of scatterers
     [t0, t1) over the whole [P, S] grid with ``compute(t0, t1)`` and the partial sums are added across
-    ranks -- ``dst`` None: all-reduce (every rank gets the echo); else reduce to rank ``dst``.
+    ranks -- ``dst`` None: all-reduce (every rank gets the echo); else reduce to rank ``dst``.  ``comm``: run the
+    reduction through the library's own entry point (``nis_echo_reduce``) instead of torch.distributed.
     fp32 summation order differs from the one-GPU run, so results agree to rounding, not bit-wise."""
     rank, n = world(group)
     t0, t1 = block_range(num_scatterers, rank, n)
     part = compute(t0, t1)
     if n > 1:
-        if dst is None:
+        if comm is not None:
+            comm.echo_reduce(part, root=-1 if dst is None else dst)
+        elif dst is None:
             dist.all_reduce(_as_real(part), op=dist.ReduceOp.SUM, group=group)
         else:
             dist.reduce(_as_real(part), dst=dst, op=dist.ReduceOp.SUM, group=group)
     return part
+
+
+class CComm:
+    """The library's own communicator (``nis_comm_*``, include/nis_sar.h): NCCL bound inside libnis_sar.so, driven through
+    the C ABI on torch's current stream.  torch.distributed is only the control plane that carries the 128-byte id from
+    rank 0 to the others -- a reference maintainer without torch.distributed would send it over MPI or a file.
+    Collective: every rank of ``group`` constructs it."""
+
+    def __init__(self, device=None, group=None):
+        import ctypes as C
+        from . import _lib
+        self.rank, self.n = world(group)
+        self.device = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
+        lib = _lib.load()
+        ident = (C.c_uint8 * 128)()
+        if self.rank == 0:
+            _lib.check(lib.nis_comm_unique_id(C.cast(ident, C.c_void_p)), "nis_comm_unique_id")
+        box = [bytes(ident)]
+        if self.n > 1:
+            dist.broadcast_object_list(box, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
+        ident = (C.c_uint8 * 128).from_buffer_copy(box[0])
+        self._h = C.c_void_p()
+        with torch.cuda.device(self.device):
+            _lib.check(lib.nis_comm_init(self.rank, max(self.n, 1), C.cast(ident, C.c_void_p), C.byref(self._h)),
+                       "nis_comm_init")
+
+    def _stream(self):
+        import ctypes as C
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def echo_reduce(self, raw: torch.Tensor, root: int = -1) -> torch.Tensor:
+        """Sum the partial echoes ``raw`` (complex64, same shape on every rank) in place: all ranks (root = -1) or root."""
+        import ctypes as C
+        from . import _lib
+        if raw.dtype != torch.complex64 or not raw.is_contiguous():
+            raise _lib.NisError("CComm.echo_reduce: raw must be a contiguous complex64 tensor")
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.load().nis_echo_reduce(self._h, C.c_void_p(raw.data_ptr()), raw.numel(), int(root), self._stream()),
+                       "nis_echo_reduce")
+        return raw
+
+    def slc_exchange(self, slc_local: torch.Tensor) -> torch.Tensor | None:
+        """Ring shift for channel pairing: returns channel rank+1's image (None on the last rank)."""
+        import ctypes as C
+        from . import _lib
+        if slc_local.dtype != torch.complex64 or not slc_local.is_contiguous():
+            raise _lib.NisError("CComm.slc_exchange: slc_local must be a contiguous complex64 tensor")
+        recv = torch.empty_like(slc_local) if self.rank < self.n - 1 else None
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.load().nis_slc_exchange(self._h, C.c_void_p(slc_local.data_ptr()),
+                                                    C.c_void_p(recv.data_ptr() if recv is not None else 0),
+                                                    slc_local.numel(), self._stream()), "nis_slc_exchange")
+        return recv
+
+    def close(self):
+        from . import _lib
+        if getattr(self, "_h", None) is not None and self._h.value:
+            torch.cuda.synchronize(self.device)
+            _lib.load().nis_comm_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 # ------------------------------------------------------------------ peer memory over NVLink / NVSwitch
@@ -110,8 +179,15 @@ class SharedBuffer:
             _lib.check(lib.nis_peer_alloc(nbytes, C.byref(self._ptr), C.cast(handle, C.c_void_p)), "nis_peer_alloc")
             self.local = torch.as_tensor(_CudaArray(self._ptr.value, shape, _TYPESTR[dtype]), device=self.device)
             handles = [None] * n
+            devs = [None] * n
             if n > 1:
                 dist.all_gather_object(handles, bytes(handle), group=group)
+                dist.all_gather_object(devs, int(self.device.index), group=group)
+            else:
+                devs = [int(self.device.index)]
+            # accumulate="atomic" into a peer's rows is defined only where the link performs system-scope atomics natively
+            # (NVLink does; PCIe peers may not): callers check this and fall back to the NCCL reduce (echo_scatterer_shards)
+            self.native_atomics = all(lib.nis_peer_native_atomics(int(self.device.index), int(d)) == 1 for d in devs)
             self._opened = {}
             self.views = []
             for r in range(n):
@@ -127,24 +203,38 @@ class SharedBuffer:
     def close(self):
         from . import _lib
         lib = _lib.load()
-        peer_barrier(self.device, self.group)
+        peer_barrier(self.device, self.group, host_sync=True)
         with torch.cuda.device(self.device):
             for p in self._opened.values():
                 lib.nis_peer_close(p)
             self._opened = {}
             self.views = []
-            peer_barrier(self.device, self.group)     # everybody has unmapped before anybody frees
+            peer_barrier(self.device, self.group, host_sync=True)     # everybody has unmapped before anybody frees
             if self._ptr:
                 lib.nis_peer_free(self._ptr)
                 self._ptr = None
             self.local = None
 
 
-def peer_barrier(device, group=None) -> None:
-    """Everything this rank has enqueued is complete and every rank has reached this point."""
-    torch.cuda.synchronize(device)
-    if world(group)[1] > 1:
-        dist.barrier(group=group)
+_barrier_token: dict = {}
+
+
+def peer_barrier(device, group=None, host_sync: bool = False) -> None:
+    """Producer -> consumer hand-off between ranks that read / reduce into each other's HBM.  Under NCCL this is a
+    one-element all-reduce enqueued on the current stream: work enqueued afterwards starts only when every rank's earlier
+    work on its stream has finished -- no host synchronisation, the CPU keeps enqueueing.  ``host_sync`` (and any other
+    backend): device synchronise + host barrier, for teardown paths that free memory."""
+    n = world(group)[1]
+    if host_sync or n == 1 or dist.get_backend(group) != "nccl":
+        torch.cuda.synchronize(device)
+        if n > 1:
+            dist.barrier(group=group)
+        return
+    key = (torch.device(device).index, id(group))
+    tok = _barrier_token.get(key)
+    if tok is None:
+        tok = _barrier_token[key] = torch.zeros(1, dtype=torch.float32, device=device)
+    dist.all_reduce(tok, group=group)
 
 
 def echo_scatterer_shards_p2p(compute_into: Callable[[int, int, int, int, torch.Tensor], None], num_scatterers: int,
@@ -157,6 +247,10 @@ def echo_scatterer_shards_p2p(compute_into: Callable[[int, int, int, int, torch.
     [P, S] echo is materialised and no separate collective runs.  Returns (p0, p1): the fully reduced rows of
     ``shared.local`` this rank holds."""
     rank, n = world(shared.group)
+    if not getattr(shared, "native_atomics", True):
+        from ._lib import NisError
+        raise NisError("echo_scatterer_shards_p2p: a peer link of this job does not perform atomics natively "
+                       "(cudaDevP2PAttrNativeAtomicSupported = 0); use echo_scatterer_shards (NCCL reduce)")
     P = shared.local.shape[0]
     t0, t1 = block_range(num_scatterers, rank, n)
     shared.local.zero_()

@@ -249,10 +249,40 @@ def golden_spotlight_tdbp():
     np.savez_compressed(os.path.join(OUT, "spotlight_tdbp.npz"), **out)
 
 
+def golden_csa_large():
+    """The reference's own sar_focus_csa at the two full sizes the GPU tests could not reach with an in-test oracle:
+    8192 x 8192 (BASELINE.json configs[1], the bench frame) and 7199 x 13200 (the default scene after the pulse shift,
+    sar_ati_dcpa_sim_csa.py:402-411).  ~1 min and ~25 GB each; stored as digests (oracle/inputs.image_digest)."""
+    from oracle import inputs
+    prm = params.spaceborne_preset()
+    out = {}
+    for tag, n_az, n_rg, seed in (("p8192", 8192, 8192, 8192), ("default", 7199, 13200, 7199)):
+        prm_t = prm if tag == "default" else prm.replace(n_samples=n_rg, window_s=n_rg / 600e6)
+        _, csa = ref_extract.ati_csa_functions(prm_t.as_globals())
+        x = inputs.large_csa_input(n_az, n_rg, seed)
+        img, rax, cax = csa(x.astype(np.complex128), prm_t.Lambda, prm_t.T_p, prm_t.k_rate, prm_t.FS, prm_t.PRF,
+                            prm_t.V_eff, prm_t.R0, prm_t.t_start_fast)
+        del x
+        assert img.shape == (n_rg, n_az)
+        d = inputs.image_digest(img, 4099)
+        del img
+        for k, v in d.items():
+            out[f"{tag}_{k}"] = v.astype(np.complex64) if k in ("dec", "rows", "cols") else v
+        out[f"{tag}_seed"] = seed
+        out[f"{tag}_rax"] = rax
+        out[f"{tag}_cax"] = cax
+        out[f"{tag}_t_start"] = prm_t.t_start_fast
+        print(tag, "sumsq", d["sumsq"], flush=True)
+    np.savez_compressed(os.path.join(OUT, "csa_large.npz"), **out)
+
+
 if __name__ == "__main__":
     if not ref_extract.reference_available():
         sys.exit("reference tree not found: fixtures can only be regenerated in the build container")
     os.makedirs(OUT, exist_ok=True)
+    if len(sys.argv) > 1 and sys.argv[1] == "large":      # the two full-size CSA frames only (minutes, ~30 GB)
+        golden_csa_large()
+        sys.exit(0)
     golden_vehicle_targets()
     golden_echo()
     golden_csa()

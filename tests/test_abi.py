@@ -29,10 +29,12 @@ def test_header_symbols_are_exported_and_bound():
 
 def test_version_and_struct_layouts():
     lib = _lib.load()
-    assert lib.nis_version() == 1
+    assert lib.nis_version() == 2          # r2: caller-owned K3 workspace, nis_comm_*, nis_peer_native_atomics
     assert C.sizeof(_lib.EchoParams) == 56
     assert C.sizeof(_lib.CsaParams) == 64
     assert C.sizeof(_lib.GmtiResult) == 16
+    # K3 workspace: 16-byte header + one 64-bit status word per 2048-pixel tile
+    assert lib.nis_gmti_workspace_bytes(1) == 24 and lib.nis_gmti_workspace_bytes(4096 * 4096) == 16 + 8 * 8192
 
 
 def test_no_cpu_fallback():
@@ -47,6 +49,55 @@ def test_no_cpu_fallback():
     from nis_sar import api
     with pytest.raises(Exception):
         api.sar_focus_csa(np.zeros((64, 64), np.complex64), 0.03, 20e-6, 2.5e13, 600e6, 6000.0, 7500.0, 5e5, 3.3e-3)
+
+
+def test_collective_entry_points_without_a_device():
+    """nis_comm_* bind NCCL at run time: without a GPU (or without NCCL) they fail with an error class and a message,
+    they never crash the process; argument checks come first."""
+    import torch  # noqa: F401  (loads libnccl.so.2 into the process when torch ships it)
+    lib = _lib.load()
+    assert lib.nis_comm_init(0, 0, None, None) == -1 and "bad argument" in _lib.last_error()
+    assert lib.nis_echo_reduce(None, None, 10, -1, None) == -1
+    assert lib.nis_slc_exchange(None, None, None, 10, None) == -1
+    assert lib.nis_peer_native_atomics(0, 0) == 1
+    assert lib.nis_comm_destroy(None) == 0
+
+
+def test_install_patches_a_namespace():
+    """nis_sar.install(): the wrappers keep the reference's names / positional signatures, inject live radar constants only
+    into entry points that read them, and leave argument-only functions (sar_focus_csa, sar_focus_rda) unwrapped."""
+    import inspect
+    from nis_sar import api
+    ns = {"C": 3e8, "R0": 5e5, "FC": 9.65e9, "BW": 5e8, "T_p": 2e-5, "FS": 6e8}
+    assert api.install(ns) is ns
+    for n in api._ENTRY_POINTS:
+        assert callable(ns[n]) and ns[n].__name__ == n, n
+    sig = inspect.signature(ns["run_bistatic_physics_gpu"])
+    assert list(sig.parameters)[:6] == ["targets", "t_vec", "pos_tx_np", "vel_tx_np", "rx_offset_dist", "vel_target_np"]
+    assert list(inspect.signature(ns["sar_focus_csa"]).parameters)[:9] == [
+        "phist", "center_wavelength_m", "pulse_width_sec", "chirp_rate_hzpsec", "sample_rate_hz", "prf_hz",
+        "platform_speed_mps", "range_ref_m", "t_start_fast"]
+    assert ns["sar_focus_csa"].keywords == {"order": "F"}           # the reference's img.T view semantics (:396)
+    ns2 = api.install({}, names=("sar_focus_rda", "calculate_snr_db"), rda_returns="vehicle", snr_preset="vehicle")
+    assert ns2["sar_focus_rda"].keywords == {"returns": "vehicle"}
+    snr, gain = ns2["calculate_snr_db"](2.8e4, 10.0, 0.03, 3.0e8, 16.384)
+    assert np.isfinite(snr) and gain > 0
+    with pytest.raises(Exception, match="not a replaceable"):
+        api.install({}, names=("save_plot",))
+    # without a GPU the patched functions raise instead of computing on the CPU
+    import torch
+    if not torch.cuda.is_available():
+        with pytest.raises(Exception):
+            ns["run_custom_physics"]([{"position": [0, 0, 0], "rcs": 1.0}], np.zeros(2), np.zeros((2, 3)), 5e-4, 1e-6, 1e10, 3e8)
+
+
+def test_hostio_placement_helpers():
+    from nis_sar import hostio
+    assert hostio._cpulist("0-3,8,10-11\n") == [0, 1, 2, 3, 8, 10, 11]
+    nodes = hostio.numa_nodes()
+    assert isinstance(nodes, dict)
+    info = hostio.bind_rank_to_numa(0, 1, policy="none")
+    assert info["node"] is None
 
 
 def test_size_classes():
