@@ -12,6 +12,17 @@ weak scaling.
 prints ONE JSON line.  `value` is Mpixel/s of focused image over all ranks with inputs resident in
 HBM; `e2e` is the same step through the drop-in Python API with host buffers (scene arrays copied
 host->device, the complex128 focused image copied device->host, every step).
+
+At every N the same run also measures the three multi-GPU workloads BASELINE.json names -- nested under
+`config.multi_gpu` so that they survive in the driver's record:
+  config 4  VideoSAR: 64 two-channel 4096 x 4096 frames (CSA x2 + fused DPCA/ATI), round robin over ranks  -> frames/s
+            (strong scaling) and the per-GPU fraction of the HBM roofline (the north_star target);
+  config 3  dense vehicle scene: 1e5 scatterers x 32768 pulses x 2048 samples sharded by scatterer, partial echoes
+            reduced by NCCL (torch.distributed and the library's own nis_echo_reduce) or inside the synthesis kernel
+            (system-scope RED.ADD into the owner's HBM over NVLink);
+  config 5  HRWS: one 4096 x 4096 receive channel per rank, pair (k, k+1) formed after an NCCL ring shift
+            (isend/irecv, nis_slc_exchange) or by the DPCA/ATI kernel reading the neighbour's image over NVLink;
+each with an in-run equality check against a one-rank recomputation.
 """
 from __future__ import annotations
 
@@ -57,6 +68,17 @@ def config_dict(args, extra=None):
 
 
 # ------------------------------------------------------------------------------------ CPU arms
+# The reference's CPU path for this step is two single-threaded numpy functions (run_physics_engine,
+# sar_focus_csa).  A full 8192 x 8192 step costs ~450 s of echo synthesis + ~40 s (21 GB) of CSA per core, so the
+# CPU arms time a BOUNDED SAMPLE and extrapolate linearly, and say so: `kind` = "port, extrapolated".
+#   echo: `pulses` whole pulses of the 8192-pulse aperture (cost is exactly linear in pulses);
+#   CSA : one full 4096 x 4096 frame (a quarter of the pixels of the bench frame; the reference's cost per pixel grows
+#         ~ log N and with cache misses, so this sample FLATTERS the CPU by an estimated 10-20 %).
+REF_ECHO_PULSES = 64
+REF_CSA_N = 4096
+REF_CSA_GB_PER_PROC = 7.0          # peak RSS of the numpy CSA at 4096^2 (complex128 temporaries), with margin
+
+
 def _cpu_echo_rate(sc, pulses):
     """Oracle (numpy port of run_physics_engine) on a pulse subset: scatterer-samples per second."""
     from oracle import sar_oracle as orc
@@ -88,9 +110,20 @@ def _cpu_worker(args):
     return e_rate, c_rate, e_dt + c_dt
 
 
-def cpu_step_throughput(procs, pulses=4, n_csa=1024):
-    """Mpixel/s of the step (echo + CSA) on `procs` host processes, each running the single-threaded
-    numpy port on its own bounded sample.  Per-pixel CPU cost = scatterers / echo_rate + 1 / csa_rate."""
+def _cpu_procs():
+    """Host processes the CPU arm may use: every core it is allowed to run on, capped by memory (7 GB per numpy CSA)."""
+    cores = max(1, len(os.sched_getaffinity(0)))
+    try:
+        avail_gb = os.sysconf("SC_AVPHYS_PAGES") * os.sysconf("SC_PAGE_SIZE") / 2 ** 30
+    except (ValueError, OSError):
+        avail_gb = 64.0
+    return max(1, min(cores, int(avail_gb * 0.8 / REF_CSA_GB_PER_PROC))), cores
+
+
+def cpu_step_throughput(procs, pulses=REF_ECHO_PULSES, n_csa=REF_CSA_N):
+    """Modelled Mpixel/s of the full step (echo + CSA) on `procs` host processes, each running the single-threaded numpy
+    port on its own bounded sample.  Per-pixel CPU cost = scatterers / echo_rate + 1 / csa_rate; a process's modelled
+    step time = 8192 x 8192 x that cost."""
     import multiprocessing as mp
     if procs <= 1:
         res = [_cpu_worker((0, pulses, n_csa))]
@@ -104,30 +137,338 @@ def cpu_step_throughput(procs, pulses=4, n_csa=1024):
 
 
 def run_reference_arm(args):
+    """--impl reference: the reference's CPU implementation of the step (numpy port, the reference itself being Python
+    that cannot be imported -- DESIGN.md section 1) on all the host cores memory allows.  Every step times a bounded
+    sample (64 of 8192 pulses + one 4096^2 CSA per process) and converts it into the MODELLED time of one full step;
+    the line says so (`kind`, `sample`, `modelled_ms_per_step`) and also carries the wall time actually spent."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    cores = max(1, len(os.sched_getaffinity(0)))
+    procs, cores = _cpu_procs()
     os.environ.setdefault("OMP_NUM_THREADS", "1")
-    vals = []
-    sample = None
-    for i in range(args.warmup + args.steps):
+    budget_s = float(os.environ.get("NIS_REF_BUDGET_S", "170"))
+    vals, sample, t_all0 = [], None, time.perf_counter()
+    n_total = args.warmup + args.steps
+    for i in range(n_total):
         t0 = time.perf_counter()
-        v, e_rate, c_rate, dt = cpu_step_throughput(cores, pulses=2, n_csa=1024)
-        if i >= args.warmup:
-            vals.append((v, time.perf_counter() - t0))
-        sample = (f"{cores} processes, each: numpy port of run_physics_engine on 2 of {N_AZ} pulses x {N_RG} samples x "
-                  f"{GRID_SIDE * GRID_SIDE} scatterers ({e_rate:.3g} scatterer-samples/s) + sar_focus_csa port on a "
-                  f"1024x1024 frame ({c_rate / 1e6:.3g} Mpixel/s); per-pixel costs added")
+        v, e_rate, c_rate, dt = cpu_step_throughput(procs)
+        wall = time.perf_counter() - t0
+        if i >= args.warmup or i == n_total - 1:
+            vals.append((v, wall))
+        sample = (f"{procs} processes ({cores} cores visible; 7 GB per process), each: numpy port of run_physics_engine on "
+                  f"{REF_ECHO_PULSES} of {N_AZ} pulses x {N_RG} samples x {GRID_SIDE * GRID_SIDE} scatterers ({e_rate:.3g} "
+                  f"scatterer-samples/s) + sar_focus_csa port on ONE {REF_CSA_N}x{REF_CSA_N} frame ({c_rate / 1e6:.3g} Mpixel/s); "
+                  f"per-pixel costs added and scaled to the {N_AZ}x{N_RG} step (extrapolation, not a run of the full step)")
+        # keep the whole arm inside a few minutes: stop early when the next sample would not fit (steps_run says how many ran)
+        if time.perf_counter() - t_all0 + wall > budget_s and len(vals) >= 1:
+            break
     v = float(np.mean([x for x, _ in vals]))
+    pixels = float(N_AZ) * N_RG
+    modelled_ms = 1e3 * pixels / (v / procs * 1e6)          # one process, one full frame
     line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": 1e3 * float(np.mean([d for _, d in vals])),
+            "steps_run": len(vals), "warmup": args.warmup,
+            "ms_per_step": modelled_ms / procs,              # modelled: `procs` frames in flight, one finishing every ...
+            "modelled_ms_per_step_one_core": modelled_ms,
+            "sample_wall_ms": 1e3 * float(np.mean([d for _, d in vals])),
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": config_dict(args),
-            "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "cpu_baseline": {"value": v, "unit": UNIT, "cores": procs, "kind": "port, extrapolated", "sample": sample},
             "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------- multi-GPU workloads
+def _ev_pair():
+    import torch
+    return torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+
+
+def _max_ms(ms, device, world):
+    import torch
+    import torch.distributed as dist
+    t = torch.tensor([ms], dtype=torch.float64, device=device)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def _all_true(flag, device, world):
+    import torch
+    import torch.distributed as dist
+    t = torch.tensor([1 if flag else 0], device=device)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MIN)
+    return bool(t.item())
+
+
+def bench_config4_videosar(device, rank, world, peak_gbs, n_frames=64, n=4096, stride=8):
+    """BASELINE.json configs[3]: a VideoSAR sub-aperture sequence -- `n_frames` two-channel n x n frames cut from one long
+    seeded collection with the stride pattern of sar_batch_sim.py:303-310, frame f = pulses [stride f, stride f + n] of each
+    receive channel -- focused frame-parallel (round robin over ranks, no data-path collective): per frame CSA of rx1[1:]
+    and rx2[:-1] (the DPCA pulse shift, sar_ati_dcpa_sim_csa.py:402-403) on two streams + the fused DPCA/ATI/detection
+    kernel with every product.  STRONG scaling: the sequence is fixed, frames/s = n_frames / max-over-ranks time.
+    Eager launches (no CUDA graph).  The 16-byte detection record of every frame is gathered and rank 0 recomputes a
+    frame another rank owned."""
+    import torch
+    import torch.distributed as dist
+    from nis_sar import device as dev, dist as nd, params
+    prm = params.spaceborne_preset().replace(n_samples=n, window_s=n / 600e6)
+    mk = lambda: dev.CsaPlan(n, n, lam=prm.Lambda, kr=prm.k_rate, fs=prm.FS, prf=prm.PRF, vr=prm.V_eff, r_ref=prm.R0,
+                             t_start=prm.t_start_fast, device=device)
+    pa, pb = mk(), mk()
+    rows = n + 1 + stride * (n_frames - 1)
+    gen = torch.Generator(device=device).manual_seed(404)       # same generator, same GPU model: identical on every rank
+    coll = [torch.view_as_complex(torch.randn((rows, n, 2), generator=gen, device=device)) for _ in range(2)]
+    coll[0][rows // 2, n // 3] += 3000.0                         # a bright scatterer so that the 5 % mask is selective
+    s1 = torch.empty((n, n), dtype=torch.complex64, device=device)
+    s2 = torch.empty_like(s1)
+    mx = torch.zeros(1, dtype=torch.float64, device=device)
+    st_a, st_b = torch.cuda.Stream(device), torch.cuda.Stream(device)
+    records = torch.zeros((n_frames, 4), dtype=torch.int32, device=device)
+
+    def frame(f):
+        cur = torch.cuda.current_stream(device)
+        st_a.wait_stream(cur)
+        st_b.wait_stream(cur)
+        with torch.cuda.stream(st_a):
+            pa.focus(coll[0][stride * f + 1: stride * f + 1 + n], out=s1, max_sq=mx)
+        with torch.cuda.stream(st_b):
+            pb.focus(coll[1][stride * f: stride * f + n], out=s2)
+        cur.wait_stream(st_a)
+        cur.wait_stream(st_b)
+        out = dev.gmti_fused(s1, s2, max_sq=mx, lazy=True)
+        records[f].copy_(out["result_dev"].view(torch.int32))
+        return out
+    mine = list(nd.frame_indices(n_frames))
+    for f in mine[:3]:
+        frame(f)
+    records.zero_()
+    torch.cuda.synchronize(device)
+    if world > 1:
+        dist.barrier()
+    e0, e1 = _ev_pair()
+    cur = torch.cuda.current_stream(device)
+    e0.record(cur)
+    for f in mine:
+        frame(f)
+    e1.record(cur)
+    torch.cuda.synchronize(device)
+    my_ms = e0.elapsed_time(e1)
+    ms = _max_ms(my_ms, device, world)
+    if world > 1:
+        dist.all_reduce(records)                                 # every frame was written by exactly one rank
+    got = records.cpu().numpy().copy()
+    equal = None
+    if rank == 0:
+        f_chk = 1 if world > 1 else n_frames - 1                 # owned by rank 1 when there is one
+        frame(f_chk)
+        torch.cuda.synchronize(device)
+        equal = bool((records[f_chk].cpu().numpy() == got[f_chk]).all())
+    fr_bytes = (2 * CSA_ALGO_BYTES_PER_PIXEL + 49.0) * n * n
+    per_gpu_ms = my_ms / max(len(mine), 1)
+    pa.close()
+    pb.close()
+    del coll, s1, s2
+    torch.cuda.empty_cache()
+    return {"workload": f"{n_frames} two-channel {n}x{n} frames (sub-apertures at stride {stride} of one seeded collection): CSA x2 "
+                        f"+ fused DPCA/ATI/threshold/compaction, all products; round robin over {world} rank(s); eager launches",
+            "frames": n_frames, "ms_total": ms, "frames_per_s": n_frames / (ms * 1e-3), "scaling": "strong",
+            "ms_per_frame_per_gpu": per_gpu_ms, "algorithmic_bytes_per_frame": fr_bytes,
+            "per_gpu_achieved_GBps": fr_bytes / (per_gpu_ms * 1e-3) / 1e9,
+            "per_gpu_frac_of_hbm_peak": fr_bytes / (per_gpu_ms * 1e-3) / 1e9 / peak_gbs,
+            "collective": "none in the data path (16-byte detection records all-reduced after the timed region)",
+            "detections_frame0": int(got[0][0]), "equals_one_rank_recompute": equal,
+            "note": "4096^2 x 8 B = 134 MB per array vs 126 MB of L2: intermediate passes partly hit L2 (ncu: 227 MB of DRAM "
+                    "traffic for a 268 MB algorithmic pass), so the fraction is against HBM peak, not a pure-DRAM figure"}
+
+
+def bench_config3_scatterer_shards(device, rank, world, num_scatterers=100000, num_pulses=32768):
+    """BASELINE.json configs[2]: sar_vehicle_sim.py geometry (fs 360 MHz, 2048 samples, 32768 pulses: :43, :85-89) with
+    1e5 scatterers tiled from vehicle_targets.py, sharded BY SCATTERER over the ranks; the partial [P, S] echoes (512 MB)
+    meet in one of three ways: torch.distributed all-reduce (NCCL), the library's nis_echo_reduce (NCCL, C ABI), or the
+    synthesis kernel's own epilogue adding each pulse block into its owner's HBM with system-scope RED.ADD over NVLink
+    (reduce-scatter semantics, no partial echo materialised).  Checked against a one-rank recomputation of 16 pulses."""
+    import torch
+    import torch.distributed as dist
+    from nis_sar import device as dev, dist as nd, scenes
+    sc = scenes.vehicle_scene(seed=0, num_pulses=num_pulses, num_scatterers=num_scatterers)
+    prm = sc["prm"]
+    S = 2048
+    kw = dict(c=prm.C, fc=prm.FC, k_rate=prm.k_rate, t_p=prm.T_p, t_start=(2 * prm.R0 / prm.C) - (S / 360e6) / 2,
+              fs=360e6, n_samples=S, device=device)
+    zero3 = np.zeros(3)
+    part = torch.zeros((num_pulses, S), dtype=torch.complex64, device=device)
+
+    def shard(a, b):
+        return dev.echo_accumulate(sc["pos"][a:b], zero3, sc["rcs"][a:b], sc["pos_sat"], None, sc["t_vec"], out=part, **kw)
+
+    def shard_into(a, b, p0, p1, dst):
+        dev.echo_accumulate(sc["pos"][a:b], zero3, sc["rcs"][a:b], sc["pos_sat"], None, sc["t_vec"], out=dst,
+                            pulse_range=(p0, p1), accumulate="atomic", **kw)
+    res = {"workload": f"{num_scatterers} scatterers x {num_pulses} pulses x {S} samples (sar_vehicle_sim.py geometry), sharded by "
+                       f"scatterer over {world} rank(s); partial echoes 512 MB per rank",
+           "scatterer_samples": float(num_scatterers) * num_pulses * S}
+    comm = nd.CComm(device=device) if world > 1 else None
+    t0, t1 = nd.block_range(num_scatterers, rank, world)
+    e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+    cur = torch.cuda.current_stream(device)
+    routes = [("nccl_torch", None)] + ([("nccl_c_abi", comm)] if comm is not None else [])
+    ref_block = None
+    for name, cm in routes:
+        for rep in range(2):                                      # first pass warms the communicator
+            torch.cuda.synchronize(device)
+            if world > 1:
+                dist.barrier()
+            e0.record(cur)
+            shard(t0, t1)
+            e1.record(cur)
+            if world > 1:
+                if cm is not None:
+                    cm.echo_reduce(part)
+                else:
+                    dist.all_reduce(torch.view_as_real(part))
+            e2.record(cur)
+            torch.cuda.synchronize(device)
+        tot, red = _max_ms(e0.elapsed_time(e2), device, world), _max_ms(e1.elapsed_time(e2), device, world)
+        res[name] = {"ms_total": tot, "ms_synthesis": tot - red, "ms_reduce": red,
+                     "g_scatterer_samples_per_s": res["scatterer_samples"] / (tot * 1e-3) / 1e9}
+        if ref_block is None:
+            p0, p1 = nd.block_range(num_pulses, rank, world)
+            ref_block = part[p0:p1].clone()
+    res["nccl_routes_bit_equal"] = None
+    if comm is not None:
+        res["nccl_routes_bit_equal"] = _all_true(torch.equal(part[p0:p1], ref_block), device, world)
+    # one-rank recomputation of 16 pulses of this rank's own block, all scatterers
+    chk = torch.zeros((num_pulses, S), dtype=torch.complex64, device=device) if world > 1 else None
+    p0, p1 = nd.block_range(num_pulses, rank, world)
+    rows = slice(p0, min(p0 + 16, p1))
+    if world > 1:
+        dev.echo_accumulate(sc["pos"], zero3, sc["rcs"], sc["pos_sat"], None, sc["t_vec"], out=chk,
+                            pulse_range=(rows.start, rows.stop), **kw)
+        err = float(torch.linalg.vector_norm(ref_block[: rows.stop - rows.start] - chk[rows]) /
+                    torch.linalg.vector_norm(chk[rows]))
+        res["rel_l2_vs_one_rank_recompute"] = _max_ms(err, device, world)
+        res["equals_one_rank_recompute"] = res["rel_l2_vs_one_rank_recompute"] < 1e-5     # fp32 summation order differs
+        del chk
+    else:
+        res["equals_one_rank_recompute"] = True
+    # fused route: RED.ADD into the owner's rows over NVLink
+    try:
+        shared = nd.SharedBuffer((num_pulses, S), torch.complex64, device=device)
+        res["peer_native_atomics"] = bool(shared.native_atomics)
+        for rep in range(2):
+            torch.cuda.synchronize(device)
+            if world > 1:
+                dist.barrier()
+            e0.record(cur)
+            own = nd.echo_scatterer_shards_p2p(shard_into, num_scatterers, shared)
+            e1.record(cur)
+            torch.cuda.synchronize(device)
+        tot = _max_ms(e0.elapsed_time(e1), device, world)
+        blk = shared.local[own[0]:own[1]]
+        err = float(torch.linalg.vector_norm(blk - ref_block) / torch.linalg.vector_norm(ref_block))
+        res["fused_red_add"] = {"ms_total": tot, "g_scatterer_samples_per_s": res["scatterer_samples"] / (tot * 1e-3) / 1e9,
+                                "rel_l2_vs_nccl_route": _max_ms(err, device, world),
+                                "what": "every rank synthesises its scatterers for all pulse blocks; the kernel epilogue adds "
+                                        "block b into rank b's HBM (RED.E.ADD.F32.SYS over NVLink); barriers included"}
+        shared.close()
+    except Exception as e:                                       # no peer path on this box: the NCCL routes stand
+        res["fused_red_add"] = {"error": str(e)[:200]}
+    if comm is not None:
+        comm.close()
+    best = min((v["ms_total"], k) for k, v in res.items() if isinstance(v, dict) and "ms_total" in v)
+    res["fastest_route"] = best[1]
+    r = res.get("nccl_torch", {})
+    res["limiter"] = ("synthesis (FP32 pipe): the reduce is %.1f %% of the step" % (100 * r["ms_reduce"] / r["ms_total"])) \
+        if world > 1 else "synthesis (FP32 pipe); no exchange at 1 rank"
+    del part, ref_block
+    torch.cuda.empty_cache()
+    return res
+
+
+def bench_config5_hrws(device, rank, world, n=4096):
+    """BASELINE.json configs[4]: HRWS -- one n x n receive channel per rank (seeded, so any rank can regenerate any
+    channel), focused where it lives; DPCA/ATI pair (k, k+1) is formed on rank k from its own image and the neighbour's,
+    which arrives by an NCCL ring shift (torch isend/irecv; the library's nis_slc_exchange) or is read in place over NVLink
+    by the products kernel (peer-mapped buffer).  At one rank both channels are local (no exchange)."""
+    import torch
+    import torch.distributed as dist
+    from nis_sar import device as dev, dist as nd, params
+    prm = params.spaceborne_preset().replace(n_samples=n, window_s=n / 600e6)
+    plan = dev.CsaPlan(n, n, lam=prm.Lambda, kr=prm.k_rate, fs=prm.FS, prf=prm.PRF, vr=prm.V_eff, r_ref=prm.R0,
+                       t_start=prm.t_start_fast, device=device)
+
+    def channel(k):
+        g = torch.Generator(device=device).manual_seed(9000 + k)
+        x = torch.view_as_complex(torch.randn((n, n, 2), generator=g, device=device))
+        x[n // 2, n // 3] += 3000.0
+        return plan.focus(x).clone()
+    mine = channel(rank)
+    prod = lambda a, b: dev.gmti_fused(a, b, lazy=True)          # every product, no host read-back
+    res = {"workload": f"{max(world, 2)} receive channels of {n}x{n}, one per rank; {max(world - 1, 1)} adjacent DPCA/ATI pair(s), "
+                       f"all products + detection list", "pairs": max(world - 1, 1)}
+    e0, e1 = _ev_pair()
+    cur = torch.cuda.current_stream(device)
+
+    def timed(fn, reps=5):
+        out = fn()
+        torch.cuda.synchronize(device)
+        if world > 1:
+            dist.barrier()
+        e0.record(cur)
+        for _ in range(reps):
+            out = fn()
+        e1.record(cur)
+        torch.cuda.synchronize(device)
+        return _max_ms(e0.elapsed_time(e1) / reps, device, world), out
+    if world == 1:
+        other = channel(1)
+        ms, out = timed(lambda: prod(mine, other))
+        res["local_pair"] = {"ms": ms}
+        res["equals_one_rank_recompute"] = True
+        res["limiter"] = "none: both channels on one GPU"
+        plan.close()
+        return res
+    comm = nd.CComm(device=device)
+    keep = {}
+
+    def via_c():
+        nxt = comm.slc_exchange(mine)
+        return None if nxt is None else prod(mine, nxt)
+    for name, fn in (("nccl_torch_isend_irecv", lambda: nd.pair_products(mine, prod)), ("nccl_c_abi_slc_exchange", via_c)):
+        ms, out = timed(fn)
+        res[name] = {"ms_per_pair_step": ms}
+        if out is not None:
+            keep[name] = (out["result_dev"].clone(), out["det_idx_raw"][:4096].clone())
+    try:
+        sh = nd.SharedBuffer((n, n), torch.complex64, device=device)
+        sh.local.copy_(mine)
+        ms, out = timed(lambda: nd.pair_products_p2p(sh, prod))
+        res["peer_read_over_nvlink"] = {"ms_per_pair_step": ms,
+                                        "what": "k_gmti_fused loads slc2 (8 of its 16 input bytes per pixel) from the neighbour's HBM"}
+        if out is not None:
+            keep["peer_read_over_nvlink"] = (out["result_dev"].clone(), out["det_idx_raw"][:4096].clone())
+        sh.close()
+    except Exception as e:
+        res["peer_read_over_nvlink"] = {"error": str(e)[:200]}
+    ok = True
+    if rank < world - 1:
+        ref = prod(mine, channel(rank + 1))                      # one-rank recomputation of this rank's pair
+        torch.cuda.synchronize(device)
+        for name, (rec, idx) in keep.items():
+            ok = ok and bool(torch.equal(rec, ref["result_dev"])) and bool(torch.equal(idx, ref["det_idx_raw"][:4096]))
+        res["detections_pair0"] = int(ref["result_dev"].view(torch.int32)[0].item()) if rank == 0 else None
+    res["equals_one_rank_recompute"] = _all_true(ok, device, world)
+    a = res.get("peer_read_over_nvlink", {}).get("ms_per_pair_step")
+    b = res["nccl_torch_isend_irecv"]["ms_per_pair_step"]
+    res["limiter"] = (f"the ring shift of one 134 MB image (NCCL send/recv: {b:.2f} ms per step) -- removed by the in-place peer read "
+                      f"({a:.2f} ms)") if a else f"the ring shift of one 134 MB image ({b:.2f} ms per step)"
+    comm.close()
+    plan.close()
+    del mine
+    torch.cuda.empty_cache()
+    return res
 
 
 # ------------------------------------------------------------------------------------- GPU arm
@@ -191,7 +532,12 @@ def run_gpu_arm(args):
         raise SystemExit("bench.py: no CUDA device -- the product path has no CPU fallback")
     torch.cuda.set_device(local)
     device = torch.device("cuda", local)
+    numa_info = {"policy": "none"}
     if world > 1:
+        # one process per GPU on a multi-socket host: keep each rank (and the pinned result buffers it allocates) on one
+        # NUMA node -- the GPU's own, or spread over the nodes when the platform reports every GPU on the same one
+        from nis_sar import hostio
+        numa_info = hostio.bind_rank_to_numa(local, world, policy=os.environ.get("NIS_NUMA_POLICY", "auto"))
         dist.init_process_group("nccl", device_id=device)
 
     sc = workload()
@@ -300,71 +646,29 @@ def run_gpu_arm(args):
     d2h = int(img.nbytes)
     del img
 
-    # ------------------------------------------------ north-star frame: 4096 x 4096 two-channel CSA + DPCA/ATI
-    ati = None
-    if world == 1:
-        n4 = 4096
-        plan.set_profiling(False)
-        del raw, slc
-        dev._plan_cache.clear()
-        plan.close()
-        torch.cuda.empty_cache()
-        # one plan (workspace) per receive channel: the two focus calls are independent until the DPCA/ATI pairing, so they
-        # run on two streams (their HBM-bound azimuth kernels overlap the other channel's compute-bound range kernel)
-        mkplan = lambda: dev.CsaPlan(n4, n4, lam=prm.Lambda, kr=prm.k_rate, fs=prm.FS, prf=prm.PRF, vr=prm.V_eff,
-                                     r_ref=prm.R0, t_start=prm.t_start_fast, device=device)
-        p4, p4b = mkplan(), mkplan()
-        gen = torch.Generator(device=device).manual_seed(5)
-        ch = [torch.view_as_complex(torch.randn((n4 + 1, n4, 2), generator=gen, device=device)) for _ in range(2)]
-        ch[0][n4 // 2, n4 // 3] += 3000.0          # a bright scatterer so that the 5 % mask is selective
-        s1 = torch.empty((n4, n4), dtype=torch.complex64, device=device)
-        s2 = torch.empty_like(s1)
-        mx = torch.zeros(1, dtype=torch.float64, device=device)
-        st_a, st_b = torch.cuda.Stream(device), torch.cuda.Stream(device)
-
-        def frame():
-            cur = torch.cuda.current_stream(device)
-            st_a.wait_stream(cur)
-            st_b.wait_stream(cur)
-            with torch.cuda.stream(st_a):
-                p4.focus(ch[0][1:], out=s1, max_sq=mx)    # DPCA pulse shift: rx1[1:], rx2[:-1] (:402-403)
-            with torch.cuda.stream(st_b):
-                p4b.focus(ch[1][:-1], out=s2)
-            cur.wait_stream(st_a)
-            cur.wait_stream(st_b)
-            return dev.gmti_fused(s1, s2, max_sq=mx, lazy=True)
-        for _ in range(5):
-            frame()
-        torch.cuda.synchronize(device)
-        # the frame is a dozen short kernels on two streams: replay it from a CUDA graph so that host launch latency is not measured
-        graph_note = "cuda graph replay"
+    # ------------------------------------------------ the three multi-GPU workloads of BASELINE.json, at this N
+    plan.set_profiling(False)
+    del raw, slc
+    dev._plan_cache.clear()
+    plan.close()
+    torch.cuda.empty_cache()
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.isfile(peaks_path):
+        peak_gbs, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    else:
+        peak_gbs, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+    multi = {}
+    for key, fn in (("config4_videosar_frames", lambda: bench_config4_videosar(device, rank, world, peak_gbs)),
+                    ("config3_scatterer_shards", lambda: bench_config3_scatterer_shards(device, rank, world)),
+                    ("config5_hrws_channel_pairs", lambda: bench_config5_hrws(device, rank, world))):
+        if os.environ.get("NIS_BENCH_SKIP_MULTI"):
+            break
         try:
-            gph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(gph):
-                out4 = frame()
-            run_frame = gph.replay
-        except Exception as e:   # capture not possible: time eager launches and say so
-            graph_note = f"eager launches (graph capture failed: {str(e)[:80]})"
-            run_frame = frame
-        for _ in range(3):
-            run_frame()
-        torch.cuda.synchronize(device)
-        ea, eb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        nfr = 50
-        cur = torch.cuda.current_stream(device)
-        ea.record(cur)
-        for _ in range(nfr):
-            run_frame()
-        eb.record(cur)
-        torch.cuda.synchronize(device)
-        fr_ms = ea.elapsed_time(eb) / nfr
-        fr_bytes = (2 * CSA_ALGO_BYTES_PER_PIXEL + 49.0) * n4 * n4
-        ati = {"workload": "4096x4096 two-channel frame: CSA x2 (one stream per channel) + fused DPCA/ATI/threshold/compaction (all products)",
-               "launch": graph_note,
-               "ms_per_frame": fr_ms, "frames_per_s": 1e3 / fr_ms, "algorithmic_bytes_per_frame": fr_bytes,
-               "achieved_GBps": fr_bytes / (fr_ms * 1e-3) / 1e9}
-        p4.close()
-        p4b.close()
+            multi[key] = fn()
+        except Exception as e:       # a failed side workload must not take the headline line with it
+            multi[key] = {"error": f"{type(e).__name__}: {str(e)[:300]}"}
+            torch.cuda.synchronize(device)
+    ati = multi.get("config4_videosar_frames")
 
     # ------------------------------------------------ the other BASELINE.json configs, one line each (single GPU)
     other = None
@@ -638,11 +942,6 @@ def run_gpu_arm(args):
     hi = np.searchsorted(tf, tau.ravel() + prm.T_p, side="right")
     in_support = float(np.mean((hi - lo) / N_RG))
     value = world * pixels / (ms_per_step * 1e-3) / 1e6
-    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
-    if os.path.isfile(peaks_path):
-        peak_gbs, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
-    else:
-        peak_gbs, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
     dom = max(stage, key=stage.get)
     dom_gbs = STAGE_ALGO_BYTES_PER_PIXEL * pixels / (stage[dom] * 1e-3) / 1e9
     csa_gbs = CSA_ALGO_BYTES_PER_PIXEL * pixels / (csa_ms * 1e-3) / 1e9
@@ -651,7 +950,7 @@ def run_gpu_arm(args):
     if os.path.isfile(tpath):
         traffic = json.load(open(tpath)).get(dom)
 
-    cpu_v, e_rate, c_rate, cpu_dt = cpu_step_throughput(1, pulses=128, n_csa=4096) if world == 1 else (None, 0, 0, 0)
+    cpu_v, e_rate, c_rate, cpu_dt = cpu_step_throughput(1) if world == 1 else (None, 0, 0, 0)
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -663,7 +962,11 @@ def run_gpu_arm(args):
                         "complex128 numpy image on the host"},
         "gpu_launches": int(launches),
         "roofline": {"bound": "hbm", "kernel": f"csa:{dom}", "achieved": dom_gbs, "peak": peak_gbs, "unit": "GB/s",
-                     "frac": dom_gbs / peak_gbs, "traffic": traffic, "peak_source": peak_src,
+                     "frac": dom_gbs / peak_gbs, "traffic": traffic,
+                     "traffic_source": "ncu --set full dram__bytes_read.sum + dram__bytes_write.sum of this kernel, one static capture "
+                                       "(profiles/traffic.json; DRAM bytes cannot be read without the profiler, and a number taken "
+                                       "under ncu is never a bench value)",
+                     "peak_source": peak_src,
                      "frac_of_nameplate_8TBps": dom_gbs / 8000.0,
                      "algorithmic_bytes_per_launch": STAGE_ALGO_BYTES_PER_PIXEL * pixels,
                      "launch_ms": stage[dom],
@@ -678,27 +981,36 @@ def run_gpu_arm(args):
         "csa": {"ms": csa_ms, "mpixels_per_s": pixels / (csa_ms * 1e-3) / 1e6},
         "clocks": clocks,
     }
-    if ati is not None:
-        ati["frac_of_hbm_peak"] = ati["achieved_GBps"] / peak_gbs
-        line["ati_frame"] = ati
+    # Everything beyond the contract's keys is nested inside `config` / `roofline`: the driver's record keeps those dicts whole
+    # and drops unknown top-level keys.
+    line["config"]["multi_gpu"] = multi
+    line["config"]["numa"] = numa_info
+    if ati is not None and "error" not in ati:
+        line["roofline"]["north_star_frame"] = {
+            "what": "4096x4096 two-channel frame (CSA x2 + fused DPCA/ATI, all products) as run in config.multi_gpu.config4_videosar_frames",
+            "ms_per_frame_per_gpu": ati["ms_per_frame_per_gpu"], "achieved": ati["per_gpu_achieved_GBps"],
+            "frac": ati["per_gpu_frac_of_hbm_peak"], "target_frac": 0.40, "launch": "eager"}
     if gmti_line is not None:
         gmti_line["frac_of_hbm_peak"] = gmti_line["achieved_GBps"] / peak_gbs
-        line["gmti_stage"] = gmti_line
+        line["roofline"]["gmti_stage"] = gmti_line
+    extra = {}
     if other:
-        line["other_configs"] = other
+        extra.update(other)
     if ref_gpu is not None:
-        line["reference_gpu_path"] = ref_gpu
+        extra["reference_gpu_path"] = ref_gpu
     if video is not None:
-        line["videosar_frame"] = video
+        extra["videosar_frame"] = video
     if rda is not None:
         rda["frac_of_hbm_peak"] = rda["achieved_GBps"] / peak_gbs
-        line["rda_frame"] = rda
+        extra["rda_frame"] = rda
+    if extra:
+        line["config"]["other_workloads"] = extra
     if cpu_v is not None:
         line["cpu_baseline"] = {
-            "value": cpu_v, "unit": UNIT, "cores": 1, "kind": "port",
-            "sample": f"numpy port of run_physics_engine on 128 of {N_AZ} pulses ({e_rate:.3g} scatterer-samples/s) + "
-                      f"sar_focus_csa port on a 4096x4096 frame ({c_rate / 1e6:.3g} Mpixel/s); per-pixel costs added; "
-                      f"{cpu_dt:.1f} s of CPU work"}
+            "value": cpu_v, "unit": UNIT, "cores": 1, "kind": "port, extrapolated",
+            "sample": f"numpy port of run_physics_engine on {REF_ECHO_PULSES} of {N_AZ} pulses ({e_rate:.3g} scatterer-samples/s) + "
+                      f"sar_focus_csa port on ONE {REF_CSA_N}x{REF_CSA_N} frame ({c_rate / 1e6:.3g} Mpixel/s); per-pixel costs "
+                      f"added and scaled to the {N_AZ}x{N_RG} step (a model of the full step, {cpu_dt:.1f} s of CPU work)"}
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

@@ -83,24 +83,22 @@ def numa_nodes() -> dict[int, list[int]]:
 
 def gpu_numa_node(device_index: int) -> int:
     """NUMA node of a CUDA device from its PCI address (-1: unknown)."""
+    bdf = None
     try:
-        bdf = torch.cuda.get_device_properties(device_index).pci_bus_id  # torch >= 2.5
+        pr = torch.cuda.get_device_properties(device_index)
+        bdf = f"{int(pr.pci_domain_id):04x}:{int(pr.pci_bus_id):02x}:{int(pr.pci_device_id):02x}.0"
     except Exception:
-        bdf = None
-    if bdf is None:
         try:
             import pynvml
             pynvml.nvmlInit()
             bdf = pynvml.nvmlDeviceGetPciInfo(pynvml.nvmlDeviceGetHandleByIndex(device_index)).busId
             if isinstance(bdf, bytes):
                 bdf = bdf.decode()
+            bdf = str(bdf).lower()
+            if len(bdf.split(":")[0]) == 8:          # NVML prints an 8-digit domain; sysfs uses 4
+                bdf = bdf[4:]
         except Exception:
             return -1
-    if isinstance(bdf, int):
-        return -1
-    bdf = str(bdf).lower()
-    if len(bdf.split(":")[0]) == 8:          # NVML prints an 8-digit domain; sysfs uses 4
-        bdf = bdf[4:]
     try:
         with open(f"/sys/bus/pci/devices/{bdf}/numa_node") as fh:
             return int(fh.read().strip())

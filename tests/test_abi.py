@@ -182,8 +182,9 @@ def test_bench_reference_arm_prints_the_contract_line():
     import subprocess
     import sys
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, NIS_REF_BUDGET_S="20")
     out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"],
-                         capture_output=True, text=True, timeout=600, cwd=root)
+                         capture_output=True, text=True, timeout=600, cwd=root, env=env)
     assert out.returncode == 0, out.stderr[-500:]
     lines = [ln for ln in out.stdout.strip().splitlines() if ln.startswith("{")]
     assert len(lines) == 1
@@ -193,4 +194,6 @@ def test_bench_reference_arm_prints_the_contract_line():
         assert k in d, k
     assert d["impl"] == "reference" and d["metric"] == "csa_focused_mpixels_per_s" and d["unit"] == "Mpixel/s"
     assert d["value"] > 0 and d["e2e"]["value"] == d["value"] and d["e2e"]["h2d_bytes_per_step"] == 0
-    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and "workload" in d["config"]
+    assert d["cpu_baseline"]["kind"].startswith("port") and "extrapolated" in d["cpu_baseline"]["kind"]
+    assert d["cpu_baseline"]["cores"] >= 1 and "workload" in d["config"] and d["steps_run"] == 1
+    assert "4096x4096" in d["cpu_baseline"]["sample"] and "64 of 8192 pulses" in d["cpu_baseline"]["sample"]
