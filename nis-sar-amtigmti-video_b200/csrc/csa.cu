@@ -138,11 +138,18 @@ __global__ void __launch_bounds__(256) k_az_outer_inv_mag(const float2* __restri
 // [A2 x W] box of tile i+1 is already in flight into the other shared buffer (cp.async.bulk.tensor.2d, completion
 // on an mbarrier).  The tile buffer doubles as the exchange buffer of the transform, so global loads never stall a
 // warp and stores leave straight from registers.
-template <class P, bool INV, int W>
+// PH: the chirp-scaling multiply Phi1 (:272-274) rides on the forward transform's store and the azimuth-compression /
+// residual-phase multiply Phi3 (:380-382) on the inverse transform's load: element (row rho, column n) is multiplied by
+// cis(a_rho n^2 + b_rho n + c_rho) from the per-row tables (L1-resident: all W threads of a row read the same 20 bytes).
+// These kernels wait on HBM / shared memory with the FMA pipe two thirds idle, while the range kernel between them is
+// bound by exactly the MUFU / FMA work this takes off it.
+template <class P, bool INV, int W, bool PH>
 __global__ void __launch_bounds__(P::NT* W) k_az_inner_tma(const __grid_constant__ CUtensorMap map,
                                                            float2* __restrict__ data, int64_t pitch,
                                                            int n_col_tiles, int n_tiles, int x0, int k10,
-                                                           const float2* __restrict__ tw) {
+                                                           const float2* __restrict__ tw,
+                                                           const uint4* __restrict__ ph_ab,
+                                                           const uint32_t* __restrict__ ph_c) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ uint64_t full[2];
     constexpr int E = P::E, NT = P::NT, A2 = P::N;
@@ -170,16 +177,28 @@ __global__ void __launch_bounds__(P::NT* W) k_az_inner_tma(const __grid_constant
         const int b = i & 1;
         float2* buf = buf0 + b * TILE_ELEMS;
         if (tid == 0 && tile + (int)gridDim.x < n_tiles) issue(tile + gridDim.x, b ^ 1);
+        const int x = x0 + tile % n_col_tiles, k1 = k10 + tile / n_col_tiles;
+        const uint32_t n = (uint32_t)(x * W + c), n2 = n * n;
         tma::mbar_wait(&full[b], (i >> 1) & 1);
         float2 v[E];
 #pragma unroll
         for (int s = 0; s < E; ++s) v[s] = buf[(t + NT * s) * W + c];
+        if constexpr (PH && INV) {
+#pragma unroll
+            for (int s = 0; s < E; ++s) {
+                const int row = k1 * A2 + t + NT * s;
+                v[s] = cmul_pk(v[s], cis_u32_pre(row_phase_hi(__ldg(ph_ab + row), __ldg(ph_c + row), n, n2)));
+            }
+        }
         __syncthreads();   // every element is in registers before the exchange overwrites the tile
         transform<P, INV, W, 0, CtaBarrier, true>(v, t, buf + c, tw);
-        const int x = x0 + tile % n_col_tiles, k1 = k10 + tile / n_col_tiles;
         float2* base = data + (int64_t)k1 * A2 * pitch + x * W + c;
 #pragma unroll
         for (int s = 0; s < E; ++s) {
+            if constexpr (PH && !INV) {
+                const int row = k1 * A2 + t + NT * s;
+                v[s] = cmul_pk(v[s], cis_u32_pre(row_phase_hi(__ldg(ph_ab + row), __ldg(ph_c + row), n, n2)));
+            }
             base[(int64_t)(t + NT * s) * pitch] = v[s];
         }
         tma::fence_proxy_async();   // this thread's exchange writes are ordered before the TMA refill of buf
@@ -199,11 +218,12 @@ __global__ void __launch_bounds__(P::NT* W) k_az_inner_tma(const __grid_constant
 // registers and stores rows k2 + M k1 (natural Doppler order) straight to HBM -- or, for the inverse transform, the
 // scaled, corner-turned image slc[column][azimuth] with azimuth-contiguous 256-byte stores, plus max |slc|^2.
 // Several CTAs of different clusters share an SM, so one cluster's load / barrier latency hides behind another's math.
-template <class P, int C, int W, bool INV, bool TOUT>
+template <class P, int C, int W, bool INV, bool TOUT, bool PH>
 __global__ void __launch_bounds__(P::NT* W, 1024 / (P::NT * W)) k_az_cluster(const __grid_constant__ CUtensorMap map,
                                                          float2* __restrict__ out, int64_t out_pitch, int n_col_tiles,
                                                          float scale, double* __restrict__ max_sq,
-                                                         const float2* __restrict__ tw, const float2* __restrict__ twN) {
+                                                         const float2* __restrict__ tw, const float2* __restrict__ twN,
+                                                         const uint4* __restrict__ ph_ab, const uint32_t* __restrict__ ph_c) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ uint64_t full;
     constexpr int E = P::E, NT = P::NT, M = P::N, NTH = NT * W;
@@ -238,6 +258,14 @@ __global__ void __launch_bounds__(P::NT* W, 1024 / (P::NT * W)) k_az_cluster(con
         float2 v[E];
 #pragma unroll
         for (int s = 0; s < E; ++s) v[s] = buf[(t + NT * s) * W + c];
+        if constexpr (PH && INV) {   // Phi3 on the load: this CTA holds rows rank + C (t + NT s) of column x W + c
+            const uint32_t n = (uint32_t)(x * W + c), n2 = n * n;
+#pragma unroll
+            for (int s = 0; s < E; ++s) {
+                const int row = (int)rank + C * (t + NT * s);
+                v[s] = cmul_pk(v[s], cis_u32_pre(row_phase_hi(__ldg(ph_ab + row), __ldg(ph_c + row), n, n2)));
+            }
+        }
         __syncthreads();   // the tile is in registers: the buffer becomes the exchange buffer
         transform<P, INV, W, 0, CtaBarrier, true>(v, t, buf + c, tw);
         if (rank != 0) {
@@ -277,8 +305,16 @@ __global__ void __launch_bounds__(P::NT* W, 1024 / (P::NT * W)) k_az_cluster(con
                 }
             } else {
                 float2* o = out + (int64_t)k2 * out_pitch + x * W + cc;
+                const uint32_t n = (uint32_t)(x * W + cc), n2 = n * n;
 #pragma unroll
-                for (int k1 = 0; k1 < C; ++k1) o[(int64_t)(k1 * M) * out_pitch] = u[brev(k1, L)];
+                for (int k1 = 0; k1 < C; ++k1) {
+                    float2 r = u[brev(k1, L)];
+                    if constexpr (PH) {   // Phi1 on the store: Doppler row k2 + M k1 (natural order)
+                        const int row = k2 + M * k1;
+                        r = cmul_pk(r, cis_u32_pre(row_phase_hi(__ldg(ph_ab + row), __ldg(ph_c + row), n, n2)));
+                    }
+                    o[(int64_t)(k1 * M) * out_pitch] = r;
+                }
             }
         }
         tma::fence_proxy_async();   // generic-proxy traffic on the buffers is ordered before the next TMA refill
@@ -321,7 +357,9 @@ struct PhaseStepper {
 // One Doppler row per group of NT threads: x Phi1 -> FFT -> x Phi2 -> IFFT -> x Phi3, one HBM round
 // trip.  RPB independent row groups share a CTA (named barriers, so groups drift apart and overlap
 // each other's load / exchange / store phases).
-template <class P, int PAD, int RPB, int MINB, bool PK>
+// PHI13: the kernel also applies Phi1 on its load and Phi3 on its store (the round-1 arrangement; kept as the NIS_CSA_PHASE=range
+// development knob and for A/B measurements).  Default: only Phi2 here, Phi1 / Phi3 in the azimuth kernels either side.
+template <class P, int PAD, int RPB, int MINB, bool PK, bool PHI13>
 __global__ void __launch_bounds__(P::NT* RPB, MINB) k_range(float2* __restrict__ data, int64_t pitch, int n_rows,
                                                             const RowCoef* __restrict__ coef,
                                                             const float2* __restrict__ tw) {
@@ -380,7 +418,7 @@ __global__ void __launch_bounds__(P::NT* RPB, MINB) k_range(float2* __restrict__
 #pragma unroll
             for (int s = 0; s < E; ++s) v[s] = p[t + NT * s];
         }
-        {
+        if constexpr (PHI13) {
             PhaseStepper ps;
             ps.init(__ldg(&rc->a1), __ldg(&rc->b1), __ldg(&rc->c1), (uint32_t)t, NT);
 #pragma unroll
@@ -399,7 +437,7 @@ __global__ void __launch_bounds__(P::NT* RPB, MINB) k_range(float2* __restrict__
         }
         bar();
         transform<P, true, 1, PAD, Bar, PK>(v, t, sm, tw, bar);
-        {
+        if constexpr (PHI13) {
             PhaseStepper ps;
             ps.init(__ldg(&rc->a3), __ldg(&rc->b3), __ldg(&rc->c3), (uint32_t)t, NT);
 #pragma unroll
@@ -407,6 +445,10 @@ __global__ void __launch_bounds__(P::NT* RPB, MINB) k_range(float2* __restrict__
                 const float2 x = PK ? cmul_pk(v[s], ps.next()) : cmul(v[s], ps.next());
                 if (live) p[t + NT * s] = x;
             }
+        } else {
+#pragma unroll
+            for (int s = 0; s < E; ++s)
+                if (live) p[t + NT * s] = v[s];
         }
         bar();
     }
@@ -444,57 +486,62 @@ int launch_outer_inv(nis_csa_plan* pl, float2* slc, double* max_sq, int col0, in
     return NIS_OK;
 }
 
-template <class P, int W>
-int launch_inner(nis_csa_plan* pl, bool inv, int col0, int ncols, int k10, int nk1, cudaStream_t st) {
+template <class P, int W, bool INV, bool PH>
+int launch_inner_one(nis_csa_plan* pl, int col0, int ncols, int k10, int nk1, cudaStream_t st) {
+    auto kern = k_az_inner_tma<P, INV, W, PH>;
     const size_t smem = 2 * (size_t)P::N * W * sizeof(float2);   // double-buffered tile
-    static bool attr_done_dev[64] = {};
-    bool& attr_done = attr_done_dev[nis::current_device() & 63];
-    if (!attr_done) {
-        NIS_CUDA_TRY(cudaFuncSetAttribute(k_az_inner_tma<P, false, W>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                          (int)smem));
-        NIS_CUDA_TRY(cudaFuncSetAttribute(k_az_inner_tma<P, true, W>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                          (int)smem));
-        attr_done = true;
+    static int per_sm_dev[64] = {};
+    int& per_sm = per_sm_dev[nis::current_device() & 63];
+    if (!per_sm) {
+        NIS_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        int n = 1;
+        NIS_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kern, P::NT * W, smem));
+        per_sm = n < 1 ? 1 : n;
     }
-    int per_sm = 1;
-    NIS_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_az_inner_tma<P, false, W>, P::NT * W, smem));
-    if (per_sm < 1) per_sm = 1;
     const int n_col_tiles = ncols / W, n_tiles = n_col_tiles * nk1;
     int grid = pl->ctx->num_sms * per_sm;
     if (grid > n_tiles) grid = n_tiles;
-    if (inv)
-        k_az_inner_tma<P, true, W><<<grid, P::NT * W, smem, st>>>(pl->tile_map, pl->work, pl->n_rg, n_col_tiles, n_tiles,
-                                                                  col0 / W, k10, pl->tw_inner);
-    else
-        k_az_inner_tma<P, false, W><<<grid, P::NT * W, smem, st>>>(pl->tile_map, pl->work, pl->n_rg, n_col_tiles, n_tiles,
-                                                                   col0 / W, k10, pl->tw_inner);
+    kern<<<grid, P::NT * W, smem, st>>>(pl->tile_map, pl->work, pl->n_rg, n_col_tiles, n_tiles, col0 / W, k10, pl->tw_inner,
+                                        INV ? pl->ph3_ab : pl->ph1_ab, INV ? pl->ph3_c : pl->ph1_c);
     NIS_LAUNCH_CHECK(pl->ctx);
     return NIS_OK;
+}
+template <class P, int W>
+int launch_inner(nis_csa_plan* pl, bool inv, int col0, int ncols, int k10, int nk1, cudaStream_t st) {
+    if (pl->phase_in_az)
+        return inv ? launch_inner_one<P, W, true, true>(pl, col0, ncols, k10, nk1, st)
+                   : launch_inner_one<P, W, false, true>(pl, col0, ncols, k10, nk1, st);
+    return inv ? launch_inner_one<P, W, true, false>(pl, col0, ncols, k10, nk1, st)
+               : launch_inner_one<P, W, false, false>(pl, col0, ncols, k10, nk1, st);
 }
 
 // PK = false: the packed forms cut this kernel's instruction count by a third but not its time (it is bound by the
 // FMA pipe and the MIO/shared-memory pipe back to back, not by issue slots; measured 0.466 vs 0.456 ms at 8192^2)
-template <class P, int PAD, int RPB, int MINB, bool PK = false>
-int launch_range(nis_csa_plan* pl, int row0, int nrows, cudaStream_t st) {
+template <class P, int PAD, int RPB, int MINB, bool PK, bool PHI13>
+int launch_range_one(nis_csa_plan* pl, int row0, int nrows, cudaStream_t st) {
+    auto kern = k_range<P, PAD, RPB, MINB, PK, PHI13>;
     constexpr int SMROW = P::N + (PAD ? (P::N >> PAD) : 0);
     constexpr int GROUP_ELEMS = SMROW + ((P::NT >= 32 && P::N <= 8192) ? P::N : 0);   // exchange buffer + prefetch buffer
     const size_t smem = (size_t)GROUP_ELEMS * RPB * sizeof(float2);
-    static bool attr_done_dev[64] = {};
-    bool& attr_done = attr_done_dev[nis::current_device() & 63];
-    if (!attr_done) {
-        NIS_CUDA_TRY(cudaFuncSetAttribute(k_range<P, PAD, RPB, MINB, PK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_done = true;
+    static int per_sm_dev[64] = {};
+    int& per_sm = per_sm_dev[nis::current_device() & 63];
+    if (!per_sm) {
+        NIS_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        int n = 1;
+        NIS_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kern, P::NT * RPB, smem));
+        per_sm = n < 1 ? 1 : n;
     }
-    int per_sm = 1;
-    NIS_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_range<P, PAD, RPB, MINB, PK>, P::NT * RPB, smem));
-    if (per_sm < 1) per_sm = 1;
     const int blocks_needed = (nrows + RPB - 1) / RPB;
     int grid = pl->ctx->num_sms * per_sm;
     if (grid > blocks_needed) grid = blocks_needed;
-    k_range<P, PAD, RPB, MINB, PK><<<grid, dim3(P::NT, RPB), smem, st>>>(pl->work + (int64_t)row0 * pl->n_rg, pl->n_rg, nrows,
-                                                                     pl->coef + row0, pl->tw_rg);
+    kern<<<grid, dim3(P::NT, RPB), smem, st>>>(pl->work + (int64_t)row0 * pl->n_rg, pl->n_rg, nrows, pl->coef + row0, pl->tw_rg);
     NIS_LAUNCH_CHECK(pl->ctx);
     return NIS_OK;
+}
+template <class P, int PAD, int RPB, int MINB, bool PK = false>
+int launch_range(nis_csa_plan* pl, int row0, int nrows, cudaStream_t st) {
+    if (pl->phase_in_az) return launch_range_one<P, PAD, RPB, MINB, PK, false>(pl, row0, nrows, st);
+    return launch_range_one<P, PAD, RPB, MINB, PK, true>(pl, row0, nrows, st);
 }
 
 // plans: <N, E, R0, R1, R2>
@@ -520,10 +567,19 @@ int upload_twiddles(float2** dev) {
 
 
 // cluster azimuth transforms: forward (raw -> W, natural Doppler row order) and inverse (W -> slc, corner-turned)
+template <class P, int C, int W, bool INV, bool PH>
+int launch_az_cluster_ph(nis_csa_plan* pl, const CUtensorMap& map, float2* out, int64_t out_pitch, double* max_sq,
+                         cudaStream_t st);
 template <class P, int C, int W, bool INV>
 int launch_az_cluster(nis_csa_plan* pl, const CUtensorMap& map, float2* out, int64_t out_pitch, double* max_sq,
                       cudaStream_t st) {
-    auto kern = k_az_cluster<P, C, W, INV, INV>;
+    if (!pl->phase_in_az) return launch_az_cluster_ph<P, C, W, INV, false>(pl, map, out, out_pitch, max_sq, st);
+    return launch_az_cluster_ph<P, C, W, INV, true>(pl, map, out, out_pitch, max_sq, st);
+}
+template <class P, int C, int W, bool INV, bool PH>
+int launch_az_cluster_ph(nis_csa_plan* pl, const CUtensorMap& map, float2* out, int64_t out_pitch, double* max_sq,
+                         cudaStream_t st) {
+    auto kern = k_az_cluster<P, C, W, INV, INV, PH>;
     const size_t smem = INV ? (size_t)W * (P::N + 2) * sizeof(float2) : (size_t)P::N * W * sizeof(float2);
     static int n_clusters_dev[64] = {};
     int& n_clusters = n_clusters_dev[nis::current_device() & 63];
@@ -557,7 +613,8 @@ int launch_az_cluster(nis_csa_plan* pl, const CUtensorMap& map, float2* out, int
     cfg.gridDim = dim3(C * nc);
     const float scale = (float)(1.0 / ((double)pl->n_az * (double)pl->n_rg));
     NIS_CUDA_TRY(cudaLaunchKernelEx(&cfg, kern, map, out, out_pitch, n_col_tiles, scale, max_sq,
-                                    (const float2*)pl->tw_inner, (const float2*)pl->tw_full));
+                                    (const float2*)pl->tw_inner, (const float2*)pl->tw_full,
+                                    (const uint4*)(INV ? pl->ph3_ab : pl->ph1_ab), (const uint32_t*)(INV ? pl->ph3_c : pl->ph1_c)));
     NIS_LAUNCH_CHECK(pl->ctx);
     return NIS_OK;
 }
@@ -781,6 +838,10 @@ extern "C" int nis_csa_plan_destroy(nis_csa_plan* pl) {
     cudaFree(pl->tw_full);
     cudaFree(pl->tw_rg);
     cudaFree(pl->coef);
+    cudaFree(pl->ph1_ab);
+    cudaFree(pl->ph1_c);
+    cudaFree(pl->ph3_ab);
+    cudaFree(pl->ph3_c);
     for (auto& set : pl->prof_ev)
         for (auto& e : set)
             if (e) cudaEventDestroy(e);
@@ -840,6 +901,30 @@ extern "C" int nis_csa_plan_create(nis_ctx* ctx, int32_t n_az, int32_t n_rg, con
         FAIL_IF(generic_create(pl));
         *out = pl;
         return NIS_OK;
+    }
+    {
+        // Phi1 / Phi3 for the azimuth kernels (default); NIS_CSA_PHASE=range keeps all three multiplies in k_range
+        const char* v = getenv("NIS_CSA_PHASE");
+        pl->phase_in_az = !(v && v[0] == 'r');
+        if (pl->phase_in_az) {
+            std::vector<RowCoef> h = build_row_coefs(n_az, n_rg, *prm, pl->A1, pl->A2);
+            std::vector<uint4> ab1(n_az), ab3(n_az);
+            std::vector<uint32_t> c1(n_az), c3(n_az);
+            for (int r = 0; r < n_az; ++r) {
+                ab1[r] = make_uint4((uint32_t)h[r].a1, (uint32_t)(h[r].a1 >> 32), (uint32_t)h[r].b1, (uint32_t)(h[r].b1 >> 32));
+                ab3[r] = make_uint4((uint32_t)h[r].a3, (uint32_t)(h[r].a3 >> 32), (uint32_t)h[r].b3, (uint32_t)(h[r].b3 >> 32));
+                c1[r] = (uint32_t)(h[r].c1 >> 32) + 0x100u;   // + half an ulp of the 23-bit sincos argument (cis_u32_pre)
+                c3[r] = (uint32_t)(h[r].c3 >> 32) + 0x100u;
+            }
+            auto up = [&](void** dst, const void* src, size_t bytes) -> int {
+                if (cudaMalloc(dst, bytes) != cudaSuccess) return NIS_ERR_NOMEM;
+                return cudaMemcpy(*dst, src, bytes, cudaMemcpyHostToDevice) == cudaSuccess ? NIS_OK : NIS_ERR_CUDA;
+            };
+            FAIL_IF(up((void**)&pl->ph1_ab, ab1.data(), n_az * sizeof(uint4)));
+            FAIL_IF(up((void**)&pl->ph1_c, c1.data(), n_az * sizeof(uint32_t)));
+            FAIL_IF(up((void**)&pl->ph3_ab, ab3.data(), n_az * sizeof(uint4)));
+            FAIL_IF(up((void**)&pl->ph3_c, c3.data(), n_az * sizeof(uint32_t)));
+        }
     }
 
     // ---- kernel selection (power-of-two path)

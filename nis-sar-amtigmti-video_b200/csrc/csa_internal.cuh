@@ -30,6 +30,22 @@ __device__ __forceinline__ uint64_t phi2_phase(const RowCoef& rc, uint32_t k, ui
     return rc.a2 * (uint64_t)(ka * ka) + rc.b2 * (uint64_t)k - (neg ? rc.bn2 : 0ull);
 }
 
+// Compact per-row form of a quadratic phase a n^2 + b n + c for the kernels that evaluate it at scattered (row, n) pairs
+// (the azimuth kernels apply Phi1 on their store and Phi3 on their load): the 64-bit a and b split into words, c reduced to its
+// top word with the half-ulp rounding offset of cis_u32_pre() folded in.  Only the top 32 bits of the sum are needed; dropping
+// the carries out of the low words costs <= 3 * 2^-32 turns.
+struct RowPhase {
+    uint32_t a_lo, a_hi, b_lo, b_hi;
+};
+static_assert(sizeof(RowPhase) == 16, "RowPhase layout");
+
+__device__ __forceinline__ uint32_t row_phase_hi(uint4 ab, uint32_t c_hi, uint32_t n, uint32_t n2) {
+    uint32_t t = c_hi + ab.y * n2 + ab.w * n;
+    t += __umulhi(ab.x, n2);
+    t += __umulhi(ab.z, n);
+    return t;
+}
+
 inline uint64_t to_fix(long double turns) {
     long double f = turns - floorl(turns);
     long double s = f * 18446744073709551616.0L;
@@ -82,6 +98,12 @@ struct nis_csa_plan {
     float2* tw_full = nullptr;
     float2* tw_rg = nullptr;
     nis::csa::RowCoef* coef = nullptr;
+    // Phi1 / Phi3 in the compact form the azimuth kernels read (null: the range kernel applies all three phase functions)
+    uint4* ph1_ab = nullptr;
+    uint32_t* ph1_c = nullptr;
+    uint4* ph3_ab = nullptr;
+    uint32_t* ph3_c = nullptr;
+    bool phase_in_az = false;
     CUtensorMap tile_map{};   // [n_az][n_rg] workspace, box = min(A2,256) rows x inner_w columns
     int inner_w = 0;
     std::vector<double> range_axis, cross_range;

@@ -100,13 +100,14 @@ __device__ __forceinline__ void st_status(unsigned long long* p, unsigned long l
 // Two adjacent pixels per thread.  VEC: 16-byte loads and 16- / 8- / 2-byte stores (every pointer suitably aligned);
 // otherwise element-wise accesses (views at odd element offsets).
 template <bool VEC>
-__global__ void __launch_bounds__(256) k_gmti_fused(const float2* __restrict__ slc1, const float2* __restrict__ slc2,
+__global__ void __launch_bounds__(256, 4) k_gmti_fused(const float2* __restrict__ slc1, const float2* __restrict__ slc2,
                                                     uint64_t n, double thresh_frac, float2 cal, int use_cal, GmtiOut o,
                                                     uint32_t* __restrict__ ticket, unsigned long long* __restrict__ status,
                                                     int n_tiles, uint32_t* __restrict__ det_idx, uint32_t det_cap,
                                                     nis_gmti_result* res) {
     __shared__ uint32_t s_tile, s_base;
     __shared__ uint32_t s_cnt[32];           // detections of group (iteration, warp) -> exclusive offset inside the tile
+    __shared__ uint2 s_bal[32];              // the group's detection ballots (even pixels, odd pixels)
     if (threadIdx.x == 0) s_tile = atomicAdd(ticket, 1u);   // tiles are numbered in the order CTAs start: a tile only
     __syncthreads();                                        // ever waits for tiles that are already running
     const uint32_t tile = s_tile;
@@ -117,8 +118,7 @@ __global__ void __launch_bounds__(256) k_gmti_fused(const float2* __restrict__ s
     const double lo_sq = thr_sq * (1.0 - 1e-12), hi_sq = thr_sq * (1.0 + 1e-12);
     const uint64_t tile_base = (uint64_t)tile * kTile;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    uint32_t bal0[kIters], bal1[kIters];
-#pragma unroll
+#pragma unroll 2
     for (int it = 0; it < kIters; ++it) {
         const uint64_t i = tile_base + (uint64_t)it * 512 + wid * 64 + 2 * lane;
         bool d0 = false, d1 = false;
@@ -165,9 +165,11 @@ __global__ void __launch_bounds__(256) k_gmti_fused(const float2* __restrict__ s
             if (o.mask) o.mask[i] = d0 ? 1 : 0;
             if (o.phase_masked) o.phase_masked[i] = p0.phm;
         }
-        bal0[it] = __ballot_sync(0xffffffffu, d0);
-        bal1[it] = __ballot_sync(0xffffffffu, d1);
-        if (lane == 0) s_cnt[it * 8 + wid] = __popc(bal0[it]) + __popc(bal1[it]);
+        const uint32_t b0 = __ballot_sync(0xffffffffu, d0), b1 = __ballot_sync(0xffffffffu, d1);
+        if (lane == 0) {
+            s_cnt[it * 8 + wid] = __popc(b0) + __popc(b1);
+            s_bal[it * 8 + wid] = make_uint2(b0, b1);
+        }
     }
     __syncthreads();
     if (wid == 0) {
@@ -215,7 +217,8 @@ __global__ void __launch_bounds__(256) k_gmti_fused(const float2* __restrict__ s
         const uint32_t below = (1u << lane) - 1u;
 #pragma unroll
         for (int it = 0; it < kIters; ++it) {
-            const uint32_t b0 = bal0[it], b1 = bal1[it];
+            const uint2 bb = s_bal[it * 8 + wid];
+            const uint32_t b0 = bb.x, b1 = bb.y;
             if (((b0 | b1) >> lane) & 1u) {
                 const uint64_t i = tile_base + (uint64_t)it * 512 + wid * 64 + 2 * lane;
                 uint32_t pos = s_base + s_cnt[it * 8 + wid] + __popc(b0 & below) + __popc(b1 & below);

@@ -114,12 +114,23 @@ def tdbp(n_pulses=2500, n_pix=512):
 
 
 def gmti(n):
+    """K3 on a dense pair (noise: ~97 % of the pixels pass the 5 % threshold -- worst case for the compaction) and on a
+    sparse one (one bright pixel); with and without max|slc1| handed in."""
     a = torch.view_as_complex(torch.randn((n, n, 2), device="cuda"))
     b = torch.view_as_complex(torch.randn((n, n, 2), device="cuda"))
-    ms = time_cuda(lambda: dev.gmti_fused(a, b), 5)
-    print(json.dumps({"what": "gmti_all_products", "n": n, "ms": ms, "GBps_49B": 49.0 * n * n / ms * 1e-6}), flush=True)
-    ms = time_cuda(lambda: dev.gmti_fused(a, b, want=("ati_phase_masked",)), 5)
-    print(json.dumps({"what": "gmti_phase_det_only", "n": n, "ms": ms, "GBps_20B": 20.0 * n * n / ms * 1e-6}), flush=True)
+    for tag in ("dense", "sparse"):
+        if tag == "sparse":
+            a[n // 2, n // 3] = 4000.0
+        mx = torch.zeros(1, dtype=torch.float64, device="cuda")
+        mx.fill_(float((torch.view_as_real(a).double() ** 2).sum(dim=-1).max()))
+        ms = time_cuda(lambda: dev.gmti_fused(a, b, lazy=True, max_sq=mx), 20, 4)
+        ms2 = time_cuda(lambda: dev.gmti_fused(a, b, lazy=True), 20, 4)
+        ms3 = time_cuda(lambda: dev.gmti_fused(a, b, lazy=True, max_sq=mx, want=("ati_phase_masked",)), 20, 4)
+        cnt = int(dev.gmti_fused(a, b, max_sq=mx, want=())["det_count"])
+        print(json.dumps({"what": "gmti", "case": tag, "n": n, "detected_fraction": cnt / (n * n), "ms_all_products_max_given": ms,
+                          "GBps_49B": 49.0 * n * n / ms * 1e-6, "frac": 49.0 * n * n / ms * 1e-6 / PEAK,
+                          "ms_all_products_own_max": ms2, "ms_phase_and_detections_only": ms3,
+                          "GBps_20B": 20.0 * n * n / ms3 * 1e-6}), flush=True)
 
 
 def echo(kind):
