@@ -222,14 +222,14 @@ NIS_API int nis_tdbp_backproject(nis_tdbp_plan* plan, const nis_c32* rc, const d
  *   phase_masked = mask ? phase : 0; det_idx = ascending flat indices with mask set;
  *   peak = first index attaining max|slc1|.
  * Any output pointer may be NULL (that product is not materialised).
- * One pass over the pair: products, detection flags and the compaction of the flagged indices happen in the same kernel
- * (per-tile counts chained by a decoupled look-back), preceded only by a pass over slc1 for max|slc1| when the caller
- * does not pass max_mag_sq_in.
+ * One pass over the pair (products, detection bitmap, per-tile counts) + a tail kernel that reads only the workspace and
+ * writes the index list and the result record; preceded by a pass over slc1 for max|slc1| only when the caller does not
+ * pass max_mag_sq_in.  No atomics and no inter-block waiting: the list is deterministic.
  * Buffers: every pointer aligned to its element size (8 B complex, 4 B float / index).  When additionally the complex
  * buffers are 16-byte, the float maps 8-byte and the mask 2-byte aligned -- true for any whole allocation -- the kernel
  * moves two pixels per access; views at odd element offsets take an element-wise variant of the same kernel.
  * n_pix < 2^32 - 1 (flat indices and det_count are 32-bit: every BASELINE size fits).
- * workspace: dev, caller-owned, nis_gmti_workspace_bytes(n_pix) bytes (8 bytes per 2048 pixels + 16), 8-byte aligned,
+ * workspace: dev, caller-owned, nis_gmti_workspace_bytes(n_pix) bytes (264 bytes per 2048 pixels + 16), 8-byte aligned,
  * contents irrelevant on entry; it must not be shared by two calls that may run concurrently.
  */
 NIS_API uint64_t nis_gmti_workspace_bytes(uint64_t n_pix);

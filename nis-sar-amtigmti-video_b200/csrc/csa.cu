@@ -141,8 +141,7 @@ __global__ void __launch_bounds__(256) k_az_outer_inv_mag(const float2* __restri
 // PH: the chirp-scaling multiply Phi1 (:272-274) rides on the forward transform's store and the azimuth-compression /
 // residual-phase multiply Phi3 (:380-382) on the inverse transform's load: element (row rho, column n) is multiplied by
 // cis(a_rho n^2 + b_rho n + c_rho) from the per-row tables (L1-resident: all W threads of a row read the same 20 bytes).
-// These kernels wait on HBM / shared memory with the FMA pipe two thirds idle, while the range kernel between them is
-// bound by exactly the MUFU / FMA work this takes off it.
+// (Development arrangement NIS_CSA_PHASE=az; the default keeps both multiplies in k_range -- measured faster.)
 template <class P, bool INV, int W, bool PH>
 __global__ void __launch_bounds__(P::NT* W) k_az_inner_tma(const __grid_constant__ CUtensorMap map,
                                                            float2* __restrict__ data, int64_t pitch,
@@ -357,8 +356,8 @@ struct PhaseStepper {
 // One Doppler row per group of NT threads: x Phi1 -> FFT -> x Phi2 -> IFFT -> x Phi3, one HBM round
 // trip.  RPB independent row groups share a CTA (named barriers, so groups drift apart and overlap
 // each other's load / exchange / store phases).
-// PHI13: the kernel also applies Phi1 on its load and Phi3 on its store (the round-1 arrangement; kept as the NIS_CSA_PHASE=range
-// development knob and for A/B measurements).  Default: only Phi2 here, Phi1 / Phi3 in the azimuth kernels either side.
+// PHI13: the kernel also applies Phi1 on its load and Phi3 on its store (default).  With NIS_CSA_PHASE=az only Phi2 is applied
+// here and Phi1 / Phi3 ride on the azimuth kernels either side (measured slower overall, see nis_csa_plan_create).
 template <class P, int PAD, int RPB, int MINB, bool PK, bool PHI13>
 __global__ void __launch_bounds__(P::NT* RPB, MINB) k_range(float2* __restrict__ data, int64_t pitch, int n_rows,
                                                             const RowCoef* __restrict__ coef,
@@ -903,9 +902,14 @@ extern "C" int nis_csa_plan_create(nis_ctx* ctx, int32_t n_az, int32_t n_rg, con
         return NIS_OK;
     }
     {
-        // Phi1 / Phi3 for the azimuth kernels (default); NIS_CSA_PHASE=range keeps all three multiplies in k_range
+        // Where Phi1 / Phi3 are applied.  Default: in k_range with Phi2 (one HBM round trip for all three).  NIS_CSA_PHASE=az
+        // moves Phi1 onto the store of the forward azimuth kernel and Phi3 onto the load of the inverse one.  Measured on a
+        // B200 (profiles/kbench_r2b_*.jsonl): k_range gains little (8192^2: 0.453 -> 0.429 ms; it is bound by its shared-memory
+        // exchanges, not by the phase arithmetic) while the azimuth kernels, which run one 512-thread CTA per SM, cannot hide
+        // the extra dependent work (0.196 -> 0.287 and 0.197 -> 0.243 ms): 1.20 -> 1.32 ms per frame, and 0.279 -> 0.291 ms at
+        // 4096^2 with the cluster engine.  Kept as a tested development knob, not the default.
         const char* v = getenv("NIS_CSA_PHASE");
-        pl->phase_in_az = !(v && v[0] == 'r');
+        pl->phase_in_az = (v && v[0] == 'a');
         if (pl->phase_in_az) {
             std::vector<RowCoef> h = build_row_coefs(n_az, n_rg, *prm, pl->A1, pl->A2);
             std::vector<uint4> ab1(n_az), ab3(n_az);

@@ -50,6 +50,204 @@ __device__ __forceinline__ bool gate(const double* __restrict__ t_fast, int n, d
     return fabs(__dsub_rn(__dsub_rn(t_fast[n], tau), off)) <= half;
 }
 
+// Inner loop of both kernels: add the samples [t_lo, t_hi) (relative to the chunk start) of every kept scatterer of the
+// chunk to the thread's accumulators.
+template <int SPT>
+__device__ __forceinline__ void accumulate_kept(float2 (&acc)[SPT], const uint4* __restrict__ rec,
+                                                const float2* __restrict__ recv, int total, int t_lo, int t_hi, int mt,
+                                                uint32_t k1, float2 vk2) {
+    constexpr int HALF = SPT / 2;
+#pragma unroll 1
+    for (int q = 0; q < total; ++q) {
+        const uint4 s = rec[q];
+        const int lo = (int)(s.w & 0xffffu), hi = (int)(s.w >> 16);
+        if (t_lo >= hi || t_hi <= lo) continue;
+        const uint32_t phi = s.x + s.y * (uint32_t)mt + k1;
+        const float2 u = cscale_pk(cis_u32(phi), __uint_as_float(s.z));
+        const float2 v = cmul_pk(recv[q], vk2);
+        // the samples of one scatterer are a geometric sequence u v^k, and any such sequence obeys the three-term
+        // recurrence p[k+1] = 2 cos(delta) p[k] - p[k-1] (v + 1/v = 2 cos delta): TWO FMAs per new complex term instead
+        // of the four of a complex multiply.  Two chains run outward from the centre sample (forward f, backward b),
+        // real and imaginary parts independently: four independent FMA chains per scatterer.  The recurrence amplifies
+        // an error of the coefficient by at most k^2 / 2 over k steps; k <= SPT/2 here (<= 3e-5 relative, reached only
+        // where the chirp's instantaneous frequency is near zero).
+        const float c2 = 2.0f * v.x;
+        float2 f0 = u, f1 = cmul_pk(u, v);
+        float2 b0 = cmul_conj_pk(u, v), b1 = cfms_pk(c2, b0, u);
+        if (t_lo >= lo && t_hi <= hi) {
+#pragma unroll
+            for (int i = 0; i < HALF; i += 2) {
+                acc[HALF + i] = cadd_pk(acc[HALF + i], f0);
+                acc[HALF + i + 1] = cadd_pk(acc[HALF + i + 1], f1);
+                acc[HALF - 1 - i] = cadd_pk(acc[HALF - 1 - i], b0);
+                acc[HALF - 2 - i] = cadd_pk(acc[HALF - 2 - i], b1);
+                if (i + 2 < HALF) {
+                    f0 = cfms_pk(c2, f1, f0);
+                    f1 = cfms_pk(c2, f0, f1);
+                    b0 = cfms_pk(c2, b1, b0);
+                    b1 = cfms_pk(c2, b0, b1);
+                }
+            }
+        } else {
+            const int a = lo - t_lo, b = hi - t_lo;   // live samples: a <= j < b
+#pragma unroll
+            for (int i = 0; i < HALF; i += 2) {
+                int j = HALF + i;
+                if (j >= a && j < b) acc[j] = cadd(acc[j], f0);
+                j = HALF + i + 1;
+                if (j >= a && j < b) acc[j] = cadd(acc[j], f1);
+                j = HALF - 1 - i;
+                if (j >= a && j < b) acc[j] = cadd(acc[j], b0);
+                j = HALF - 2 - i;
+                if (j >= a && j < b) acc[j] = cadd(acc[j], b1);
+                if (i + 2 < HALF) {
+                    f0 = cfms_pk(c2, f1, f0);
+                    f1 = cfms_pk(c2, f0, f1);
+                    b0 = cfms_pk(c2, b1, b0);
+                    b1 = cfms_pk(c2, b0, b1);
+                }
+            }
+        }
+    }
+}
+
+// exact chirp support [lo, hi) of a delay on the caller's sample-time table: the closed-form estimate corrected by the
+// reference's own fp64 gate expression (boundary samples bit-exact)
+__device__ __forceinline__ void chirp_support(const EchoConst& k, const double* __restrict__ t_fast, double tau, double off,
+                                              double half, int& lo, int& hi) {
+    lo = (int)ceil((tau + off - half - k.t_start) / k.dt_fast);
+    hi = (int)floor((tau + off + half - k.t_start) / k.dt_fast) + 1;
+    lo = max(0, min(lo, k.S));
+    hi = max(0, min(hi, k.S));
+#pragma unroll 1
+    for (int it = 0; it < 3 && lo > 0 && gate(t_fast, lo - 1, tau, off, half); ++it) --lo;
+#pragma unroll 1
+    for (int it = 0; it < 3 && lo < k.S && !gate(t_fast, lo, tau, off, half); ++it) ++lo;
+#pragma unroll 1
+    for (int it = 0; it < 3 && hi < k.S && gate(t_fast, hi, tau, off, half); ++it) ++hi;
+#pragma unroll 1
+    for (int it = 0; it < 3 && hi > 0 && !gate(t_fast, hi - 1, tau, off, half); ++it) --hi;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Sparse scenes (T <= 256 scatterers: point-target grids, a single ship): ONE CTA per pulse walks all chunks of the window.
+// The fp64 geometry -- position, two norms, delay, exact chirp support -- is evaluated once per (scatterer, pulse) and kept
+// in shared memory; per chunk only the phase polynomial about the chunk centre is re-expanded (a dozen fp64 operations).
+// k_echo spends a quarter of its instructions on that geometry when every chunk-CTA of a pulse repeats it for a handful
+// of scatterers (bench scene, 81 scatterers x 2 chunks: 299 M warp instructions, profiles/prof_echo_r1.txt).
+template <int SPT>
+__global__ void __launch_bounds__(256, 3) k_echo_sparse(EchoConst k, EchoTail<SPT> tail, const double* __restrict__ pos0,
+                                                        const double* __restrict__ vel, const double* __restrict__ amp,
+                                                        const double* __restrict__ pos_tx, const double* __restrict__ pos_rx,
+                                                        const double* __restrict__ t_slow, const double* __restrict__ t_fast,
+                                                        float2* __restrict__ raw, int n_chunks) {
+    constexpr int NTH = 256, CH = NTH * SPT, HALF = SPT / 2;
+    __shared__ uint4 rec[256];
+    __shared__ float2 recv[256];
+    __shared__ double s_tau[256];
+    __shared__ int2 s_sup[256];      // absolute support [lo, hi)
+    __shared__ float s_amp[256];
+    __shared__ int warp_cnt[8];
+
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int pulse = k.P0 + blockIdx.x;
+    const int mt = tid * SPT + HALF - CH / 2;
+    const int t_lo = tid * SPT, t_hi = t_lo + SPT;
+    const uint32_t k1 = frac32(k.a_turns * (double)mt * (double)mt);
+    const uint32_t k2 = frac32(2.0 * k.a_turns * (double)mt);
+    const float2 vk2 = cis_u32(k2);
+    const double half = k.t_p / 2, off = half;
+
+    // ---- once per pulse: geometry of scatterer `tid`
+    if (tid < k.T) {
+        const double ti = t_slow[pulse];
+        const double tx0 = pos_tx[3 * pulse], tx1 = pos_tx[3 * pulse + 1], tx2 = pos_tx[3 * pulse + 2];
+        const double* vb = k.per_target_velocity ? vel + 3 * tid : vel;
+        const double px = __dadd_rn(pos0[3 * tid], __dmul_rn(vb[0], ti)),
+                     py = __dadd_rn(pos0[3 * tid + 1], __dmul_rn(vb[1], ti)),
+                     pz = __dadd_rn(pos0[3 * tid + 2], __dmul_rn(vb[2], ti));
+        double dx = px - tx0, dy = py - tx1, dz = pz - tx2;
+        const double d_tx = sqrt(__dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz)));
+        double tau;
+        if (k.bistatic) {
+            dx = px - pos_rx[3 * pulse]; dy = py - pos_rx[3 * pulse + 1]; dz = pz - pos_rx[3 * pulse + 2];
+            const double d_rx = sqrt(__dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz)));
+            tau = __ddiv_rn(__dadd_rn(d_tx, d_rx), k.c);
+        } else {
+            tau = __ddiv_rn(__dmul_rn(2.0, d_tx), k.c);
+        }
+        int lo, hi;
+        chirp_support(k, t_fast, tau, off, half, lo, hi);
+        s_tau[tid] = tau;
+        s_sup[tid] = make_int2(lo, hi);
+        s_amp[tid] = (float)amp[tid];
+    }
+    __syncthreads();
+
+    for (int chunk = 0; chunk < n_chunks; ++chunk) {
+        const int n0 = chunk * CH, nc = n0 + CH / 2;
+        // ---- per chunk: phase polynomial about the chunk centre, ordered compaction of the scatterers that reach it
+        bool keep = false;
+        uint4 r = make_uint4(0, 0, 0, 0);
+        if (tid < k.T) {
+            const int2 sup = s_sup[tid];
+            const int rlo = max(sup.x - n0, 0), rhi = min(sup.y - n0, CH);
+            if (rlo < rhi) {
+                keep = true;
+                const double tau = s_tau[tid];
+                const double uu = (k.t_start + (double)nc * k.dt_fast) - tau - off;
+                r.x = frac32(fma(0.5 * k.k_rate * uu, uu, -k.fc * tau));
+                r.y = frac32(k.k_rate * uu * k.dt_fast);
+                r.z = __float_as_uint(s_amp[tid]);
+                r.w = (uint32_t)rlo | ((uint32_t)rhi << 16);
+            }
+        }
+        const unsigned ball = __ballot_sync(0xffffffffu, keep);
+        if (lane == 0) warp_cnt[wid] = __popc(ball);
+        __syncthreads();   // also: the previous chunk's consumers are done with rec[]
+        int slot = __popc(ball & ((1u << lane) - 1u));
+        int total = 0;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) {
+            const int cw = warp_cnt[w];
+            if (w < wid) slot += cw;
+            total += cw;
+        }
+        if (keep) {
+            rec[slot] = r;
+            recv[slot] = cis_u32(r.y);
+        }
+        __syncthreads();
+        if (n0 + t_lo >= k.S) continue;       // threads past the end of the window (uniform barriers above)
+        float2 acc[SPT];
+#pragma unroll
+        for (int j = 0; j < SPT; ++j) acc[j] = make_float2(0.f, 0.f);
+        accumulate_kept<SPT>(acc, rec, recv, total, t_lo, t_hi, mt, k1, vk2);
+        float2* out = raw + (int64_t)pulse * k.S + n0 + t_lo;
+        if (k.accumulate == 0 && n0 + t_hi <= k.S) {   // whole thread inside the window: 16-byte stores
+#pragma unroll
+            for (int j = 0; j < SPT; j += 2) {
+                const float2 x0 = cmul(acc[j], tail.e[j]), x1 = cmul(acc[j + 1], tail.e[j + 1]);
+                *reinterpret_cast<float4*>(out + j) = make_float4(x0.x, x0.y, x1.x, x1.y);
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < SPT; ++j) {
+                if (n0 + t_lo + j < k.S) {
+                    float2 x = cmul(acc[j], tail.e[j]);
+                    if (k.accumulate == 2) {
+                        atomicAdd_system(&out[j].x, x.x);
+                        atomicAdd_system(&out[j].y, x.y);
+                    } else {
+                        if (k.accumulate) { const float2 o = out[j]; x.x += o.x; x.y += o.y; }
+                        out[j] = x;
+                    }
+                }
+            }
+        }
+    }
+}
+
 // SPOT: the spotlight model is a separate instantiation, so that the stripmap engines keep their register budget
 // W256: the CTA has all 256 threads (chunk width and tile size are compile-time constants)
 template <int SPT, bool SPOT, bool W256>
@@ -172,58 +370,7 @@ __global__ void __launch_bounds__(256, SPOT ? 1 : 4) k_echo(EchoConst k, EchoTai
         __syncthreads();
 
         // ------------------------------------------------ inner loop: every thread, every kept scatterer
-#pragma unroll 1
-        for (int q = 0; q < total; ++q) {
-            const uint4 s = rec[q];
-            const int lo = (int)(s.w & 0xffffu), hi = (int)(s.w >> 16);
-            if (t_lo >= hi || t_hi <= lo) continue;
-            const uint32_t phi = s.x + s.y * (uint32_t)mt + k1;
-            const float2 u = cscale_pk(cis_u32(phi), __uint_as_float(s.z));
-            const float2 v = cmul_pk(recv[q], vk2);
-            // the samples of one scatterer are a geometric sequence u v^k, and any such sequence obeys the three-term
-            // recurrence p[k+1] = 2 cos(delta) p[k] - p[k-1] (v + 1/v = 2 cos delta): TWO FMAs per new complex term instead
-            // of the four of a complex multiply.  Two chains run outward from the centre sample (forward f, backward b),
-            // real and imaginary parts independently: four independent FMA chains per scatterer.  The recurrence amplifies
-            // an error of the coefficient by at most k^2 / 2 over k steps; k <= SPT/2 here (<= 3e-5 relative, reached only
-            // where the chirp's instantaneous frequency is near zero).
-            const float c2 = 2.0f * v.x;
-            float2 f0 = u, f1 = cmul_pk(u, v);
-            float2 b0 = cmul_conj_pk(u, v), b1 = cfms_pk(c2, b0, u);
-            if (t_lo >= lo && t_hi <= hi) {
-#pragma unroll
-                for (int i = 0; i < HALF; i += 2) {
-                    acc[HALF + i] = cadd_pk(acc[HALF + i], f0);
-                    acc[HALF + i + 1] = cadd_pk(acc[HALF + i + 1], f1);
-                    acc[HALF - 1 - i] = cadd_pk(acc[HALF - 1 - i], b0);
-                    acc[HALF - 2 - i] = cadd_pk(acc[HALF - 2 - i], b1);
-                    if (i + 2 < HALF) {
-                        f0 = cfms_pk(c2, f1, f0);
-                        f1 = cfms_pk(c2, f0, f1);
-                        b0 = cfms_pk(c2, b1, b0);
-                        b1 = cfms_pk(c2, b0, b1);
-                    }
-                }
-            } else {
-                const int a = lo - t_lo, b = hi - t_lo;   // live samples: a <= j < b
-#pragma unroll
-                for (int i = 0; i < HALF; i += 2) {
-                    int j = HALF + i;
-                    if (j >= a && j < b) acc[j] = cadd(acc[j], f0);
-                    j = HALF + i + 1;
-                    if (j >= a && j < b) acc[j] = cadd(acc[j], f1);
-                    j = HALF - 1 - i;
-                    if (j >= a && j < b) acc[j] = cadd(acc[j], b0);
-                    j = HALF - 2 - i;
-                    if (j >= a && j < b) acc[j] = cadd(acc[j], b1);
-                    if (i + 2 < HALF) {
-                        f0 = cfms_pk(c2, f1, f0);
-                        f1 = cfms_pk(c2, f0, f1);
-                        b0 = cfms_pk(c2, b1, b0);
-                        b1 = cfms_pk(c2, b0, b1);
-                    }
-                }
-            }
-        }
+        accumulate_kept<SPT>(acc, rec, recv, total, t_lo, t_hi, mt, k1, vk2);
     }
 
     // ------------------------------------------------ epilogue: common quadratic factor, store
@@ -272,6 +419,17 @@ int launch_echo(nis_ctx* ctx, const EchoConst& k, const double* pos0, const doub
     }
     const EchoShape sh = echo_shape(k.S, SPT);
     dim3 grid(sh.chunks, n_pulses);
+    // sparse scenes: one CTA per pulse, geometry once per (scatterer, pulse).  Needs enough pulses to fill the GPU and rows
+    // whose 16-byte vector stores are aligned (S even); NIS_ECHO_SPARSE=0 disables it (development knob)
+    const char* sparse_env = getenv("NIS_ECHO_SPARSE");
+    const bool sparse_ok = !(sparse_env && sparse_env[0] == '0');
+    if (sparse_ok && !k.spotlight && k.T > 0 && k.T <= 256 && n_pulses >= 2 * ctx->num_sms && (k.S % 2) == 0 &&
+        (((uintptr_t)raw) & 15) == 0) {
+        const int n_chunks = (k.S + 256 * SPT - 1) / (256 * SPT);
+        k_echo_sparse<SPT><<<n_pulses, 256, 0, st>>>(k, tail, pos0, vel, amp, pos_tx, pos_rx, t_slow, t_fast, raw, n_chunks);
+        NIS_LAUNCH_CHECK(ctx);
+        return NIS_OK;
+    }
     if (k.spotlight) k_echo<SPT, true, false><<<grid, sh.threads, 0, st>>>(k, tail, pos0, vel, amp, pos_tx, pos_rx, t_slow, t_fast, raw);
     else if (sh.threads == 256) k_echo<SPT, false, true><<<grid, 256, 0, st>>>(k, tail, pos0, vel, amp, pos_tx, pos_rx, t_slow, t_fast, raw);
     else k_echo<SPT, false, false><<<grid, sh.threads, 0, st>>>(k, tail, pos0, vel, amp, pos_tx, pos_rx, t_slow, t_fast, raw);

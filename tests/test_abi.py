@@ -33,8 +33,8 @@ def test_version_and_struct_layouts():
     assert C.sizeof(_lib.EchoParams) == 56
     assert C.sizeof(_lib.CsaParams) == 64
     assert C.sizeof(_lib.GmtiResult) == 16
-    # K3 workspace: 16-byte header + one 64-bit status word per 2048-pixel tile
-    assert lib.nis_gmti_workspace_bytes(1) == 24 and lib.nis_gmti_workspace_bytes(4096 * 4096) == 16 + 8 * 8192
+    # K3 workspace: 16-byte header + per 2048-pixel tile a 256-byte detection bitmap, a count and an arg-max candidate
+    assert lib.nis_gmti_workspace_bytes(1) == 16 + 264 and lib.nis_gmti_workspace_bytes(4096 * 4096) == 16 + 264 * 8192
 
 
 def test_no_cpu_fallback():
