@@ -554,6 +554,9 @@ using P2048 = Plan<2048, 16, 16, 16, 8>;
 using P4096 = Plan<4096, 16, 16, 16, 16>;
 using P8192 = Plan<8192, 16, 16, 8, 8, 8>;
 using P16384 = Plan<16384, 16, 16, 16, 8, 8>;
+// 8192 samples, 32 per thread: three passes (two shared-memory exchanges per transform instead of three) on 256 threads that
+// may use the whole register file (one CTA per SM either way) -- the default at 8192 samples
+using P8192E32 = Plan<8192, 32, 32, 16, 16>;
 
 template <class P>
 int upload_twiddles(float2** dev) {
@@ -943,7 +946,18 @@ extern "C" int nis_csa_plan_create(nis_ctx* ctx, int32_t n_az, int32_t n_rg, con
         // one row per CTA, several CTAs per SM: independent CTAs drift out of phase, so one CTA's shared-memory exchange
         // overlaps another's butterflies (measured: 0.096 vs 0.104 ms at 4096^2 against two row groups inside one CTA)
         case 4096: pl->range = launch_range<P4096, 4, 1, 2>; FAIL_IF(upload_twiddles<P4096>(&pl->tw_rg)); break;
-        case 8192: pl->range = launch_range<P8192, 4, 1, 1>; FAIL_IF(upload_twiddles<P8192>(&pl->tw_rg)); break;
+        case 8192:
+            // 32 samples per thread (three passes, 256 threads x 213 registers, no spills): 0.417 ms against 0.457 ms for the
+            // 16-sample four-pass plan at 8192^2 (profiles/kbench_r2e.jsonl); packed fp32x2 on top of it: 0.423 ms, not used.
+            // NIS_RANGE_PLAN=e16 selects the old plan (development knob, both are parity-tested)
+            if (const char* v = getenv("NIS_RANGE_PLAN"); v && v[0] == 'e' && v[1] == '1') {
+                pl->range = launch_range<P8192, 4, 1, 1>;
+                FAIL_IF(upload_twiddles<P8192>(&pl->tw_rg));
+            } else {
+                pl->range = launch_range<P8192E32, 5, 1, 1>;
+                FAIL_IF(upload_twiddles<P8192E32>(&pl->tw_rg));
+            }
+            break;
         default: pl->range = launch_range<P16384, 4, 1, 1>; FAIL_IF(upload_twiddles<P16384>(&pl->tw_rg)); break;
     }
     FAIL_IF(upload_full_twiddles(pl));

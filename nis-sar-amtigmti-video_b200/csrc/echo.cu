@@ -133,8 +133,11 @@ __device__ __forceinline__ void chirp_support(const EchoConst& k, const double* 
 // Sparse scenes (T <= 256 scatterers: point-target grids, a single ship): ONE CTA per pulse walks all chunks of the window.
 // The fp64 geometry -- position, two norms, delay, exact chirp support -- is evaluated once per (scatterer, pulse) and kept
 // in shared memory; per chunk only the phase polynomial about the chunk centre is re-expanded (a dozen fp64 operations).
-// k_echo spends a quarter of its instructions on that geometry when every chunk-CTA of a pulse repeats it for a handful
-// of scatterers (bench scene, 81 scatterers x 2 chunks: 299 M warp instructions, profiles/prof_echo_r1.txt).
+// Measured on the bench scene (81 scatterers, 8192 x 8192): 263 M instead of 299 M warp instructions, 0.42 instead of
+// 0.49 ms, no spills at 72 registers (profiles/prof_echo_sparse_r2.txt).  What remains is the inner loop itself: per
+// (scatterer, warp) 13 instructions of loop control, 21 of per-scatterer set-up, 29 for the sixteen samples.  Tried and
+// rejected (measured slower): 32 samples per thread (113 registers, two CTAs per SM: 0.64 ms), per-warp work lists that
+// skip non-intersecting (scatterer, warp) pairs plus a bit-mask form of the edge path (+4 % on all three scenes).
 template <int SPT>
 __global__ void __launch_bounds__(256, 3) k_echo_sparse(EchoConst k, EchoTail<SPT> tail, const double* __restrict__ pos0,
                                                         const double* __restrict__ vel, const double* __restrict__ amp,
