@@ -141,8 +141,8 @@ NIS_API int nis_csa_size_class(int32_t n_az, int32_t n_rg);
 NIS_API int nis_csa_axes(const nis_csa_plan* plan, double* range_axis, double* cross_range);
 /* phist: dev [n_az][pitch] complex64, pitch in elements (>= n_rg).  The DPCA co-registration of
  * :402-403 (rx1[1:], rx2[:-1]) is a pointer offset of one row by the caller.
- * slc: dev [n_rg][n_az].  max_sq (optional, dev, 1 double, zeroed by the caller): max |slc|^2 evaluated in
- * fp64 on the stored fp32 samples, accumulated with max -- hand it to nis_gmti_fused to skip its first pass. */
+ * slc: dev [n_rg][n_az].  max_sq (optional, dev, 1 double, reset by the call on the same stream): max |slc|^2 evaluated
+ * in fp64 on the stored fp32 samples -- hand it to nis_gmti_fused to skip its pass over slc1. */
 NIS_API int nis_csa_focus(nis_csa_plan* plan, const nis_c32* phist, int64_t pitch, nis_c32* slc,
                   double* max_sq, nis_stream stream);
 

@@ -978,6 +978,7 @@ extern "C" int nis_csa_focus(nis_csa_plan* pl, const nis_c32* phist, int64_t pit
     NIS_REQUIRE(pl && phist && slc, "nis_csa_focus: null argument");
     NIS_REQUIRE(pitch >= pl->n_rg, "nis_csa_focus: pitch %lld < n_rg %d", (long long)pitch, pl->n_rg);
     cudaStream_t st = (cudaStream_t)stream;
+    if (max_sq != nullptr) NIS_CUDA_TRY(cudaMemsetAsync(max_sq, 0, sizeof(double), st));   // the last kernel accumulates with max
     if (pl->size_class == 2)
         return generic_focus(pl, reinterpret_cast<const float2*>(phist), pitch, reinterpret_cast<float2*>(slc), max_sq, st);
     cudaEvent_t* ev = pl->profiling ? pl->prof_ev[pl->prof_calls % nis_csa_plan::kProfRing] : nullptr;

@@ -404,7 +404,9 @@ using P256 = Plan<256, 16, 16, 16, 1>;
 using P1024 = Plan<1024, 16, 16, 8, 8>;
 using P4096 = Plan<4096, 16, 16, 16, 16>;
 using P16384 = Plan<16384, 32, 32, 32, 16>;
-using P8192H = Plan<8192, 16, 16, 8, 8, 8>;
+// half-length transforms of the pruned Bluestein core: 32 samples per thread, three passes (as the 8192-sample range kernel)
+using P8192H = Plan<8192, 32, 32, 16, 16>;
+constexpr int kPad8192H = 5;
 
 void host_fft(std::vector<std::complex<double>>& a) {   // in-place radix-2, forward
     const size_t n = a.size();
@@ -547,7 +549,7 @@ template <int MODE>
 int launch_row(nis_ctx* ctx, const GenLen& g, float2* data, int64_t pitch, int n_rows, const RowCoef* coef,
                float scale, double* max_sq, cudaStream_t st) {
     if (g.kind == 1 && g.bfe != nullptr && MODE != RANGE && !getenv("NIS_BLUE_NOPRUNE")) {
-        constexpr int PAD = 4;
+        constexpr int PAD = kPad8192H;
         constexpr int SMROW = P8192H::N + (P8192H::N >> PAD);
         const size_t smem = (size_t)(SMROW + 2 * P8192H::N) * sizeof(float2);
         static bool attr_done_dev[64] = {};

@@ -142,7 +142,7 @@ class CsaPlan:
     def focus(self, phist, out=None, max_sq=None):
         """phist: complex64 CUDA tensor [n_az, n_rg] (rows may be strided: a ``raw[1:]`` view is fine).
         Returns slc [n_rg, n_az] complex64 -- the array the reference returns as ``img.T``.  ``max_sq``: optional
-        1-element float64 CUDA tensor, zeroed here, that receives max |slc|^2 (exact, for ``gmti_fused``)."""
+        1-element float64 CUDA tensor that receives max |slc|^2 (exact, for ``gmti_fused``; reset by the library)."""
         if phist.dtype != torch.complex64 or phist.dim() != 2 or phist.stride(1) != 1:
             raise NisError("CsaPlan.focus: phist must be a complex64 [n_az, n_rg] tensor with unit column stride")
         if tuple(phist.shape) != (self.n_az, self.n_rg):
@@ -150,10 +150,8 @@ class CsaPlan:
         if out is None:
             out = torch.empty((self.n_rg, self.n_az), dtype=torch.complex64, device=phist.device)
         with torch.cuda.device(self.di):
-            if max_sq is not None:
-                if max_sq.dtype != torch.float64 or max_sq.numel() != 1:
-                    raise NisError("CsaPlan.focus: max_sq must be a 1-element float64 tensor")
-                max_sq.zero_()
+            if max_sq is not None and (max_sq.dtype != torch.float64 or max_sq.numel() != 1):
+                raise NisError("CsaPlan.focus: max_sq must be a 1-element float64 tensor")
             rc = _lib.load().nis_csa_focus(self._h, _ptr(phist), phist.stride(0), _ptr(out), _ptr(max_sq),
                                            C.c_void_p(_stream_ptr(self.di)))
         _lib.check(rc, "nis_csa_focus")
@@ -380,13 +378,38 @@ def peak_power(x):
 GMTI_PRODUCTS = ("ati_interf", "ati_phase", "dpca_diff", "dpca_mag", "slc1_mag", "mag_mask", "ati_phase_masked")
 
 
+_GMTI_DTYPES = {"ati_interf": torch.complex64, "ati_phase": torch.float32, "dpca_diff": torch.complex64,
+                "dpca_mag": torch.float32, "slc1_mag": torch.float32, "mag_mask": torch.uint8, "ati_phase_masked": torch.float32}
+
+
+class GmtiBuffers:
+    """Pre-allocated outputs of ``gmti_fused`` for one frame shape: the requested product maps, the detection list, the
+    library's workspace and the 16-byte result record.  A VideoSAR loop that forms a pair per frame passes the same
+    object every time (``gmti_fused(..., buffers=b, lazy=True)``): nothing is allocated per frame.  One object per
+    stream -- two calls that may run concurrently must not share it."""
+
+    def __init__(self, shape, want=GMTI_PRODUCTS, det_cap=None, device="cuda"):
+        di = _dev_index(device)
+        dev = torch.device("cuda", di)
+        self.shape = tuple(int(v) for v in shape)
+        n = int(np.prod(self.shape))
+        self.want = tuple(want)
+        self.products = {k: torch.empty(self.shape, dtype=_GMTI_DTYPES[k], device=dev) for k in self.want}
+        self.cap = n if det_cap is None else int(det_cap)
+        self.det = torch.empty((max(self.cap, 1),), dtype=torch.int32, device=dev)
+        self.ws_bytes = int(_lib.load().nis_gmti_workspace_bytes(n))
+        self.ws = torch.empty(((self.ws_bytes + 7) // 8,), dtype=torch.int64, device=dev)
+        self.result = torch.empty((2,), dtype=torch.int64, device=dev).view(torch.uint8)
+
+
 def gmti_fused(slc1, slc2, thresh_frac=0.05, cal_phase=0.0, want=GMTI_PRODUCTS, det_cap=None, max_sq=None,
-               lazy=False):
+               lazy=False, buffers: "GmtiBuffers | None" = None):
     """K3.  slc1/slc2: complex64 CUDA tensors of one shape.  Returns a dict with the requested
     product tensors (``max_sq``: optional 1-element float64 CUDA tensor filled by ``CsaPlan.focus(..., max_sq=)``
     for slc1 -- skips the max pass) plus ``det_idx`` (uint32 -> int64 tensor of flat indices, ascending),
     ``det_count``, ``peak_idx``, ``max_mag`` (python scalars; reading them synchronises).  ``lazy=True`` skips
-    that read-back and returns the raw device buffers (``det_idx_raw``, ``result_dev``) instead."""
+    that read-back and returns the raw device buffers (``det_idx_raw``, ``result_dev``) instead.  ``buffers``: a
+    ``GmtiBuffers`` of the same shape -- its tensors are written and returned, ``want`` / ``det_cap`` come from it."""
     if slc1.dtype != torch.complex64 or slc2.dtype != torch.complex64 or slc1.shape != slc2.shape:
         raise NisError("gmti_fused: slc1 and slc2 must be complex64 tensors of the same shape")
     if not (slc1.is_contiguous() and slc2.is_contiguous()):
@@ -396,10 +419,14 @@ def gmti_fused(slc1, slc2, thresh_frac=0.05, cal_phase=0.0, want=GMTI_PRODUCTS, 
     n = slc1.numel()
     shape = tuple(slc1.shape)
     outs = {}
+    if buffers is not None:
+        if buffers.shape != shape or buffers.det.device != dev:
+            raise NisError(f"gmti_fused: buffers are for shape {buffers.shape} on {buffers.det.device}, got {shape} on {dev}")
+        want, det_cap = buffers.want, buffers.cap
     with torch.cuda.device(di):
         def alloc(name, dtype):
             if name in want:
-                outs[name] = torch.empty(shape, dtype=dtype, device=dev)
+                outs[name] = buffers.products[name] if buffers is not None else torch.empty(shape, dtype=dtype, device=dev)
                 return outs[name]
             return None
         interf = alloc("ati_interf", torch.complex64)
@@ -410,13 +437,16 @@ def gmti_fused(slc1, slc2, thresh_frac=0.05, cal_phase=0.0, want=GMTI_PRODUCTS, 
         mask = alloc("mag_mask", torch.uint8)
         pmask = alloc("ati_phase_masked", torch.float32)
         cap = n if det_cap is None else int(det_cap)
-        det = torch.empty((max(cap, 1),), dtype=torch.int32, device=dev)
         lib = _lib.load()
-        # per-call workspace and result record from torch's stream-ordered allocator (nothing is zero-filled here: the
-        # library initialises both); concurrent calls on other streams get their own
-        ws_bytes = int(lib.nis_gmti_workspace_bytes(n))
-        ws = torch.empty(((ws_bytes + 7) // 8,), dtype=torch.int64, device=dev)
-        res = torch.empty((2,), dtype=torch.int64, device=dev).view(torch.uint8)
+        if buffers is not None:
+            det, ws_bytes, ws, res = buffers.det, buffers.ws_bytes, buffers.ws, buffers.result
+        else:
+            # per-call workspace and result record from torch's stream-ordered allocator (nothing is zero-filled here:
+            # the library writes both); concurrent calls on other streams get their own
+            det = torch.empty((max(cap, 1),), dtype=torch.int32, device=dev)
+            ws_bytes = int(lib.nis_gmti_workspace_bytes(n))
+            ws = torch.empty(((ws_bytes + 7) // 8,), dtype=torch.int64, device=dev)
+            res = torch.empty((2,), dtype=torch.int64, device=dev).view(torch.uint8)
         rc = lib.nis_gmti_fused(_lib.context(di), _ptr(slc1), _ptr(slc2), n, float(thresh_frac),
                                 float(cal_phase), _ptr(interf), _ptr(phase), _ptr(diff), _ptr(dmag),
                                 _ptr(mag1), _ptr(mask), _ptr(pmask), _ptr(det), cap, _ptr(max_sq), _ptr(ws), ws_bytes,
