@@ -53,7 +53,7 @@ struct GenLen {
     int N = 0, kind = 0 /* 0 mixed, 1 Bluestein */, npass = 0, M = 0;
     int radix[kMaxPass] = {};
     float2 *twN = nullptr, *chirp = nullptr, *bfft = nullptr, *tw_pow2 = nullptr;
-    float2 *bfe = nullptr, *bfo = nullptr, *twm = nullptr, *tw_half = nullptr;
+    float2 *bfe = nullptr, *bfo = nullptr, *twm = nullptr, *tw_half = nullptr, *tw_half32 = nullptr;
     float2* ct_tw = nullptr;   // per-pass tables of the compile-time plan (mixed_ct.cuh), when the length has one
     GenDev dev() const {
         GenDev d{};
@@ -70,7 +70,7 @@ struct GenLen {
     }
     void release() {
         cudaFree(twN); cudaFree(chirp); cudaFree(bfft); cudaFree(tw_pow2);
-        cudaFree(bfe); cudaFree(bfo); cudaFree(twm); cudaFree(tw_half); cudaFree(ct_tw);
+        cudaFree(bfe); cudaFree(bfo); cudaFree(twm); cudaFree(tw_half); cudaFree(tw_half32); cudaFree(ct_tw);
     }
 };
 
@@ -404,9 +404,10 @@ using P256 = Plan<256, 16, 16, 16, 1>;
 using P1024 = Plan<1024, 16, 16, 8, 8>;
 using P4096 = Plan<4096, 16, 16, 16, 16>;
 using P16384 = Plan<16384, 32, 32, 32, 16>;
-// half-length transforms of the pruned Bluestein core: 32 samples per thread, three passes (as the 8192-sample range kernel)
-using P8192H = Plan<8192, 32, 32, 16, 16>;
-constexpr int kPad8192H = 5;
+// half-length transforms of the pruned Bluestein core: 16 samples per thread, four passes; NIS_BLUE_PLAN=e32 selects the
+// 32-sample three-pass plan of the 8192-sample range kernel (development knob)
+using P8192H = Plan<8192, 16, 16, 8, 8, 8>;
+using P8192H32 = Plan<8192, 32, 32, 16, 16>;
 
 void host_fft(std::vector<std::complex<double>>& a) {   // in-place radix-2, forward
     const size_t n = a.size();
@@ -515,6 +516,7 @@ int build_length(int n, GenLen* g) {
         if ((rc = upload(bo, &g->bfo)) != NIS_OK) return rc;
         if ((rc = upload(tm, &g->twm)) != NIS_OK) return rc;
         if ((rc = upload_pow2_twiddles<P8192H>(&g->tw_half)) != NIS_OK) return rc;
+        if ((rc = upload_pow2_twiddles<P8192H32>(&g->tw_half32)) != NIS_OK) return rc;
     }
     switch (M) {
         case 64: return upload_pow2_twiddles<P64>(&g->tw_pow2);
@@ -545,25 +547,33 @@ int launch_blue(nis_ctx* ctx, const GenLen& g, float2* data, int64_t pitch, int 
     return NIS_OK;
 }
 
+template <int MODE, class P, int PAD>
+int launch_blue_pruned(nis_ctx* ctx, const GenLen& g, float2* data, int64_t pitch, int n_rows, float scale, double* max_sq,
+                       cudaStream_t st) {
+    constexpr int SMROW = P::N + (P::N >> PAD);
+    const size_t smem = (size_t)(SMROW + 2 * P::N) * sizeof(float2);
+    static bool attr_done_dev[64] = {};
+    bool& attr_done = attr_done_dev[nis::current_device() & 63];
+    if (!attr_done) {
+        NIS_CUDA_TRY(cudaFuncSetAttribute(k_row_blue_pruned<MODE, P, PAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_done = true;
+    }
+    int grid = ctx->num_sms;
+    if (grid > n_rows) grid = n_rows;
+    GenDev d = g.dev();
+    if (P::E == 32) d.tw_half = g.tw_half32;
+    k_row_blue_pruned<MODE, P, PAD><<<grid, P::NT, smem, st>>>(d, data, pitch, n_rows, scale, max_sq);
+    NIS_LAUNCH_CHECK(ctx);
+    return NIS_OK;
+}
+
 template <int MODE>
 int launch_row(nis_ctx* ctx, const GenLen& g, float2* data, int64_t pitch, int n_rows, const RowCoef* coef,
                float scale, double* max_sq, cudaStream_t st) {
     if (g.kind == 1 && g.bfe != nullptr && MODE != RANGE && !getenv("NIS_BLUE_NOPRUNE")) {
-        constexpr int PAD = kPad8192H;
-        constexpr int SMROW = P8192H::N + (P8192H::N >> PAD);
-        const size_t smem = (size_t)(SMROW + 2 * P8192H::N) * sizeof(float2);
-        static bool attr_done_dev[64] = {};
-        bool& attr_done = attr_done_dev[nis::current_device() & 63];
-        if (!attr_done) {
-            NIS_CUDA_TRY(cudaFuncSetAttribute(k_row_blue_pruned<MODE, P8192H, PAD>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                              (int)smem));
-            attr_done = true;
-        }
-        int grid = ctx->num_sms;
-        if (grid > n_rows) grid = n_rows;
-        k_row_blue_pruned<MODE, P8192H, PAD><<<grid, P8192H::NT, smem, st>>>(g.dev(), data, pitch, n_rows, scale, max_sq);
-        NIS_LAUNCH_CHECK(ctx);
-        return NIS_OK;
+        const char* bp = getenv("NIS_BLUE_PLAN");
+        if (bp && bp[0] == 'e' && bp[1] == '3') return launch_blue_pruned<MODE, P8192H32, 5>(ctx, g, data, pitch, n_rows, scale, max_sq, st);
+        return launch_blue_pruned<MODE, P8192H, 4>(ctx, g, data, pitch, n_rows, scale, max_sq, st);
     }
     if (g.kind == 1) {
         switch (g.M) {
