@@ -5,17 +5,18 @@ CUDA library or a device is missing (no CPU fallback)."""
 from .params import RadarParams, spaceborne_preset, airborne_vehicle_preset  # noqa: F401
 from . import targets, scenes  # noqa: F401
 
-_LAZY = {"run_bistatic_physics_gpu", "sar_focus_csa", "run_physics_engine", "run_moving_physics",
-         "run_custom_physics", "gmti_products", "dpca_coregister", "install", "set_default_params",
-         "save_ati_dpca_npz",
-         "set_default_device"}
+_SUBMODULES = ("device", "api", "dist", "hostio", "viewer", "video")
 
 
 def __getattr__(name):
-    if name in _LAZY:
-        from . import api
-        return getattr(api, name)
-    if name in ("device", "api", "dist", "pipeline"):
+    """Everything public in ``nis_sar.api`` (the reference's entry points: run_bistatic_physics_gpu, sar_focus_csa,
+    sar_focus_rda, gmti_products, add_ocean_noise, tdbp_gpu, install, ...) is reachable as ``nis_sar.<name>``; torch and the
+    CUDA library are only imported when one of them is first used."""
+    if name in _SUBMODULES:
         import importlib
         return importlib.import_module(f"{__name__}.{name}")
-    raise AttributeError(name)
+    if not name.startswith("_"):
+        from . import api
+        if hasattr(api, name):
+            return getattr(api, name)
+    raise AttributeError(f"module {__name__!r} has no attribute {name!r}")
