@@ -47,7 +47,18 @@ struct GenDev {   // by-value kernel argument
     const float2* bfo;
     const float2* twm;
     const float2* tw_half;
+    uint64_t chirp_k;       // round(2^64 / 2N): n^2 * chirp_k >> 32 = (n^2 / 2N mod 1) in 2^-32 turns (integer wrap-around)
+    int twm_shift;          // 32 - log2(M): n << twm_shift = n / M in 2^-32 turns
 };
+
+// Bluestein chirp a[n] = exp(-i pi n^2 / N) and modulation w_M^n = exp(-2 pi i n / M) evaluated on the fly (two MUFU
+// operations each) instead of read from tables: the pruned core touches them four times per element, 256 KB per row that
+// no L1 could hold beside 196 KB of shared memory -- ncu showed the stage waiting on L2 for them (long_scoreboard 37 %).
+__device__ __forceinline__ float2 blue_chirp(const GenDev& g, uint32_t n) {
+    const uint32_t u = (uint32_t)(((uint64_t)(n * n) * g.chirp_k) >> 32);
+    return cis_u32(0u - u);
+}
+__device__ __forceinline__ float2 blue_twm(const GenDev& g, uint32_t n) { return cis_u32(0u - (n << g.twm_shift)); }
 
 struct GenLen {
     int N = 0, kind = 0 /* 0 mixed, 1 Bluestein */, npass = 0, M = 0;
@@ -66,6 +77,9 @@ struct GenLen {
         }
         d.twN = twN; d.chirp = chirp; d.bfft = bfft; d.tw_pow2 = tw_pow2;
         d.bfe = bfe; d.bfo = bfo; d.twm = twm; d.tw_half = tw_half;
+        d.chirp_k = N > 0 ? (uint64_t)((((unsigned __int128)1 << 64) + (unsigned)N) / (2u * (unsigned)N)) : 0;
+        d.twm_shift = 32;
+        for (int m = M; m > 1; m >>= 1) --d.twm_shift;
         return d;
     }
     void release() {
@@ -313,7 +327,7 @@ __global__ void __launch_bounds__(P::NT) k_row_blue(GenDev g, float2* __restrict
 // M-point circular convolution splits into even / odd spectral bins -- two H-point transforms of u and u w_M^n, two H-point
 // inverses A, B, y[n] = A[n] + w_M^-n B[n] -- on the 16-elements-per-thread plan instead of the 32-element one.  u and A
 // are parked in shared memory (each thread re-reads only its own elements).
-template <class P, int PAD, bool INV>
+template <class P, int PAD, bool INV, bool FLY>
 __device__ __forceinline__ void bluestein_core_pruned(float2* v, int t, float2* sm, float2* park_u, float2* park_a,
                                                       const GenDev& g) {
     constexpr int E = P::E, NT = P::NT;
@@ -335,7 +349,7 @@ __device__ __forceinline__ void bluestein_core_pruned(float2* v, int t, float2* 
 #pragma unroll
             for (int s = 0; s < E; ++s) {
                 park_a[t + NT * s] = v[s];
-                v[s] = cmul(park_u[t + NT * s], __ldg(g.twm + t + NT * s));
+                v[s] = cmul(park_u[t + NT * s], FLY ? blue_twm(g, (uint32_t)(t + NT * s)) : __ldg(g.twm + t + NT * s));
             }
             __syncthreads();
         }
@@ -345,10 +359,10 @@ __device__ __forceinline__ void bluestein_core_pruned(float2* v, int t, float2* 
         const int idx = t + NT * s;
         float2 y = make_float2(0.f, 0.f);
         if (idx < g.N) {
-            const float2 c = cmul_conj(v[s], __ldg(g.twm + idx));
+            const float2 c = cmul_conj(v[s], FLY ? blue_twm(g, (uint32_t)idx) : __ldg(g.twm + idx));
             const float2 a = park_a[idx];
             y = make_float2(a.x + c.x, a.y + c.y);
-            const float2 ch = __ldg(g.chirp + idx);
+            const float2 ch = FLY ? blue_chirp(g, (uint32_t)idx) : __ldg(g.chirp + idx);
             y = INV ? cmul_conj(y, ch) : cmul(y, ch);
         }
         v[s] = y;
@@ -357,7 +371,7 @@ __device__ __forceinline__ void bluestein_core_pruned(float2* v, int t, float2* 
 }
 
 // azimuth transforms (AZ_FWD / AZ_INV) of rows whose length takes the pruned Bluestein core
-template <int MODE, class P, int PAD>
+template <int MODE, class P, int PAD, bool FLY>
 __global__ void __launch_bounds__(P::NT) k_row_blue_pruned(GenDev g, float2* __restrict__ data, int64_t pitch, int n_rows,
                                                            float scale, double* __restrict__ max_sq) {
     extern __shared__ float2 sm[];
@@ -375,13 +389,13 @@ __global__ void __launch_bounds__(P::NT) k_row_blue_pruned(GenDev g, float2* __r
             const int idx = t + NT * s;
             float2 x = make_float2(0.f, 0.f);
             if (idx < g.N) {
-                const float2 a = __ldg(g.chirp + idx);
+                const float2 a = FLY ? blue_chirp(g, (uint32_t)idx) : __ldg(g.chirp + idx);
                 x = (MODE == AZ_INV) ? cmul_conj(p[idx], a) : cmul(p[idx], a);
             }
             v[s] = x;
         }
-        if (MODE == AZ_INV) bluestein_core_pruned<P, PAD, true>(v, t, sm, park_u, park_a, g);
-        else bluestein_core_pruned<P, PAD, false>(v, t, sm, park_u, park_a, g);
+        if (MODE == AZ_INV) bluestein_core_pruned<P, PAD, true, FLY>(v, t, sm, park_u, park_a, g);
+        else bluestein_core_pruned<P, PAD, false, FLY>(v, t, sm, park_u, park_a, g);
 #pragma unroll
         for (int s = 0; s < E; ++s) {
             const int idx = t + NT * s;
@@ -547,22 +561,23 @@ int launch_blue(nis_ctx* ctx, const GenLen& g, float2* data, int64_t pitch, int 
     return NIS_OK;
 }
 
-template <int MODE, class P, int PAD>
+template <int MODE, class P, int PAD, bool FLY>
 int launch_blue_pruned(nis_ctx* ctx, const GenLen& g, float2* data, int64_t pitch, int n_rows, float scale, double* max_sq,
                        cudaStream_t st) {
+    auto kern = k_row_blue_pruned<MODE, P, PAD, FLY>;
     constexpr int SMROW = P::N + (P::N >> PAD);
     const size_t smem = (size_t)(SMROW + 2 * P::N) * sizeof(float2);
     static bool attr_done_dev[64] = {};
     bool& attr_done = attr_done_dev[nis::current_device() & 63];
     if (!attr_done) {
-        NIS_CUDA_TRY(cudaFuncSetAttribute(k_row_blue_pruned<MODE, P, PAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        NIS_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr_done = true;
     }
     int grid = ctx->num_sms;
     if (grid > n_rows) grid = n_rows;
     GenDev d = g.dev();
     if (P::E == 32) d.tw_half = g.tw_half32;
-    k_row_blue_pruned<MODE, P, PAD><<<grid, P::NT, smem, st>>>(d, data, pitch, n_rows, scale, max_sq);
+    kern<<<grid, P::NT, smem, st>>>(d, data, pitch, n_rows, scale, max_sq);
     NIS_LAUNCH_CHECK(ctx);
     return NIS_OK;
 }
@@ -572,8 +587,9 @@ int launch_row(nis_ctx* ctx, const GenLen& g, float2* data, int64_t pitch, int n
                float scale, double* max_sq, cudaStream_t st) {
     if (g.kind == 1 && g.bfe != nullptr && MODE != RANGE && !getenv("NIS_BLUE_NOPRUNE")) {
         const char* bp = getenv("NIS_BLUE_PLAN");
-        if (bp && bp[0] == 'e' && bp[1] == '3') return launch_blue_pruned<MODE, P8192H32, 5>(ctx, g, data, pitch, n_rows, scale, max_sq, st);
-        return launch_blue_pruned<MODE, P8192H, 4>(ctx, g, data, pitch, n_rows, scale, max_sq, st);
+        if (bp && bp[0] == 'e' && bp[1] == '3') return launch_blue_pruned<MODE, P8192H32, 5, true>(ctx, g, data, pitch, n_rows, scale, max_sq, st);
+        if (getenv("NIS_BLUE_TABLES")) return launch_blue_pruned<MODE, P8192H, 4, false>(ctx, g, data, pitch, n_rows, scale, max_sq, st);
+        return launch_blue_pruned<MODE, P8192H, 4, true>(ctx, g, data, pitch, n_rows, scale, max_sq, st);
     }
     if (g.kind == 1) {
         switch (g.M) {
