@@ -276,12 +276,55 @@ def golden_csa_large():
     np.savez_compressed(os.path.join(OUT, "csa_large.npz"), **out)
 
 
+def golden_chain_4096():
+    """The north-star frame at its real size through the UNMODIFIED reference: two-channel echo of the destroyer + 40 clutter
+    scatterers (run_bistatic_physics_gpu x 4, 4097 pulses x 4096 samples -- FS chosen so that int(22e-6 FS) = 4096), pulse
+    shift, sar_focus_csa x 2 at 4096 x 4096, the inline ATI / DPCA block.  ~3 min here; stored as digests."""
+    from oracle import inputs
+    fs = 4096.5 / 22e-6
+    prm = params.spaceborne_preset(fs=fs, bw=150e6)
+    assert int(22e-6 * prm.FS) == 4096
+    P = 4097
+    sc = scenes.ati_scene(seed=41, num_pulses=P, num_clutter=40, prm=prm, t_int=None)
+    bist, csa = ref_extract.ati_csa_functions(prm.as_globals())
+    ship = _as_targets(sc["ship_pos"], sc["ship_rcs"])
+    clut = _as_targets(sc["clutter_pos"], sc["clutter_rcs"])
+    raws = []
+    for off in sc["rx_offsets"]:
+        a, t0 = bist(ship, sc["t_vec"], sc["pos_tx"], sc["vel_tx"], off, sc["ship_vel"])
+        b, _ = bist(clut, sc["t_vec"], sc["pos_tx"], sc["vel_tx"], off, sc["clutter_vel"])
+        raws.append(a + b)
+        print("echo channel done", raws[-1].shape, flush=True)
+    rx1, rx2 = raws[0][1:, :], raws[1][:-1, :]
+    slc1, rax, cax = csa(rx1, prm.Lambda, prm.T_p, prm.k_rate, prm.FS, prm.PRF, prm.V_eff, prm.R0, t0)
+    slc2, _, _ = csa(rx2, prm.Lambda, prm.T_p, prm.k_rate, prm.FS, prm.PRF, prm.V_eff, prm.R0, t0)
+    prod = ref_extract.ati_inline_products(slc1, slc2)
+    mag = prod["slc1_mag"]
+    thr = mag.max() * 0.05
+    out = {"seed": 41, "num_pulses": P, "num_clutter": 40, "fs": fs, "bw": 150e6, "t_start_fast": t0, "rax": rax, "cax": cax}
+    d = inputs.image_digest(np.ascontiguousarray(raws[0]), 4099)
+    out.update({f"raw1_{k}": (v.astype(np.complex64) if k in ("dec", "rows", "cols") else v) for k, v in d.items()})
+    for tag, img in (("slc1", slc1), ("slc2", slc2), ("interf", prod["ati_interf"]), ("dpca", prod["dpca_diff"])):
+        d = inputs.image_digest(np.ascontiguousarray(img), 4099)
+        out.update({f"{tag}_{k}": (v.astype(np.complex64) if k in ("dec", "rows", "cols") else v) for k, v in d.items()})
+    out["det_idx"] = np.flatnonzero(prod["mag_mask"]).astype(np.int32)
+    out["peak_idx"] = int(np.argmax(mag))
+    out["phase_at_det"] = prod["ati_phase_masked"][prod["mag_mask"]].astype(np.float32)
+    out["margin"] = float(np.min(np.abs(mag - thr)) / thr)
+    out["dpca_peak_idx"] = int(np.argmax(prod["dpca_mag"]))
+    print("detections", len(out["det_idx"]), "margin", out["margin"], flush=True)
+    np.savez_compressed(os.path.join(OUT, "chain_ati_4096.npz"), **out)
+
+
 if __name__ == "__main__":
     if not ref_extract.reference_available():
         sys.exit("reference tree not found: fixtures can only be regenerated in the build container")
     os.makedirs(OUT, exist_ok=True)
     if len(sys.argv) > 1 and sys.argv[1] == "large":      # the two full-size CSA frames only (minutes, ~30 GB)
         golden_csa_large()
+        sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "chain4096":  # the north-star two-channel frame at full size (minutes)
+        golden_chain_4096()
         sys.exit(0)
     golden_vehicle_targets()
     golden_echo()

@@ -142,6 +142,39 @@ def test_chain_digest():
     assert np.max(np.abs(np.angle(np.exp(1j * (prod["ati_phase_masked"][prod["mag_mask"]] - g["phase_at_det"]))))) < 1e-5
 
 
+@pytest.mark.skipif(not os.environ.get("NIS_SLOW_TESTS"), reason="6 minutes of numpy: set NIS_SLOW_TESTS=1 (run once per change of the oracle)")
+def test_north_star_frame_digest_full_size():
+    """The oracle at the north_star size (4097 pulses x 4096 samples, two channels, CSA 4096 x 4096 x 2, GMTI) against the
+    digests of the unmodified reference's run (oracle/make_golden.py chain4096).  The GPU test of the same frame compares with
+    the reference digests directly; this one shows that the oracle restates the reference at full size as well."""
+    from oracle import inputs
+    g = _load("chain_ati_4096.npz")
+    prm = params.spaceborne_preset(fs=float(g["fs"]), bw=float(g["bw"]))
+    sc = scenes.ati_scene(seed=int(g["seed"]), num_pulses=int(g["num_pulses"]), num_clutter=int(g["num_clutter"]), prm=prm,
+                          t_int=None)
+    gl = prm.as_globals()
+    raws = []
+    for off in sc["rx_offsets"]:
+        a, t0 = orc.echo_bistatic(sc["ship_pos"], sc["ship_rcs"], sc["t_vec"], sc["pos_tx"], sc["vel_tx"], off, sc["ship_vel"], gl)
+        b, _ = orc.echo_bistatic(sc["clutter_pos"], sc["clutter_rcs"], sc["t_vec"], sc["pos_tx"], sc["vel_tx"], off,
+                                 sc["clutter_vel"], gl)
+        raws.append(a + b)
+    assert raws[0].shape == (4097, 4096) and t0 == float(g["t_start_fast"])
+    d = inputs.image_digest(raws[0], int(g["raw1_step"]), int(g["raw1_block"]))
+    assert _rel(d["dec"], g["raw1_dec"]) < 1e-6 and abs(d["sumsq"] / float(g["raw1_sumsq"]) - 1) < 1e-9
+    rx1, rx2 = orc.dpca_coregister(raws[0], raws[1])
+    slc1, rax, cax = orc.focus_csa(rx1, prm.Lambda, prm.k_rate, prm.FS, prm.PRF, prm.V_eff, prm.R0, t0)
+    slc2, _, _ = orc.focus_csa(rx2, prm.Lambda, prm.k_rate, prm.FS, prm.PRF, prm.V_eff, prm.R0, t0)
+    del raws
+    for tag, img in (("slc1", slc1), ("slc2", slc2)):
+        d = inputs.image_digest(np.ascontiguousarray(img), int(g[f"{tag}_step"]), int(g[f"{tag}_block"]))
+        assert _rel(d["dec"], g[f"{tag}_dec"]) < 1e-6 and _rel(d["rows"], g[f"{tag}_rows"]) < 1e-6   # stored as complex64
+        assert np.allclose(d["tile_energy"], g[f"{tag}_tile_energy"], rtol=1e-5)   # the two fp64 echo evaluation orders differ by ~1e-7
+    prod = orc.gmti_products(slc1, slc2)
+    assert np.array_equal(prod["det_idx"], g["det_idx"]) and prod["peak_idx"] == int(g["peak_idx"])
+    assert np.array_equal(rax, g["rax"])
+
+
 def test_gmti_definitions_small():
     rng = np.random.default_rng(3)
     s1 = rng.standard_normal((7, 5)) + 1j * rng.standard_normal((7, 5))
