@@ -37,6 +37,12 @@ def test_version_and_struct_layouts():
     assert lib.nis_gmti_workspace_bytes(1) == 16 + 264 and lib.nis_gmti_workspace_bytes(4096 * 4096) == 16 + 264 * 8192
 
 
+def test_graft_entry_build_passes():
+    """The driver's "does it build" check: __graft_entry__.build() (make is a no-op when the library is current)."""
+    import __graft_entry__ as g
+    g.build()
+
+
 def test_no_cpu_fallback():
     import torch
     if torch.cuda.is_available():
