@@ -701,7 +701,10 @@ def run_gpu_arm(args):
     torch.cuda.synchronize(device)
     e2e_s = (time.perf_counter() - t0) / e2e_steps
     h2d = int(sc["pos"].nbytes + sc["rcs"].nbytes + sc["pos_sat"].nbytes + sc["t_vec"].nbytes + 8 * N_RG + 24)
-    d2h = int(img.nbytes)
+    from nis_sar import hostio
+    d2h_info = dict(hostio.last_transfer["d2h"] or {})
+    d2h = int(d2h_info.get("pcie_bytes", img.nbytes))     # bytes that crossed PCIe; the host array is img.nbytes
+    d2h_info["host_result_bytes"] = int(img.nbytes)
     del img
 
     # ------------------------------------------------ the three multi-GPU workloads of BASELINE.json, at this N
@@ -1024,7 +1027,7 @@ def run_gpu_arm(args):
         "dtype": "f32 (complex64 samples; fp64 geometry and phase coefficients)", "data": "synthetic",
         "config": config_dict(args),
         "e2e": {"value": world * pixels / (e2e_ms * 1e-3) / 1e6, "unit": UNIT, "h2d_bytes_per_step": h2d,
-                "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms,
+                "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms, "d2h_transfer": d2h_info,
                 "path": "nis_sar.api.run_physics_engine(return_device=True) -> nis_sar.api.sar_focus_csa -> "
                         "complex128 numpy image on the host"},
         "gpu_launches": int(launches),

@@ -318,6 +318,15 @@ NIS_API int nis_slc_exchange(nis_comm* comm, const nis_c32* slc_local, nis_c32* 
  * are the only host-side cost. */
 NIS_API int nis_narrow_c128_to_c32(nis_ctx* ctx, const double* src /* dev [n*2] */, nis_c32* dst, uint64_t n, nis_stream stream);
 NIS_API int nis_widen_c32_to_c128(nis_ctx* ctx, const nis_c32* src, double* dst /* dev [n*2] */, uint64_t n, nis_stream stream);
+/* Host <-> device transfer of the reference's complex128 arrays in their NARROW form (half the PCIe bytes), converted
+ * on the host cores while the DMA engine runs (csrc/hostcopy.cpp): chunks of 4 MiB through a ring of page-locked slots
+ * owned by the library, `threads` worker threads (1..32), one whole chunk per thread.  Both calls BLOCK until the
+ * destination is complete; host pointers may be pageable or page-locked.  The values are those of the device-side
+ * helpers above (float -> double exact, double -> float round to nearest even).
+ *   nis_d2h_widen   host_dst[2n doubles] = (double) dev_src[n complex64]
+ *   nis_h2d_narrow  dev_dst[n complex64] = (float) host_src[2n doubles] */
+NIS_API int nis_d2h_widen(nis_ctx* ctx, const nis_c32* dev_src, double* host_dst, uint64_t n, int32_t threads, nis_stream stream);
+NIS_API int nis_h2d_narrow(nis_ctx* ctx, const double* host_src, nis_c32* dev_dst, uint64_t n, int32_t threads, nis_stream stream);
 /* out[c][r] = in[r][c] for a rows x cols complex64 matrix (tiled, coalesced both sides) */
 NIS_API int nis_transpose_c32(nis_ctx* ctx, const nis_c32* in, nis_c32* out, int32_t rows, int32_t cols, nis_stream stream);
 

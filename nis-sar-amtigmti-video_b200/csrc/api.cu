@@ -152,6 +152,28 @@ extern "C" int nis_widen_c32_to_c128(nis_ctx* ctx, const nis_c32* src, double* d
     return NIS_OK;
 }
 
+// host-converted transfers of the complex128 contract (hostcopy.cpp)
+namespace nis {
+int hostcopy_d2h_widen(int device, const float* dev_src, double* dst, size_t n_floats, int threads, cudaStream_t st);
+int hostcopy_h2d_narrow(int device, const double* src, float* dev_dst, size_t n_floats, int threads, cudaStream_t st);
+}
+extern "C" int nis_d2h_widen(nis_ctx* ctx, const nis_c32* dev_src, double* host_dst, uint64_t n, int32_t threads,
+                             nis_stream stream) {
+    NIS_REQUIRE(ctx && dev_src && host_dst, "nis_d2h_widen: null argument");
+    NIS_REQUIRE(threads >= 1 && threads <= 32, "nis_d2h_widen: threads = %d outside 1..32", threads);
+    DeviceGuard guard(ctx->device);
+    return hostcopy_d2h_widen(ctx->device, reinterpret_cast<const float*>(dev_src), host_dst, (size_t)n * 2, threads,
+                              (cudaStream_t)stream);
+}
+extern "C" int nis_h2d_narrow(nis_ctx* ctx, const double* host_src, nis_c32* dev_dst, uint64_t n, int32_t threads,
+                              nis_stream stream) {
+    NIS_REQUIRE(ctx && host_src && dev_dst, "nis_h2d_narrow: null argument");
+    NIS_REQUIRE(threads >= 1 && threads <= 32, "nis_h2d_narrow: threads = %d outside 1..32", threads);
+    DeviceGuard guard(ctx->device);
+    return hostcopy_h2d_narrow(ctx->device, host_src, reinterpret_cast<float*>(dev_dst), (size_t)n * 2, threads,
+                               (cudaStream_t)stream);
+}
+
 namespace nis {
 int launch_transpose(nis_ctx* ctx, const float2* in, int64_t in_pitch, float2* out, int rows, int cols,
                      cudaStream_t st) {

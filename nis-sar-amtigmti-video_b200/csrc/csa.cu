@@ -453,6 +453,99 @@ __global__ void __launch_bounds__(P::NT* RPB, MINB) k_range(float2* __restrict__
     }
 }
 
+// The same row pipeline with ONE copy of the transform in the instruction stream: the inverse transform is run as
+// conj(FFT(conj(.))) (bit-identical to the conjugated-twiddle form: every operation is mirrored exactly), so the loop
+// body executes twice per row and the conjugations ride on the phase multiplies.  The straight-line form above is
+// 4096 SASS instructions (64 KB) at 8192 samples -- twice the 32 KB instruction cache, ncu: 5 % of the stalls
+// `no_instruction`; this one is a little more than half of that.  One row per CTA, next row prefetched by TMA.
+template <class P, int PAD, int PF, int MINB>
+__global__ void __launch_bounds__(P::NT, MINB) k_range_rolled(float2* __restrict__ data, int64_t pitch, int n_rows,
+                                                           const RowCoef* __restrict__ coef,
+                                                           const float2* __restrict__ tw) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    __shared__ uint64_t full;
+    constexpr int E = P::E, NT = P::NT, N = P::N;
+    constexpr int SMROW = N + (PAD ? (N >> PAD) : 0);
+    const int t = threadIdx.x;
+    float2* sm = reinterpret_cast<float2*>(smem_raw);
+    // PF = 1: the next row is prefetched into a buffer of its own while this one is transformed; PF = 2: into the exchange
+    // buffer itself, as soon as the last gather of the row has left it (the copy then overlaps the last pass, Phi3 and the
+    // stores) -- no second buffer, so two CTAs fit an SM; PF = 0: plain loads
+    float2* pf = PF == 1 ? sm + SMROW : sm;
+    CtaBarrier bar;
+    const int row_stride = gridDim.x;
+    if constexpr (PF != 0) {
+        if (t == 0) {
+            tma::mbar_init(&full, 1);
+            tma::fence_barrier_init();
+            if ((int)blockIdx.x < n_rows) {
+                tma::mbar_arrive_expect_tx(&full, N * sizeof(float2));
+                tma::bulk_load_1d(pf, data + (int64_t)blockIdx.x * pitch, N * sizeof(float2), &full);
+            }
+        }
+        __syncthreads();
+    }
+    int it = 0;
+    for (int row = blockIdx.x; row < n_rows; row += row_stride, ++it) {
+        const RowCoef* rc = coef + row;
+        float2* p = data + (int64_t)row * pitch;
+        float2 v[E];
+        if constexpr (PF != 0) {
+            tma::mbar_wait(&full, it & 1);
+#pragma unroll
+            for (int s = 0; s < E; ++s) v[s] = pf[t + NT * s];
+            bar();   // the whole row is in registers: the prefetch buffer may be refilled
+            if (PF == 1 && t == 0 && row + row_stride < n_rows) {
+                tma::mbar_arrive_expect_tx(&full, N * sizeof(float2));
+                tma::bulk_load_1d(pf, data + (int64_t)(row + row_stride) * pitch, N * sizeof(float2), &full);
+            }
+        } else {
+#pragma unroll
+            for (int s = 0; s < E; ++s) v[s] = __ldcs(p + t + NT * s);
+        }
+        {
+            PhaseStepper ps;
+            ps.init(__ldg(&rc->a1), __ldg(&rc->b1), __ldg(&rc->c1), (uint32_t)t, NT);
+#pragma unroll
+            for (int s = 0; s < E; ++s) v[s] = cmul(v[s], ps.next());
+        }
+#pragma unroll 1
+        for (int half = 0; half < 2; ++half) {
+            transform<P, false, 1, PAD, CtaBarrier, false>(v, t, sm, tw, bar);
+            if (half == 0) {   // v <- conj(v Phi2)
+                const uint64_t a2 = __ldg(&rc->a2), b2 = __ldg(&rc->b2);
+                PhaseStepper ps;
+                ps.init(a2, b2, 0ull, (uint32_t)t, NT);
+#pragma unroll
+                for (int s = 0; s < E / 2; ++s) {
+                    const float2 w = ps.next(), x = v[s];
+                    v[s] = make_float2(fmaf(x.x, w.x, -x.y * w.y), fmaf(-x.x, w.y, -x.y * w.x));
+                }
+                ps.init_mirror(a2, b2, __ldg(&rc->bn2), (uint32_t)(N / 2 - t), (uint32_t)(N / 2 + t), NT);
+#pragma unroll
+                for (int s = E / 2; s < E; ++s) {
+                    const float2 w = ps.next(), x = v[s];
+                    v[s] = make_float2(fmaf(x.x, w.x, -x.y * w.y), fmaf(-x.x, w.y, -x.y * w.x));
+                }
+            }
+            bar();
+        }
+        if constexpr (PF == 2) {
+            if (t == 0 && row + row_stride < n_rows) {
+                tma::fence_proxy_async();   // the generic-proxy reads of the buffer (ordered by the barrier) precede the refill
+                tma::mbar_arrive_expect_tx(&full, N * sizeof(float2));
+                tma::bulk_load_1d(pf, data + (int64_t)(row + row_stride) * pitch, N * sizeof(float2), &full);
+            }
+        }
+        {   // conj(v) Phi3
+            PhaseStepper ps;
+            ps.init(__ldg(&rc->a3), __ldg(&rc->b3), __ldg(&rc->c3), (uint32_t)t, NT);
+#pragma unroll
+            for (int s = 0; s < E; ++s) p[t + NT * s] = cmul_conj(ps.next(), v[s]);
+        }
+    }
+}
+
 // ------------------------------------------------------------------------------ host: plan
 }  // namespace
 
@@ -541,6 +634,24 @@ template <class P, int PAD, int RPB, int MINB, bool PK = false>
 int launch_range(nis_csa_plan* pl, int row0, int nrows, cudaStream_t st) {
     if (pl->phase_in_az) return launch_range_one<P, PAD, RPB, MINB, PK, false>(pl, row0, nrows, st);
     return launch_range_one<P, PAD, RPB, MINB, PK, true>(pl, row0, nrows, st);
+}
+
+template <class P, int PAD, int PF, int MINB>
+int launch_range_rolled(nis_csa_plan* pl, int row0, int nrows, cudaStream_t st) {
+    auto kern = k_range_rolled<P, PAD, PF, MINB>;
+    constexpr int SMROW = P::N + (PAD ? (P::N >> PAD) : 0);
+    const size_t smem = (size_t)(SMROW + (PF == 1 ? P::N : 0)) * sizeof(float2);
+    static bool attr_done_dev[64] = {};
+    bool& attr_done = attr_done_dev[nis::current_device() & 63];
+    if (!attr_done) {
+        NIS_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_done = true;
+    }
+    int grid = pl->ctx->num_sms * MINB;
+    if (grid > nrows) grid = nrows;
+    kern<<<grid, P::NT, smem, st>>>(pl->work + (int64_t)row0 * pl->n_rg, pl->n_rg, nrows, pl->coef + row0, pl->tw_rg);
+    NIS_LAUNCH_CHECK(pl->ctx);
+    return NIS_OK;
 }
 
 // plans: <N, E, R0, R1, R2>
@@ -945,19 +1056,30 @@ extern "C" int nis_csa_plan_create(nis_ctx* ctx, int32_t n_az, int32_t n_rg, con
         case 2048: pl->range = launch_range<P2048, 4, 1, 4>; FAIL_IF(upload_twiddles<P2048>(&pl->tw_rg)); break;
         // one row per CTA, several CTAs per SM: independent CTAs drift out of phase, so one CTA's shared-memory exchange
         // overlaps another's butterflies (measured: 0.096 vs 0.104 ms at 4096^2 against two row groups inside one CTA)
+        // (the rolled two-CTA form of the 8192-sample kernel below gains nothing here: 0.098 vs 0.097 ms, and three CTAs per SM
+        // at 80 registers spill: 0.119 ms)
         case 4096: pl->range = launch_range<P4096, 4, 1, 2>; FAIL_IF(upload_twiddles<P4096>(&pl->tw_rg)); break;
-        case 8192:
-            // 32 samples per thread (three passes, 256 threads x 213 registers, no spills): 0.417 ms against 0.457 ms for the
-            // 16-sample four-pass plan at 8192^2 (profiles/kbench_r2e.jsonl); packed fp32x2 on top of it: 0.423 ms, not used.
-            // NIS_RANGE_PLAN=e16 selects the old plan (development knob, both are parity-tested)
-            if (const char* v = getenv("NIS_RANGE_PLAN"); v && v[0] == 'e' && v[1] == '1') {
+        case 8192: {
+            // 32 samples per thread, three passes 32 x 16 x 16.  Default (round 2): k_range_rolled -- ONE copy of the transform
+            // in the instruction stream (inverse = conj FFT conj), which ptxas fits into 128 registers without spills, so TWO
+            // 256-thread CTAs share an SM and drift out of phase (one CTA's exchange overlaps the other's butterflies); the
+            // next row is prefetched by TMA into the exchange buffer itself once the row's last gather has left it.
+            // Measured at 8192^2 (profiles/kbench_r2f.jsonl): 0.370 ms; without the prefetch 0.399; one CTA per SM with a
+            // prefetch buffer of its own (153 registers) 0.468; packed fp32x2 butterflies (216 B of spills) 0.430.
+            // NIS_RANGE_PLAN=e32flat: the straight-line kernel (213 registers, one CTA per SM, 4096 SASS instructions =
+            // twice the instruction cache): 0.418 ms; NIS_RANGE_PLAN=e16: 16 samples per thread, four passes: 0.457 ms.
+            // All three are parity-tested (tests/test_gpu_parity_r2.py).
+            const char* v = getenv("NIS_RANGE_PLAN");
+            if (v && v[0] == 'e' && v[1] == '1') {
                 pl->range = launch_range<P8192, 4, 1, 1>;
                 FAIL_IF(upload_twiddles<P8192>(&pl->tw_rg));
             } else {
-                pl->range = launch_range<P8192E32, 5, 1, 1>;
+                if (pl->phase_in_az || (v && strcmp(v, "e32flat") == 0)) pl->range = launch_range<P8192E32, 5, 1, 1>;
+                else pl->range = launch_range_rolled<P8192E32, 5, 2, 2>;
                 FAIL_IF(upload_twiddles<P8192E32>(&pl->tw_rg));
             }
             break;
+        }
         default: pl->range = launch_range<P16384, 4, 1, 1>; FAIL_IF(upload_twiddles<P16384>(&pl->tw_rg)); break;
     }
     FAIL_IF(upload_full_twiddles(pl));

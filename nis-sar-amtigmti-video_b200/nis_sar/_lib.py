@@ -98,6 +98,8 @@ SIGNATURES = {
     "nis_gmti_balance_sum": (C.c_int, [_P, _P, _P, C.c_uint64, _P, _P]),
     "nis_narrow_c128_to_c32": (C.c_int, [_P, _P, _P, C.c_uint64, _P]),
     "nis_widen_c32_to_c128": (C.c_int, [_P, _P, _P, C.c_uint64, _P]),
+    "nis_d2h_widen": (C.c_int, [_P, _P, _P, C.c_uint64, C.c_int32, _P]),
+    "nis_h2d_narrow": (C.c_int, [_P, _P, _P, C.c_uint64, C.c_int32, _P]),
     "nis_transpose_c32": (C.c_int, [_P, _P, _P, C.c_int32, C.c_int32, _P]),
 }
 

@@ -68,11 +68,7 @@ def _upload_c32(a, device) -> torch.Tensor:
     turn = h.ndim == 2 and h.flags.f_contiguous and not h.flags.c_contiguous
     if turn:
         h = h.T
-    h = np.ascontiguousarray(h)
-    if h.dtype == np.complex64:
-        x = torch.from_numpy(h).to(device)
-    else:
-        x = dev.narrow_c128(torch.from_numpy(h.astype(np.complex128, copy=False)).to(device))
+    x = hostio.to_device_c64(h, device)
     return dev.transpose_c32(x) if turn else x
 
 
@@ -174,9 +170,7 @@ def tdbp_gpu(raw_t, pos_plat, vel_plat, t_start, num_samples, vel_focus, t_pulse
         x = raw_t if raw_t.dtype == torch.complex64 else dev.narrow_c128(raw_t.to(torch.complex128).contiguous())
         x = x.to(device) if not x.is_cuda else x
     else:
-        h = np.ascontiguousarray(raw_t)
-        x = torch.from_numpy(h).to(device) if h.dtype == np.complex64 else \
-            dev.narrow_c128(torch.from_numpy(h.astype(np.complex128, copy=False)).to(device))
+        x = hostio.to_device_c64(raw_t, device)
     key = (prm.C, prm.FC, prm.k_rate, prm.T_p, prm.FS, float(t_start), int(num_samples), float(scene_size), int(nx), int(ny),
            x.device.index)
     plan = _tdbp_plans.get(key)
@@ -211,10 +205,7 @@ def sar_focus_csa(phist, center_wavelength_m, pulse_width_sec, chirp_rate_hzpsec
         h = np.asarray(phist)
         if h.ndim != 2:
             raise dev.NisError("sar_focus_csa: phist must be 2-D [N_az, N_rg]")
-        if h.dtype == np.complex64:
-            x = torch.from_numpy(np.ascontiguousarray(h)).to(device)
-        else:
-            x = dev.narrow_c128(torch.from_numpy(np.ascontiguousarray(h, dtype=np.complex128)).to(device))
+        x = hostio.to_device_c64(h, device)
     n_az, n_rg = x.shape
     plan = dev.cached_plan(n_az, n_rg, lam=float(center_wavelength_m), kr=float(chirp_rate_hzpsec),
                            fs=float(sample_rate_hz), prf=float(prf_hz), vr=float(platform_speed_mps),
@@ -280,9 +271,7 @@ def add_ocean_noise(raw_data, snr_db, scr_db=10.0, k_nu=1.0, *, seed=None, devic
     if torch.is_tensor(raw_data):
         x = raw_data if raw_data.dtype == torch.complex64 else dev.narrow_c128(raw_data.to(torch.complex128).contiguous())
         return dev.add_noise(x.contiguous(), snr_db, scr_db, k_nu, seed)
-    h = np.ascontiguousarray(raw_data)
-    x = torch.from_numpy(h).to(device) if h.dtype == np.complex64 else \
-        dev.narrow_c128(torch.from_numpy(h.astype(np.complex128, copy=False)).to(device))
+    x = hostio.to_device_c64(raw_data, device)
     dev.add_noise(x, snr_db, scr_db, k_nu, seed)
     return x if return_device else _to_host_c128(x)
 
@@ -329,10 +318,7 @@ def sar_focus_rda(phist, center_wavelength_m, pulse_width_sec, chirp_rate_hzpsec
         if h.ndim != 2:
             raise dev.NisError("sar_focus_rda: phist must be 2-D [num_ranges, num_pulses]")
         ht = h.T                                     # pulse-major; C-contiguous when phist is raw_data.T
-        if ht.dtype == np.complex64:
-            xt = torch.from_numpy(np.ascontiguousarray(ht)).to(device)
-        else:
-            xt = dev.narrow_c128(torch.from_numpy(np.ascontiguousarray(ht, dtype=np.complex128)).to(device))
+        xt = hostio.to_device_c64(ht, device)
     n_pulses, n_ranges = xt.shape
     plan = dev.cached_rda_plan(n_pulses, n_ranges, lam=float(center_wavelength_m), t_p=float(pulse_width_sec),
                                kr=float(chirp_rate_hzpsec), fs=float(sample_rate_hz), prf=float(prf_hz),

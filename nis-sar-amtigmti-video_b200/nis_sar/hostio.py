@@ -4,10 +4,15 @@ The reference's functions return freshly allocated complex128 numpy arrays (SURV
 complex64.  One image of the bench frame is 1.07 GB on the host, so end to end the step is a PCIe transfer with a
 0.3 ms widening kernel in front of it; what this module controls is WHERE that transfer lands:
 
-* ``to_host_c128(t, out=None)``: widen on the device, one asynchronous D2H copy into page-locked memory.  Without
-  ``out`` the block comes from torch's caching host allocator (re-used once the caller drops the previous result --
-  no ``cudaHostAlloc`` per call in steady state); with ``out`` (``pinned_empty``) the caller owns a persistent buffer
-  and nothing is allocated at all.
+* ``to_host_c128(t, out=None)``: two routes.  With enough host cores (``host_threads() >= 6``) the NARROW form crosses
+  PCIe -- half the bytes -- in 4 MiB chunks and worker threads widen float -> double straight into the result while
+  the DMA engine runs (``nis_d2h_widen``, csrc/hostcopy.cpp): 19 -> 12-14 ms for the 8192 x 8192 image.  Otherwise:
+  widen on the device, one asynchronous D2H copy of the wide form.  Without ``out`` the block comes from torch's caching
+  host allocator (re-used once the caller drops the previous result -- no ``cudaHostAlloc`` per call in steady state);
+  with ``out`` (``pinned_empty`` or any C-contiguous complex128 array) nothing is allocated at all.
+* ``to_device_c64(h, device)``: the same for inputs -- complex128 numpy -> complex64 on the device, narrowed on the host
+  cores into the transfer ring (``nis_h2d_narrow``) instead of a pageable copy of the wide form + a device kernel.
+  ``NIS_HOST_THREADS`` sets the worker count (0: always convert on the device).
 * ``bind_rank_to_numa(local_rank, ...)``: one process per GPU on a two-socket host -- pin the process (and with it the
   first-touch placement of every pinned block it allocates afterwards) to the NUMA node of its GPU, or, when the
   platform reports every GPU on one node, spread the ranks over the nodes so that eight result streams do not share one
@@ -20,8 +25,39 @@ import os
 import numpy as np
 import torch
 
-from . import device as dev
+import ctypes as C
+
+from . import _lib, device as dev
 from ._lib import NisError
+
+_MIN_THREADS_FOR_HOST_ROUTE = 6      # measured: 4 threads tie with the wide DMA, 8 win by 20 %, 12-16 by 35 %
+_MIN_ELEMENTS_FOR_HOST_ROUTE = 1 << 21
+
+
+def host_threads() -> int:
+    """Worker threads of the host-converted transfers: ``NIS_HOST_THREADS``, else the cores this process may run on
+    divided among the ranks of the node (``LOCAL_WORLD_SIZE``), one left for the thread that drives the DMA, at most 16."""
+    env = os.environ.get("NIS_HOST_THREADS")
+    if env is not None:
+        try:
+            return max(0, min(32, int(env)))
+        except ValueError:
+            pass
+    try:
+        avail = len(os.sched_getaffinity(0))
+    except AttributeError:
+        avail = os.cpu_count() or 1
+    ranks = max(1, int(os.environ.get("LOCAL_WORLD_SIZE", "1") or 1))
+    return max(0, min(16, avail // ranks - 1))
+
+
+# what the last to_host_c128 / to_device_c64 call did (bench.py reports the bytes that really crossed PCIe)
+last_transfer = {"d2h": None, "h2d": None}
+
+
+def _host_route(n_elements: int) -> int:
+    t = host_threads()
+    return t if (t >= _MIN_THREADS_FOR_HOST_ROUTE and n_elements >= _MIN_ELEMENTS_FOR_HOST_ROUTE) else 0
 
 
 def pinned_empty(shape, dtype=np.complex128, order="C") -> np.ndarray:
@@ -39,16 +75,48 @@ def to_host_c128(t: torch.Tensor, out: np.ndarray | None = None) -> np.ndarray:
     """complex64 CUDA tensor -> complex128 numpy array of the same shape (C order)."""
     if not t.is_cuda or t.dtype != torch.complex64:
         raise NisError("to_host_c128: expected a complex64 CUDA tensor")
-    wide = dev.widen_c32(t.contiguous())
-    if out is None:
-        host = torch.empty(wide.shape, dtype=torch.complex128, pin_memory=True)
-    else:
-        if out.dtype != np.complex128 or tuple(out.shape) != tuple(wide.shape) or not out.flags.c_contiguous:
-            raise NisError(f"to_host_c128: out must be a C-contiguous complex128 array of shape {tuple(wide.shape)}")
-        host = torch.from_numpy(out)          # pinned if it came from pinned_empty(): the copy below is then one DMA
-    host.copy_(wide, non_blocking=True)
+    t = t.contiguous()
+    if out is not None and (out.dtype != np.complex128 or tuple(out.shape) != tuple(t.shape) or not out.flags.c_contiguous):
+        raise NisError(f"to_host_c128: out must be a C-contiguous complex128 array of shape {tuple(t.shape)}")
+    threads = _host_route(t.numel())
+    if threads:
+        host = torch.empty(t.shape, dtype=torch.complex128, pin_memory=True).numpy() if out is None else out
+        di = dev._dev_index(t.device)
+        with torch.cuda.device(di):
+            rc = _lib.load().nis_d2h_widen(_lib.context(di), dev._ptr(t), C.c_void_p(host.ctypes.data), t.numel(), threads,
+                                           C.c_void_p(dev._stream_ptr(di)))
+        _lib.check(rc, "nis_d2h_widen")
+        last_transfer["d2h"] = {"route": "complex64 over PCIe, widened by host threads (nis_d2h_widen)", "threads": threads,
+                                "pcie_bytes": 8 * t.numel(), "host_bytes": 16 * t.numel()}
+        return host
+    wide = dev.widen_c32(t)
+    host = torch.empty(wide.shape, dtype=torch.complex128, pin_memory=True) if out is None else torch.from_numpy(out)
+    host.copy_(wide, non_blocking=True)       # one DMA when the destination is page-locked
     torch.cuda.current_stream(t.device).synchronize()
+    last_transfer["d2h"] = {"route": "widened on the device, complex128 over PCIe", "threads": 0,
+                            "pcie_bytes": 16 * t.numel(), "host_bytes": 16 * t.numel()}
     return host.numpy() if out is None else out
+
+
+def to_device_c64(h: np.ndarray, device) -> torch.Tensor:
+    """C-contiguous complex128 (or complex64) numpy array -> complex64 CUDA tensor of the same shape."""
+    h = np.ascontiguousarray(h)
+    if h.dtype == np.complex64:
+        return torch.from_numpy(h).to(device)
+    if h.dtype != np.complex128:
+        h = h.astype(np.complex128)
+    threads = _host_route(h.size)
+    if not threads:
+        return dev.narrow_c128(torch.from_numpy(h).to(device))
+    x = torch.empty(h.shape, dtype=torch.complex64, device=device)
+    di = dev._dev_index(x.device)
+    with torch.cuda.device(di):
+        rc = _lib.load().nis_h2d_narrow(_lib.context(di), C.c_void_p(h.ctypes.data), dev._ptr(x), h.size, threads,
+                                        C.c_void_p(dev._stream_ptr(di)))
+    _lib.check(rc, "nis_h2d_narrow")
+    last_transfer["h2d"] = {"route": "narrowed by host threads, complex64 over PCIe (nis_h2d_narrow)", "threads": threads,
+                            "pcie_bytes": 8 * h.size, "host_bytes": 16 * h.size}
+    return x
 
 
 # ------------------------------------------------------------------------------------------ placement

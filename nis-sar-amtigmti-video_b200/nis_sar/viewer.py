@@ -17,6 +17,7 @@ import torch
 
 from . import _lib
 from . import device as dev
+from . import hostio
 
 MODES = ("Ch1 Magnitude", "Ch1 Phase", "Ch2 Magnitude", "Ch2 Phase", "DPCA Magnitude", "DPCA Phase", "ATI Phase")
 
@@ -50,9 +51,7 @@ class SARData:
             t = t if t.dtype == torch.complex64 else dev.narrow_c128(t.to(torch.complex128).contiguous())
             return t.contiguous().to(self.device)
         h = np.asarray(a).T                                     # storage orientation [N_range, N_cross]
-        if h.dtype == np.complex64:
-            return torch.from_numpy(np.ascontiguousarray(h)).to(self.device)
-        return dev.narrow_c128(torch.from_numpy(np.ascontiguousarray(h, dtype=np.complex128)).to(self.device))
+        return hostio.to_device_c64(h, self.device)
 
     def compute_all(self):
         """All seven maps in one pass over the two images (:42-52)."""

@@ -203,3 +203,23 @@ def test_bench_reference_arm_prints_the_contract_line():
     assert d["cpu_baseline"]["kind"].startswith("port") and "extrapolated" in d["cpu_baseline"]["kind"]
     assert d["cpu_baseline"]["cores"] >= 1 and "workload" in d["config"] and d["steps_run"] == 1
     assert "4096x4096" in d["cpu_baseline"]["sample"] and "64 of 8192 pulses" in d["cpu_baseline"]["sample"]
+
+
+def test_host_transfer_thread_policy(monkeypatch):
+    """nis_sar.hostio.host_threads(): NIS_HOST_THREADS wins; otherwise the cores of this process are divided among the
+    ranks of the node and one is left to the thread that drives the DMA; the host-converted route needs >= 6 of them."""
+    from nis_sar import hostio
+    monkeypatch.setenv("NIS_HOST_THREADS", "12")
+    assert hostio.host_threads() == 12 and hostio._host_route(1 << 24) == 12 and hostio._host_route(1000) == 0
+    monkeypatch.setenv("NIS_HOST_THREADS", "0")
+    assert hostio.host_threads() == 0 and hostio._host_route(1 << 24) == 0
+    monkeypatch.delenv("NIS_HOST_THREADS")
+    monkeypatch.setattr(os, "sched_getaffinity", lambda pid: set(range(32)), raising=False)
+    monkeypatch.setenv("LOCAL_WORLD_SIZE", "1")
+    assert hostio.host_threads() == 16
+    monkeypatch.setenv("LOCAL_WORLD_SIZE", "8")
+    assert hostio.host_threads() == 3 and hostio._host_route(1 << 24) == 0      # 8 ranks on 32 cores: device route
+    monkeypatch.setenv("LOCAL_WORLD_SIZE", "2")
+    assert hostio.host_threads() == 15
+    lib = _lib.load()
+    assert lib.nis_d2h_widen(None, None, None, 4, 4, None) == -1 and "null argument" in _lib.last_error()
