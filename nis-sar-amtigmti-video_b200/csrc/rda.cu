@@ -58,21 +58,31 @@ __global__ void __launch_bounds__(P::NT) k_rda_range(const float2* __restrict__ 
             const int idx = t + NT * s;
             v[s] = idx < N ? p[idx] : make_float2(0.f, 0.f);
         }
-        transform<P, false, 1, PAD>(v, t, sm, tw);
+        // forward and inverse transform share ONE copy of the code: the inverse runs as conj(FFT(conj(.))), bit-identical to
+        // the conjugated-twiddle form, the conjugations folded into the filter multiply and the store (two inlined bodies of
+        // the 32-element 16384-point plan spilled 680 bytes per thread at its 128-register cap)
+#pragma unroll 1
+        for (int step = 0; step < 2; ++step) {
+            transform<P, false, 1, PAD>(v, t, sm, tw);
+            if (step == 0) {   // v <- conj(v Hf)
 #pragma unroll
-        for (int s = 0; s < E; ++s) v[s] = cmul_pk(v[s], __ldg(Hf + t + NT * s));
-        __syncthreads();
-        transform<P, true, 1, PAD>(v, t, sm, tw);
+                for (int s = 0; s < E; ++s) {
+                    const float2 h = __ldg(Hf + t + NT * s), x = v[s];
+                    v[s] = make_float2(fmaf(x.x, h.x, -x.y * h.y), fmaf(-x.x, h.y, -x.y * h.x));
+                }
+            }
+            __syncthreads();
+        }
         const float w = win[row];
 #pragma unroll
         for (int s = 0; s < E; ++s) {
             const int o = t + NT * s - s0;
             if (o >= 0 && o < N) {
-                if (rc_out != nullptr) rc_out[(int64_t)row * N + o] = v[s];
-                work[(int64_t)row * work_pitch + o] = make_float2(v[s].x * w, v[s].y * w);
+                const float2 y = make_float2(v[s].x, -v[s].y);
+                if (rc_out != nullptr) rc_out[(int64_t)row * N + o] = y;
+                work[(int64_t)row * work_pitch + o] = make_float2(y.x * w, y.y * w);
             }
         }
-        __syncthreads();
     }
 }
 
@@ -100,21 +110,28 @@ __global__ void __launch_bounds__(P::NT) k_rda_range_blocked(const float2* __res
             const int xi = in0 + t + NT * s;
             v[s] = (xi >= 0 && xi < N) ? p[xi] : make_float2(0.f, 0.f);
         }
-        transform<P, false, 1, PAD>(v, t, sm, tw);
+#pragma unroll 1
+        for (int step = 0; step < 2; ++step) {   // one copy of the transform: inverse = conj FFT conj (see k_rda_range)
+            transform<P, false, 1, PAD>(v, t, sm, tw);
+            if (step == 0) {
 #pragma unroll
-        for (int s = 0; s < E; ++s) v[s] = cmul_pk(v[s], __ldg(Hf + t + NT * s));
-        __syncthreads();
-        transform<P, true, 1, PAD>(v, t, sm, tw);
+                for (int s = 0; s < E; ++s) {
+                    const float2 h = __ldg(Hf + t + NT * s), x = v[s];
+                    v[s] = make_float2(fmaf(x.x, h.x, -x.y * h.y), fmaf(-x.x, h.y, -x.y * h.x));
+                }
+            }
+            __syncthreads();
+        }
         const float w = win[row];
 #pragma unroll
         for (int s = 0; s < E; ++s) {
             const int j = t + NT * s, o = o0 + j - (L - 1);
             if (j >= L - 1 && o < N) {
-                if (rc_out != nullptr) rc_out[(int64_t)row * N + o] = v[s];
-                work[(int64_t)row * work_pitch + o] = make_float2(v[s].x * w, v[s].y * w);
+                const float2 y = make_float2(v[s].x, -v[s].y);
+                if (rc_out != nullptr) rc_out[(int64_t)row * N + o] = y;
+                work[(int64_t)row * work_pitch + o] = make_float2(y.x * w, y.y * w);
             }
         }
-        __syncthreads();
     }
 }
 
@@ -143,34 +160,71 @@ __global__ void __launch_bounds__(P::NT) k_rda_range_pruned(const float2* __rest
     for (int row = blockIdx.x; row < n_rows; row += gridDim.x) {
         const float2* p = in + (int64_t)row * in_pitch;
         float2 v[E];
-        // even bins, then odd bins: one copy of the two transforms in the instruction stream (the 32-element plan is large)
+        // even bins, then odd bins, forward and inverse: ONE copy of the transform in the instruction stream.  The inverse is
+        // run as conj(FFT(conj(.))) -- bit-identical to the conjugated-twiddle form -- with the conjugations folded into the
+        // filter multiply and into the uses of the result.  Round 2: with four inlined transform bodies (two per branch) the
+        // 32-element plan needed ~700 bytes of local memory per thread at its 128-register cap (ncu: 4.8 GB of DRAM writes
+        // for a 0.76 GB pass); one body fits the registers.
+        if constexpr (P::E < 32) {
+            // (the 16-element plans fit their registers either way, and two bodies schedule a little better: 8192^2 frame
+            // 1.86 ms against 1.93 ms rolled)
 #pragma unroll 1
-        for (int br = 0; br < 2; ++br) {
-            const float2* __restrict__ hf = br ? HfO : HfE;
+            for (int br = 0; br < 2; ++br) {
+                const float2* __restrict__ hf = br ? HfO : HfE;
 #pragma unroll
-            for (int s = 0; s < E; ++s) {
-                const int idx = t + NT * s;
-                float2 x = idx < N ? p[idx] : make_float2(0.f, 0.f);
-                if (br) x = cmul_pk(x, __ldg(twM + idx));
-                v[s] = x;
-            }
-            transform<P, false, 1, PAD>(v, t, sm, tw);
+                for (int s = 0; s < E; ++s) {
+                    const int idx = t + NT * s;
+                    float2 x = idx < N ? p[idx] : make_float2(0.f, 0.f);
+                    if (br) x = cmul_pk(x, __ldg(twM + idx));
+                    v[s] = x;
+                }
+                transform<P, false, 1, PAD>(v, t, sm, tw);
 #pragma unroll
-            for (int s = 0; s < E; ++s) v[s] = cmul_pk(v[s], __ldg(hf + t + NT * s));
-            __syncthreads();
-            transform<P, true, 1, PAD>(v, t, sm, tw);
-            if (br == 0) {
+                for (int s = 0; s < E; ++s) {   // v <- conj(v Hf) ...
+                    const float2 h = __ldg(hf + t + NT * s), x = v[s];
+                    v[s] = make_float2(fmaf(x.x, h.x, -x.y * h.y), fmaf(-x.x, h.y, -x.y * h.x));
+                }
+                __syncthreads();
+                transform<P, false, 1, PAD>(v, t, sm, tw);   // ... so that conj of this forward transform is the inverse
+                if (br == 0) {
 #pragma unroll
-                for (int s = 0; s < E; ++s) park[t + NT * s] = v[s];
+                    for (int s = 0; s < E; ++s) park[t + NT * s] = make_float2(v[s].x, -v[s].y);
+                }
                 __syncthreads();
             }
+        } else
+#pragma unroll 1
+        for (int step = 0; step < 4; ++step) {
+            const int br = step >> 1;
+            if ((step & 1) == 0) {
+#pragma unroll
+                for (int s = 0; s < E; ++s) {
+                    const int idx = t + NT * s;
+                    float2 x = idx < N ? p[idx] : make_float2(0.f, 0.f);
+                    if (br) x = cmul_pk(x, __ldg(twM + idx));
+                    v[s] = x;
+                }
+            }
+            transform<P, false, 1, PAD>(v, t, sm, tw);
+            if ((step & 1) == 0) {          // v <- conj(v Hf)
+                const float2* __restrict__ hf = br ? HfO : HfE;
+#pragma unroll
+                for (int s = 0; s < E; ++s) {
+                    const float2 h = __ldg(hf + t + NT * s), x = v[s];
+                    v[s] = make_float2(fmaf(x.x, h.x, -x.y * h.y), fmaf(-x.x, h.y, -x.y * h.x));
+                }
+            } else if (br == 0) {           // A = conj(v), parked
+#pragma unroll
+                for (int s = 0; s < E; ++s) park[t + NT * s] = make_float2(v[s].x, -v[s].y);
+            }
+            __syncthreads();
         }
         const float w = win[row];
 #pragma unroll
         for (int s = 0; s < E; ++s) {
             const int idx = t + NT * s;
             const float2 a = park[idx];
-            const float2 c = cmul_conj_pk(v[s], __ldg(twM + idx));
+            const float2 c = cmul_conj_pk(make_float2(v[s].x, -v[s].y), __ldg(twM + idx));
             const float2 y1 = cadd_pk(a, c), y2 = csub_pk(a, c);
             const int o1 = idx - s0, o2 = idx + H - s0;
             if (o1 >= 0 && o1 < N) {

@@ -49,17 +49,25 @@ __global__ void __launch_bounds__(P::NT) k_tdbp_range(const float2* __restrict__
             if (idx >= N) idx %= N;
             v[s] = p[idx];
         }
-        transform<P, false, 1, PAD>(v, t, sm, tw);
+        // forward and inverse transform share ONE copy of the code (inverse = conj FFT conj, bit-identical to the
+        // conjugated-twiddle form): two inlined bodies of the 32-element plan spilled 340 bytes per thread at 128 registers
+#pragma unroll 1
+        for (int step = 0; step < 2; ++step) {
+            transform<P, false, 1, PAD>(v, t, sm, tw);
+            if (step == 0) {   // v <- conj(v Hc)
 #pragma unroll
-        for (int s = 0; s < E; ++s) v[s] = cmul_pk(v[s], __ldg(Hc + t + NT * s));
-        __syncthreads();
-        transform<P, true, 1, PAD>(v, t, sm, tw);
+                for (int s = 0; s < E; ++s) {
+                    const float2 h = __ldg(Hc + t + NT * s), x = v[s];
+                    v[s] = make_float2(fmaf(x.x, h.x, -x.y * h.y), fmaf(-x.x, h.y, -x.y * h.x));
+                }
+            }
+            __syncthreads();
+        }
 #pragma unroll
         for (int s = 0; s < E; ++s) {
             const int j = t + NT * s;
-            if (j < B && i0 + j < N) rc[(int64_t)pulse * N + i0 + j] = v[s];
+            if (j < B && i0 + j < N) rc[(int64_t)pulse * N + i0 + j] = make_float2(v[s].x, -v[s].y);
         }
-        __syncthreads();
     }
     (void)M;
 }

@@ -216,10 +216,10 @@ def test_host_transfer_thread_policy(monkeypatch):
     monkeypatch.delenv("NIS_HOST_THREADS")
     monkeypatch.setattr(os, "sched_getaffinity", lambda pid: set(range(32)), raising=False)
     monkeypatch.setenv("LOCAL_WORLD_SIZE", "1")
-    assert hostio.host_threads() == 16
+    assert hostio.host_threads() == 12
     monkeypatch.setenv("LOCAL_WORLD_SIZE", "8")
     assert hostio.host_threads() == 3 and hostio._host_route(1 << 24) == 0      # 8 ranks on 32 cores: device route
     monkeypatch.setenv("LOCAL_WORLD_SIZE", "2")
-    assert hostio.host_threads() == 15
+    assert hostio.host_threads() == 12
     lib = _lib.load()
     assert lib.nis_d2h_widen(None, None, None, 4, 4, None) == -1 and "null argument" in _lib.last_error()
