@@ -7,13 +7,15 @@
 //   d2h_widen   device complex64 -> chunked DMA into a ring of page-locked slots -> T threads widen float -> double
 //               (AVX2, non-temporal stores) straight into the caller's array, one whole chunk per thread, no barrier
 //   h2d_narrow  caller's complex128 array (pageable is fine) -> T threads narrow into the ring -> chunked DMA
-// Measured (tools/d2h_widen_probe.cpp): 8192^2 image 19.0 ms -> 12-14 ms with 12-16 threads.
+// Measured (tools/d2h_widen_probe.cpp, tools/e2e_route_probe.py): 8192^2 image 19 ms -> 12-15 ms
+// with 8-12 threads on a rank that has the host to itself; with several ranks the host memory path is the limit either way.
 // float -> double is exact and double -> float rounds to nearest even, exactly as the device kernels k_widen / k_narrow
 // (api.cu) and numpy's astype do, so the bytes the caller sees do not depend on the route.
 #include <cuda_runtime.h>
 #include <immintrin.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <atomic>
@@ -26,8 +28,29 @@ void set_error(const char* fmt, ...);   // api.cu
 
 namespace {
 
-constexpr int kMaxSlots = 40;
-constexpr size_t kChunkFloats = size_t(1) << 20;   // 4 MiB of complex64 per slot = 8 MiB of complex128
+constexpr int kMaxSlots = 64;
+constexpr size_t kSlotFloats = size_t(1) << 20;    // capacity of a ring slot: 4 MiB of complex64 = 8 MiB of complex128
+
+// chunk length (floats) and ring depth in use; NIS_HOST_CHUNK_KB / NIS_HOST_SLOTS override them (development knobs)
+size_t chunk_floats() {
+    static const size_t v = [] {
+        size_t kb = 1024;   // measured: 1 MiB chunks beat 4 MiB by 10-15 % alone and with two ranks (staging reads hit the LLC)
+        if (const char* e = getenv("NIS_HOST_CHUNK_KB")) kb = (size_t)atol(e);
+        if (kb < 64) kb = 64;
+        if (kb > 4096) kb = 4096;
+        return kb * 1024 / sizeof(float);
+    }();
+    return v;
+}
+int ring_slots(int threads) {
+    static const int forced = [] {
+        const char* e = getenv("NIS_HOST_SLOTS");
+        return e ? atoi(e) : 0;
+    }();
+    int n = forced > 0 ? forced : 2 * threads + 4;
+    if (n < threads + 2) n = threads + 2;
+    return n > kMaxSlots ? kMaxSlots : n;
+}
 
 struct Ring {
     std::mutex mu;                 // one transfer at a time per device
@@ -40,7 +63,7 @@ Ring g_ring[64];
 bool ring_reserve(Ring& r, int want, cudaError_t* err) {
     while (r.n < want) {
         float* p = nullptr;
-        cudaError_t e = cudaHostAlloc(reinterpret_cast<void**>(&p), kChunkFloats * sizeof(float), cudaHostAllocDefault);
+        cudaError_t e = cudaHostAlloc(reinterpret_cast<void**>(&p), kSlotFloats * sizeof(float), cudaHostAllocDefault);
         if (e == cudaSuccess) {
             e = cudaEventCreateWithFlags(&r.ev[r.n], cudaEventDisableTiming);
             if (e != cudaSuccess) cudaFreeHost(p);
@@ -81,7 +104,19 @@ void narrow(const double* s, float* d, size_t n) {
     for (size_t i = 0; i < n; ++i) d[i] = (float)s[i];
 }
 
-inline void relax() { _mm_pause(); }
+// spin politely: a burst of pauses, then give the core away (the workers may share cores with the threads of other ranks)
+int spin_limit() {   // NIS_HOST_SPIN: pauses before the first yield (0: never yield; development knob)
+    static const int v = [] { const char* e = getenv("NIS_HOST_SPIN"); return e ? atoi(e) : 2048; }();
+    return v;
+}
+struct Backoff {
+    int n = 0;
+    void operator()() {
+        const int lim = spin_limit();
+        if (lim == 0 || ++n < lim) _mm_pause();
+        else { std::this_thread::yield(); n = lim / 2; }
+    }
+};
 
 int fail_cuda(const char* what, cudaError_t e) {
     set_error("%s failed: %s", what, cudaGetErrorString(e));
@@ -97,8 +132,9 @@ int hostcopy_d2h_widen(int device, const float* dev_src, double* dst, size_t n_f
     if (threads > 32) threads = 32;
     Ring& r = g_ring[device & 63];
     std::lock_guard<std::mutex> lock(r.mu);
+    const size_t kChunkFloats = chunk_floats();
     const size_t nchunks = (n_floats + kChunkFloats - 1) / kChunkFloats;
-    const int NS = (int)std::min<size_t>(nchunks, (size_t)std::min(kMaxSlots, 2 * threads + 4));
+    const int NS = (int)std::min<size_t>(nchunks, (size_t)ring_slots(threads));
     cudaError_t err = cudaSuccess;
     if (!ring_reserve(r, NS, &err)) return fail_cuda("cudaHostAlloc (transfer ring)", err);
 
@@ -109,6 +145,7 @@ int hostcopy_d2h_widen(int device, const float* dev_src, double* dst, size_t n_f
     auto len_of = [&](size_t c) { return std::min(kChunkFloats, n_floats - c * kChunkFloats); };
     auto worker = [&](int k) {
         for (size_t c = (size_t)k; c < nchunks; c += (size_t)threads) {
+            Backoff relax;
             while (arrived.load(std::memory_order_acquire) <= (long)c) {
                 if (abort_flag.load(std::memory_order_relaxed)) return;
                 relax();
@@ -134,6 +171,7 @@ int hostcopy_d2h_widen(int device, const float* dev_src, double* dst, size_t n_f
         return cudaSuccess;
     };
     for (size_t c = 0; c < nchunks && err == cudaSuccess; ++c) {
+        Backoff relax;
         while (err == cudaSuccess && next <= c) {    // (cannot stall: chunk c - NS was published long ago)
             err = enqueue_ready();
             if (next <= c) relax();
@@ -168,8 +206,9 @@ int hostcopy_h2d_narrow(int device, const double* src, float* dev_dst, size_t n_
     if (threads > 32) threads = 32;
     Ring& r = g_ring[device & 63];
     std::lock_guard<std::mutex> lock(r.mu);
+    const size_t kChunkFloats = chunk_floats();
     const size_t nchunks = (n_floats + kChunkFloats - 1) / kChunkFloats;
-    const int NS = (int)std::min<size_t>(nchunks, (size_t)std::min(kMaxSlots, 2 * threads + 4));
+    const int NS = (int)std::min<size_t>(nchunks, (size_t)ring_slots(threads));
     cudaError_t err = cudaSuccess;
     if (!ring_reserve(r, NS, &err)) return fail_cuda("cudaHostAlloc (transfer ring)", err);
 
@@ -180,6 +219,7 @@ int hostcopy_h2d_narrow(int device, const double* src, float* dev_dst, size_t n_
     auto len_of = [&](size_t c) { return std::min(kChunkFloats, n_floats - c * kChunkFloats); };
     auto worker = [&](int k) {
         for (size_t c = (size_t)k; c < nchunks; c += (size_t)threads) {
+            Backoff relax;
             while ((long)c >= freed.load(std::memory_order_acquire) + NS) {
                 if (abort_flag.load(std::memory_order_relaxed)) return;
                 relax();
@@ -202,6 +242,7 @@ int hostcopy_h2d_narrow(int device, const double* src, float* dev_dst, size_t n_
             freed.store(++fr, std::memory_order_release);
         }
     };
+    Backoff relax;
     while (sent < nchunks && err == cudaSuccess) {
         if (filled[sent].load(std::memory_order_acquire)) {
             err = cudaMemcpyAsync(dev_dst + sent * kChunkFloats, r.slot[sent % NS], len_of(sent) * sizeof(float),

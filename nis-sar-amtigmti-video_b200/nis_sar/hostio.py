@@ -36,7 +36,8 @@ _MIN_ELEMENTS_FOR_HOST_ROUTE = 1 << 21
 
 def host_threads() -> int:
     """Worker threads of the host-converted transfers: ``NIS_HOST_THREADS``, else the cores this process may run on
-    divided among the ranks of the node (``LOCAL_WORLD_SIZE``), one left for the thread that drives the DMA, at most 12."""
+    divided among the ranks of the node (``LOCAL_WORLD_SIZE``), two left for the thread that drives the DMA and the
+    runtime's own threads (spinning workers on an over-subscribed host cost 2-3 x: tools/e2e_route_probe.py), at most 12."""
     env = os.environ.get("NIS_HOST_THREADS")
     if env is not None:
         try:
@@ -48,7 +49,7 @@ def host_threads() -> int:
     except AttributeError:
         avail = os.cpu_count() or 1
     ranks = max(1, int(os.environ.get("LOCAL_WORLD_SIZE", "1") or 1))
-    return max(0, min(12, avail // ranks - 1))     # measured: 8-12 workers saturate the host memory path
+    return max(0, min(12, avail // ranks - 2))     # measured: 8-12 workers saturate the host memory path
 
 
 # what the last to_host_c128 / to_device_c64 call did (bench.py reports the bytes that really crossed PCIe)

@@ -218,7 +218,7 @@ def test_host_transfer_thread_policy(monkeypatch):
     monkeypatch.setenv("LOCAL_WORLD_SIZE", "1")
     assert hostio.host_threads() == 12
     monkeypatch.setenv("LOCAL_WORLD_SIZE", "8")
-    assert hostio.host_threads() == 3 and hostio._host_route(1 << 24) == 0      # 8 ranks on 32 cores: device route
+    assert hostio.host_threads() == 2 and hostio._host_route(1 << 24) == 0      # 8 ranks on 32 cores: device route
     monkeypatch.setenv("LOCAL_WORLD_SIZE", "2")
     assert hostio.host_threads() == 12
     lib = _lib.load()

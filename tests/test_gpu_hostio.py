@@ -9,7 +9,7 @@ from nis_sar import hostio
 
 pytestmark = pytest.mark.gpu
 
-CHUNK = 1 << 19     # complex elements per ring slot (4 MiB of complex64)
+CHUNK = 1 << 17     # complex elements per transfer chunk (1 MiB of complex64)
 
 
 def _rand_c64(n, seed):
@@ -19,7 +19,7 @@ def _rand_c64(n, seed):
 
 
 @pytest.mark.parametrize("threads", [1, 3, 8])
-@pytest.mark.parametrize("n", [1, 7, 4099, CHUNK - 1, CHUNK + 5, 9 * CHUNK + 12345])
+@pytest.mark.parametrize("n", [1, 7, 4099, CHUNK - 1, CHUNK + 5, 9 * CHUNK + 12345, 45 * CHUNK + 3])   # the last wraps every ring
 def test_d2h_widen_is_bitwise_the_device_route(n, threads, monkeypatch):
     x = _rand_c64(n, n % 1000 + threads)
     monkeypatch.setenv("NIS_HOST_THREADS", "0")
@@ -41,7 +41,7 @@ def test_d2h_widen_is_bitwise_the_device_route(n, threads, monkeypatch):
 
 
 @pytest.mark.parametrize("threads", [1, 5])
-@pytest.mark.parametrize("n", [3, 4099, CHUNK + 5, 6 * CHUNK + 777])
+@pytest.mark.parametrize("n", [3, 4099, CHUNK + 5, 6 * CHUNK + 777, 31 * CHUNK + 1])
 def test_h2d_narrow_is_bitwise_numpy_astype(n, threads, monkeypatch):
     rng = np.random.default_rng(n + threads)
     h = (rng.standard_normal(n) * 10.0 ** rng.integers(-30, 30, n) + 1j * rng.standard_normal(n)).astype(np.complex128)
