@@ -218,7 +218,7 @@ __global__ void __launch_bounds__(P::NT* W) k_az_inner_tma(const __grid_constant
 // scaled, corner-turned image slc[column][azimuth] with azimuth-contiguous 256-byte stores, plus max |slc|^2.
 // Several CTAs of different clusters share an SM, so one cluster's load / barrier latency hides behind another's math.
 template <class P, int C, int W, bool INV, bool TOUT, bool PH>
-__global__ void __launch_bounds__(P::NT* W, 1024 / (P::NT * W)) k_az_cluster(const __grid_constant__ CUtensorMap map,
+__global__ void __launch_bounds__(P::NT* W, (P::E >= 32 ? 512 : 1024) / (P::NT * W)) k_az_cluster(const __grid_constant__ CUtensorMap map,
                                                          float2* __restrict__ out, int64_t out_pitch, int n_col_tiles,
                                                          float scale, double* __restrict__ max_sq,
                                                          const float2* __restrict__ tw, const float2* __restrict__ twN,
@@ -668,6 +668,8 @@ using P16384 = Plan<16384, 16, 16, 16, 8, 8>;
 // 8192 samples, 32 per thread: three passes (two shared-memory exchanges per transform instead of three) on 256 threads that
 // may use the whole register file (one CTA per SM either way) -- the default at 8192 samples
 using P8192E32 = Plan<8192, 32, 32, 16, 16>;
+using P512E32 = Plan<512, 32, 32, 16, 1>;
+using P1024E32 = Plan<1024, 32, 32, 32, 1>;
 
 template <class P>
 int upload_twiddles(float2** dev) {
@@ -769,6 +771,8 @@ const AzClusterCfg kAzCluster[] = {
     {8192, 3, az_cluster_setup<P512, 16, 16>},
     {4096, 1, az_cluster_setup<P512, 8, 8>},  {4096, 2, az_cluster_setup<P1024, 4, 8>},
     {4096, 3, az_cluster_setup<P256, 16, 8>}, {4096, 4, az_cluster_setup<P256, 16, 16>},
+    {4096, 5, az_cluster_setup<P512E32, 8, 16>}, {4096, 6, az_cluster_setup<P512E32, 8, 8>},
+    {8192, 5, az_cluster_setup<P1024E32, 8, 8>}, {8192, 6, az_cluster_setup<P512E32, 16, 16>},
     {2048, 1, az_cluster_setup<P256, 8, 8>},  {2048, 2, az_cluster_setup<P512, 4, 8>},
     {1024, 1, az_cluster_setup<P256, 4, 8>},
 };
@@ -820,8 +824,29 @@ int setup_az_four_step(nis_csa_plan* pl) {
         case 256: pl->inner_w = 16; pl->inner = launch_inner<P256, 16>; TRY_RC(upload_twiddles<P256>(&pl->tw_inner)); break;
         // 512-point tiles: 16 columns (128-byte row pieces, one 512-thread CTA per SM) measured 12 % faster than 8 columns
         // (three 256-thread CTAs per SM): 0.194 vs 0.220 ms per transform at 8192^2; 4 columns: 0.245 ms
-        case 512: pl->inner_w = 16; pl->inner = launch_inner<P512, 16>; TRY_RC(upload_twiddles<P512>(&pl->tw_inner)); break;
-        default: pl->inner_w = 8; pl->inner = launch_inner<P1024, 8>; TRY_RC(upload_twiddles<P1024>(&pl->tw_inner)); break;
+        // 512- and 1024-point tiles: 32 samples per thread, TWO passes (32 x 16, 32 x 32) = one exchange through the tile
+        // instead of two -- three shared-memory accesses per sample instead of five, 256 threads.  Measured at 8192^2:
+        // 0.197 -> 0.184 ms per stage (5.8 TB/s).  NIS_AZ_INNER_PLAN=e16 restores the three-pass plans (development knob).
+        case 512:
+            pl->inner_w = 16;
+            if (const char* v = getenv("NIS_AZ_INNER_PLAN"); v && v[0] == 'e' && v[1] == '1') {
+                pl->inner = launch_inner<P512, 16>;
+                TRY_RC(upload_twiddles<P512>(&pl->tw_inner));
+            } else {
+                pl->inner = launch_inner<P512E32, 16>;
+                TRY_RC(upload_twiddles<P512E32>(&pl->tw_inner));
+            }
+            break;
+        default:
+            pl->inner_w = 8;
+            if (const char* v = getenv("NIS_AZ_INNER_PLAN"); v && v[0] == 'e' && v[1] == '1') {
+                pl->inner = launch_inner<P1024, 8>;
+                TRY_RC(upload_twiddles<P1024>(&pl->tw_inner));
+            } else {
+                pl->inner = launch_inner<P1024E32, 8>;
+                TRY_RC(upload_twiddles<P1024E32>(&pl->tw_inner));
+            }
+            break;
     }
 #undef TRY_RC
     if (n_rg % pl->inner_w) {
@@ -995,8 +1020,13 @@ extern "C" int nis_csa_plan_create(nis_ctx* ctx, int32_t n_az, int32_t n_rg, con
         for (const auto& s : kAzSplits)
             if (s.n == n_az) { pl->A1 = s.a1; pl->A2 = s.a2; }
         // default: whole-column cluster transforms where they measured faster than the two-kernel four-step
-        // (n_az = 4096: 0.187 vs 0.204 ms per frame on a B200); NIS_CSA_AZ = 0 / k overrides (development knob)
-        int az_id = (n_az == 4096) ? 1 : 0;
+        // (n_az = 4096: 0.187 vs 0.204 ms per frame on a B200); NIS_CSA_AZ = 0 / k overrides (development knob).
+        // Configuration 6 (round 2): 512-point per-CTA transforms on the TWO-pass plan 32 x 16 (32 samples per thread, one
+        // exchange through the tile instead of two, 128-thread CTAs): 0.0856 / 0.0863 ms per transform at 4096^2 against
+        // 0.0936 / 0.0941 for configuration 1 (three passes, 256 threads); 16-column tiles (5): 0.097 / 0.103.  At 8192 the
+        // same plans (5: 8 x 1024, 6: 16 x 512) reach 0.38-0.39 / 0.45-0.47 ms per transform: the four-step engine (0.354 /
+        // 0.384 for its two kernels) stays the default there.
+        int az_id = (n_az == 4096) ? 6 : 0;
         if (const char* v = getenv("NIS_CSA_AZ")) az_id = atoi(v);
         for (const auto& c : kAzCluster)
             if (c.n_az == n_az && c.id == az_id && n_rg % 16 == 0) FAIL_IF(c.setup(pl));
