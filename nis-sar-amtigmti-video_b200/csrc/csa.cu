@@ -773,6 +773,7 @@ const AzClusterCfg kAzCluster[] = {
     {4096, 3, az_cluster_setup<P256, 16, 8>}, {4096, 4, az_cluster_setup<P256, 16, 16>},
     {4096, 5, az_cluster_setup<P512E32, 8, 16>}, {4096, 6, az_cluster_setup<P512E32, 8, 8>},
     {8192, 5, az_cluster_setup<P1024E32, 8, 8>}, {8192, 6, az_cluster_setup<P512E32, 16, 16>},
+    {8192, 7, az_cluster_setup<P512E32, 16, 8>},
     {2048, 1, az_cluster_setup<P256, 8, 8>},  {2048, 2, az_cluster_setup<P512, 4, 8>},
     {1024, 1, az_cluster_setup<P256, 4, 8>},
 };
@@ -1019,6 +1020,8 @@ extern "C" int nis_csa_plan_create(nis_ctx* ctx, int32_t n_az, int32_t n_rg, con
     } else {
         for (const auto& s : kAzSplits)
             if (s.n == n_az) { pl->A1 = s.a1; pl->A2 = s.a2; }
+        // (8192 = 32 x 256 instead of 16 x 512 measured slower: 1.216 vs 1.096 ms per frame, the radix-32 corner-turning
+        // outer stage takes 0.271 ms)
         // default: whole-column cluster transforms where they measured faster than the two-kernel four-step
         // (n_az = 4096: 0.187 vs 0.204 ms per frame on a B200); NIS_CSA_AZ = 0 / k overrides (development knob).
         // Configuration 6 (round 2): 512-point per-CTA transforms on the TWO-pass plan 32 x 16 (32 samples per thread, one

@@ -163,7 +163,7 @@ def test_csa_random_input_vs_oracle(api, n_az, n_rg):
 @pytest.mark.gpu
 @pytest.mark.parametrize("n_az,az_cfg", [(1024, 1), (2048, 1), (2048, 2), (4096, 0), (4096, 1), (4096, 2), (4096, 3),
                                          (4096, 4), (4096, 5), (4096, 6), (8192, 1), (8192, 2), (8192, 3), (8192, 5),
-                                         (8192, 6), (16384, 1), (32768, 0)])
+                                         (8192, 6), (8192, 7), (16384, 1), (32768, 0)])
 def test_csa_azimuth_engines_vs_oracle(api, dev, n_az, az_cfg, monkeypatch):
     """Every azimuth engine of the power-of-two path -- the two-kernel four-step (0) and each thread-block-cluster
     configuration (cluster size x per-CTA transform length x tile width) -- against the oracle, selected with the
