@@ -102,7 +102,16 @@ __global__ void __launch_bounds__(256) k_az_outer_inv(const float2* __restrict__
         slc[(int64_t)(n0 + nn) * n_az + a1 * A2 + a20 + l] = x;
         if (max_sq != nullptr) m = fmax(m, sq_mag_f64(x));
     }
-    if (max_sq != nullptr) atomic_max_f64(max_sq, warp_max_f64(m));
+    if (max_sq != nullptr) {   // one atomic per CTA (16384 CTAs at 8192^2), not one per warp
+        __shared__ double wmax[8];
+        m = warp_max_f64(m);
+        if ((threadIdx.x & 31) == 0) wmax[threadIdx.x >> 5] = m;
+        __syncthreads();
+        if (threadIdx.x < 32) {
+            m = threadIdx.x < 8 ? wmax[threadIdx.x] : 0.0;
+            atomic_max_f64(max_sq, warp_max_f64(m));
+        }
+    }
 }
 
 

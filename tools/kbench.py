@@ -37,7 +37,9 @@ def csa_stages(n_az, n_rg, iters=10):
     x = torch.view_as_complex(torch.randn((n_az, n_rg, 2), device="cuda"))
     out = torch.empty((n_rg, n_az), dtype=torch.complex64, device="cuda")
     total = time_cuda(lambda: plan.focus(x, out=out), iters)
-    rec = {"what": "csa", "n_az": n_az, "n_rg": n_rg, "ms": total,
+    mx = torch.zeros(1, dtype=torch.float64, device="cuda")
+    total_mx = time_cuda(lambda: plan.focus(x, out=out, max_sq=mx), iters)
+    rec = {"what": "csa", "n_az": n_az, "n_rg": n_rg, "ms": total, "ms_with_max_sq": total_mx,
            "GBps_48B": 48.0 * n_az * n_rg / total * 1e-6, "frac": 48.0 * n_az * n_rg / total * 1e-6 / PEAK}
     try:
         plan.set_profiling(True)
