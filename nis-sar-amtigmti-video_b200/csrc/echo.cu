@@ -134,14 +134,15 @@ __device__ __forceinline__ void chirp_support(const EchoConst& k, const double* 
 // The fp64 geometry -- position, two norms, delay, exact chirp support -- is evaluated once per (scatterer, pulse) and kept
 // in shared memory; per chunk only the phase polynomial about the chunk centre is re-expanded (a dozen fp64 operations).
 // Measured on the bench scene (81 scatterers, 8192 x 8192): 263 M instead of 299 M warp instructions, 0.42 instead of
-// 0.49 ms, no spills at 72 registers (profiles/prof_echo_sparse_r2.txt).  What remains is the inner loop itself: per
+// 0.49 ms, no spills at 72 registers (profiles/prof_echo_sparse_r2.txt); later, at 64 registers (still no spills) and four
+// CTAs per SM: 0.418 -> 0.396 ms (ncu had shown 24 of 64 warp slots in use and the schedulers idle 44 % of the time).  What remains is the inner loop itself: per
 // (scatterer, warp) 13 instructions of loop control, 21 of per-scatterer set-up, 29 for the sixteen samples.  Tried and
 // rejected (measured slower): 32 samples per thread (113 registers, two CTAs per SM: 0.64 ms); per-warp work lists that
 // skip non-intersecting (scatterer, warp) pairs (dense kernel: +4 % on the vehicle and the default clutter scene -- the
 // ballot-compacted list and its indirection cost more than the 13-instruction skips they remove); record tiles double
 // buffered with one barrier per tile instead of two (no change: the barrier stalls ncu shows are load imbalance).
 template <int SPT>
-__global__ void __launch_bounds__(256, 3) k_echo_sparse(EchoConst k, EchoTail<SPT> tail, const double* __restrict__ pos0,
+__global__ void __launch_bounds__(256, 4) k_echo_sparse(EchoConst k, EchoTail<SPT> tail, const double* __restrict__ pos0,
                                                         const double* __restrict__ vel, const double* __restrict__ amp,
                                                         const double* __restrict__ pos_tx, const double* __restrict__ pos_rx,
                                                         const double* __restrict__ t_slow, const double* __restrict__ t_fast,
