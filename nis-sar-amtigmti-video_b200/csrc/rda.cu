@@ -41,8 +41,10 @@ struct RdaRow {          // one per stored Doppler row
 static_assert(sizeof(RdaRow) == 40, "RdaRow layout");
 
 // ------------------------------------------------------------------------------ range compression
+// (8192 points on the 32-samples-per-thread three-pass plan: 256 threads at <= 128 registers, two CTAs per SM -- the
+// arrangement of k_range_rolled in csa.cu)
 template <class P, int PAD>
-__global__ void __launch_bounds__(P::NT) k_rda_range(const float2* __restrict__ in, int64_t in_pitch,
+__global__ void __launch_bounds__(P::NT, (P::E == 32 && P::N == 8192) ? 2 : 1) k_rda_range(const float2* __restrict__ in, int64_t in_pitch,
                                                      float2* __restrict__ work, int64_t work_pitch,
                                                      float2* __restrict__ rc_out, int n_rows, int N, int s0,
                                                      const float2* __restrict__ Hf, const float* __restrict__ win,
@@ -146,7 +148,7 @@ __global__ void __launch_bounds__(P::NT) k_rda_range_blocked(const float2* __res
 // the row buffer leaves no shared memory for A, which is parked in a per-CTA global scratch line instead -- 128 KB per CTA,
 // written and re-read by the same thread, resident in L2.
 template <class P, int PAD, bool GPARK>
-__global__ void __launch_bounds__(P::NT) k_rda_range_pruned(const float2* __restrict__ in, int64_t in_pitch,
+__global__ void __launch_bounds__(P::NT, (P::E == 32 && P::N == 8192) ? 2 : 1) k_rda_range_pruned(const float2* __restrict__ in, int64_t in_pitch,
                                                             float2* __restrict__ work, int64_t work_pitch,
                                                             float2* __restrict__ rc_out, int n_rows, int N, int s0,
                                                             const float2* __restrict__ HfE, const float2* __restrict__ HfO,
@@ -322,6 +324,7 @@ using P2048 = Plan<2048, 16, 16, 16, 8>;
 using P4096 = Plan<4096, 16, 16, 16, 16>;
 using P8192 = Plan<8192, 16, 16, 8, 8, 8>;
 using P16384 = Plan<16384, 32, 32, 32, 16>;
+using P8192E32 = Plan<8192, 32, 32, 16, 16>;
 
 void host_fft_pow2(std::vector<std::complex<double>>& a) {   // in-place radix-2, forward
     const size_t n = a.size();
@@ -609,6 +612,13 @@ extern "C" int nis_rda_plan_create(nis_ctx* ctx, int32_t P, int32_t S, const nis
         CUDA_FAIL_IF(cudaMalloc(&pl->gpark, (size_t)pl->gpark_lines * 16384 * sizeof(float2)));
         pl->range_fn = launch_rda_range_pruned<P16384, 5, true>;
         FAIL_IF(upload_tw<P16384>(&pl->tw));
+    } else if (prune && !getenv("NIS_RDA_E16")) {
+        // two CTAs per SM: 32 samples per thread on the three-pass plan, one transform body at <= 128 registers, A parked in an
+        // L2-resident scratch line per CTA instead of shared memory (which would hold one CTA only)
+        pl->gpark_lines = 2 * ctx->num_sms;
+        CUDA_FAIL_IF(cudaMalloc(&pl->gpark, (size_t)pl->gpark_lines * 8192 * sizeof(float2)));
+        pl->range_fn = launch_rda_range_pruned<P8192E32, 5, true>;
+        FAIL_IF(upload_tw<P8192E32>(&pl->tw));
     } else if (prune) {
         pl->range_fn = launch_rda_range_pruned<P8192, 4, false>;
         FAIL_IF(upload_tw<P8192>(&pl->tw));
@@ -618,7 +628,10 @@ extern "C" int nis_rda_plan_create(nis_ctx* ctx, int32_t P, int32_t S, const nis
         case 1024: pl->range_fn = launch_rda_range<P1024, 4>; FAIL_IF(upload_tw<P1024>(&pl->tw)); break;
         case 2048: pl->range_fn = launch_rda_range<P2048, 4>; FAIL_IF(upload_tw<P2048>(&pl->tw)); break;
         case 4096: pl->range_fn = launch_rda_range<P4096, 4>; FAIL_IF(upload_tw<P4096>(&pl->tw)); break;
-        case 8192: pl->range_fn = launch_rda_range<P8192, 4>; FAIL_IF(upload_tw<P8192>(&pl->tw)); break;
+        case 8192:
+            if (getenv("NIS_RDA_E16")) { pl->range_fn = launch_rda_range<P8192, 4>; FAIL_IF(upload_tw<P8192>(&pl->tw)); }
+            else { pl->range_fn = launch_rda_range<P8192E32, 5>; FAIL_IF(upload_tw<P8192E32>(&pl->tw)); }
+            break;
         default: pl->range_fn = launch_rda_range<P16384, 5>; FAIL_IF(upload_tw<P16384>(&pl->tw)); break;
     }
     // ---- azimuth Hamming weights (:396)
