@@ -678,6 +678,7 @@ using P16384 = Plan<16384, 16, 16, 16, 8, 8>;
 // may use the whole register file (one CTA per SM either way) -- the default at 8192 samples
 using P8192E32 = Plan<8192, 32, 32, 16, 16>;
 using P512E32 = Plan<512, 32, 32, 16, 1>;
+using P16384E32 = Plan<16384, 32, 32, 32, 16>;
 using P1024E32 = Plan<1024, 32, 32, 32, 1>;
 
 template <class P>
@@ -1122,7 +1123,15 @@ extern "C" int nis_csa_plan_create(nis_ctx* ctx, int32_t n_az, int32_t n_rg, con
             }
             break;
         }
-        default: pl->range = launch_range<P16384, 4, 1, 1>; FAIL_IF(upload_twiddles<P16384>(&pl->tw_rg)); break;
+        default:   // 16384 samples: the rolled form on the three-pass plan 32 x 32 x 16 (512 threads, one CTA per SM)
+            if (pl->phase_in_az || getenv("NIS_RANGE_PLAN")) {
+                pl->range = launch_range<P16384, 4, 1, 1>;
+                FAIL_IF(upload_twiddles<P16384>(&pl->tw_rg));
+            } else {
+                pl->range = launch_range_rolled<P16384E32, 5, 2, 1>;
+                FAIL_IF(upload_twiddles<P16384E32>(&pl->tw_rg));
+            }
+            break;
     }
     FAIL_IF(upload_full_twiddles(pl));
 #undef FAIL_IF
