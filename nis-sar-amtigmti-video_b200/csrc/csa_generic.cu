@@ -266,12 +266,45 @@ __device__ __forceinline__ void bluestein_core(float2* v, int t, float2* sm, con
     __syncthreads();
 }
 
+// The same core with ONE copy of the transform in the instruction stream (the inverse transform runs as
+// conj(FFT(conj(.))), the direction of the DFT is a run-time sign): for the 32-samples-per-thread 16384-point plan, whose
+// kernels inlined two to four transform bodies and spilled 460-1900 bytes per thread at the plan's 128-register cap.
+template <class P, int PAD>
+__device__ __forceinline__ void bluestein_core_rolled(float2* v, int t, float2* sm, const GenDev& g, bool inv) {
+    constexpr int E = P::E, NT = P::NT;
+    const float sg = inv ? -1.0f : 1.0f;
+#pragma unroll 1
+    for (int step = 0; step < 2; ++step) {
+        transform<P, false, 1, PAD>(v, t, sm, g.tw_pow2);
+        if (step == 0) {   // v <- conj(v h), h conjugated for the inverse DFT
+#pragma unroll
+            for (int s = 0; s < E; ++s) {
+                float2 h = __ldg(g.bfft + t + NT * s);
+                h.y *= sg;
+                const float2 w = cmul(v[s], h);
+                v[s] = make_float2(w.x, -w.y);
+            }
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int s = 0; s < E; ++s) {
+        const int idx = t + NT * s;
+        if (idx < g.N) {
+            float2 a = __ldg(g.chirp + idx);
+            a.y *= sg;
+            v[s] = cmul(make_float2(v[s].x, -v[s].y), a);
+        }
+    }
+}
+
 template <int MODE, class P, int PAD>
 __global__ void __launch_bounds__(P::NT) k_row_blue(GenDev g, float2* __restrict__ data, int64_t pitch, int n_rows,
                                                     const RowCoef* __restrict__ coef, float scale,
                                                     double* __restrict__ max_sq) {
     extern __shared__ float2 sm[];
     constexpr int E = P::E, NT = P::NT;
+    constexpr bool ROLLED = P::E >= 32;
     const int t = threadIdx.x;
     double mx = 0.0;
     for (int row = blockIdx.x; row < n_rows; row += gridDim.x) {
@@ -291,20 +324,40 @@ __global__ void __launch_bounds__(P::NT) k_row_blue(GenDev g, float2* __restrict
             }
             v[s] = x;
         }
-        if (MODE == AZ_INV) bluestein_core<P, PAD, true>(v, t, sm, g);
-        else bluestein_core<P, PAD, false>(v, t, sm, g);
-        if (MODE == RANGE) {
+        if constexpr (ROLLED) {
+            // forward DFT (or the inverse one for AZ_INV); in RANGE mode a second trip: x Phi2, inverse DFT
+#pragma unroll 1
+            for (int pass = 0; pass < (MODE == RANGE ? 2 : 1); ++pass) {
+                if (MODE == RANGE && pass == 1) {
 #pragma unroll
-            for (int s = 0; s < E; ++s) {
-                const int idx = t + NT * s;
-                float2 x = make_float2(0.f, 0.f);
-                if (idx < g.N) {
-                    x = cmul(v[s], cis_u64(phi2_phase(rc, (uint32_t)idx, (uint32_t)g.N)));
-                    x = cmul_conj(x, __ldg(g.chirp + idx));
+                    for (int s = 0; s < E; ++s) {
+                        const int idx = t + NT * s;
+                        float2 x = make_float2(0.f, 0.f);
+                        if (idx < g.N) {
+                            x = cmul(v[s], cis_u64(phi2_phase(rc, (uint32_t)idx, (uint32_t)g.N)));
+                            x = cmul_conj(x, __ldg(g.chirp + idx));
+                        }
+                        v[s] = x;
+                    }
                 }
-                v[s] = x;
+                bluestein_core_rolled<P, PAD>(v, t, sm, g, MODE == AZ_INV || pass == 1);
             }
-            bluestein_core<P, PAD, true>(v, t, sm, g);
+        } else {
+            if (MODE == AZ_INV) bluestein_core<P, PAD, true>(v, t, sm, g);
+            else bluestein_core<P, PAD, false>(v, t, sm, g);
+            if (MODE == RANGE) {
+#pragma unroll
+                for (int s = 0; s < E; ++s) {
+                    const int idx = t + NT * s;
+                    float2 x = make_float2(0.f, 0.f);
+                    if (idx < g.N) {
+                        x = cmul(v[s], cis_u64(phi2_phase(rc, (uint32_t)idx, (uint32_t)g.N)));
+                        x = cmul_conj(x, __ldg(g.chirp + idx));
+                    }
+                    v[s] = x;
+                }
+                bluestein_core<P, PAD, true>(v, t, sm, g);
+            }
         }
 #pragma unroll
         for (int s = 0; s < E; ++s) {
