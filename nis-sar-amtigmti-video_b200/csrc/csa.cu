@@ -838,6 +838,8 @@ int setup_az_four_step(nis_csa_plan* pl) {
         // 512- and 1024-point tiles: 32 samples per thread, TWO passes (32 x 16, 32 x 32) = one exchange through the tile
         // instead of two -- three shared-memory accesses per sample instead of five, 256 threads.  Measured at 8192^2:
         // 0.197 -> 0.184 ms per stage (5.8 TB/s).  NIS_AZ_INNER_PLAN=e16 restores the three-pass plans (development knob).
+        // (Single-buffered 64 KB tiles with THREE such CTAs per SM, the next tile pulled into the same buffer after the last
+        // gather: 0.183 / 0.185 ms -- no change, occupancy is not what limits this stage; not kept.)
         case 512:
             pl->inner_w = 16;
             if (const char* v = getenv("NIS_AZ_INNER_PLAN"); v && v[0] == 'e' && v[1] == '1') {
