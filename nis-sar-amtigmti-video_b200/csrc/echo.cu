@@ -29,6 +29,7 @@ namespace {
 struct EchoConst {
     double c, fc, k_rate, t_p, t_start, dt_fast;
     double a_turns;  // (k/2) dt^2
+    uint64_t a64;    // the same in 64-bit fixed-point turns (exact A m^2 mod 1 by integer wrap-around)
     int T, P0, S, per_target_velocity, accumulate, bistatic;
     int spotlight;   // 1: run_physics_spotlight model (sar_batch_sim.py:83-169): pos_rx carries the platform velocity
     double ant;      // pi l_ant / lambda of the one-way sinc^2 pattern (spotlight)
@@ -52,16 +53,24 @@ __device__ __forceinline__ bool gate(const double* __restrict__ t_fast, int n, d
 
 // Inner loop of both kernels: add the samples [t_lo, t_hi) (relative to the chunk start) of every kept scatterer of the
 // chunk to the thread's accumulators.
+// Control flow is decided per WARP, not per thread (late round 2; ncu on the bench scene had shown the lane that
+// straddles an end of a chirp running a 78-instruction predicated copy of the sample loop on its own, after the other 31
+// lanes had run theirs -- 15 % of all instructions -- and on short chirps, sar_vehicle_sim.py's 360 samples, every warp a
+// chirp touches has such a lane): a chirp either misses the warp's 32 windows (skip), covers all of them (plain loop, no
+// per-thread tests at all), or has an end among them -- then EVERY lane runs one predicated loop on a bit mask of its live
+// samples (one LOP3-to-predicate and one predicated packed add per sample).
 template <int SPT>
 __device__ __forceinline__ void accumulate_kept(float2 (&acc)[SPT], const uint4* __restrict__ rec,
                                                 const float2* __restrict__ recv, int total, int t_lo, int t_hi, int mt,
                                                 uint32_t k1, float2 vk2) {
     constexpr int HALF = SPT / 2;
+    const int wlo = t_lo - (int)(threadIdx.x & 31) * SPT, whi = wlo + 32 * SPT;   // the warp's samples
 #pragma unroll 1
     for (int q = 0; q < total; ++q) {
         const uint4 s = rec[q];
         const int lo = (int)(s.w & 0xffffu), hi = (int)(s.w >> 16);
-        if (t_lo >= hi || t_hi <= lo) continue;
+        if (wlo >= hi || whi <= lo) continue;          // (warp-uniform)
+        const bool whole = lo <= wlo && hi >= whi;     // (warp-uniform) every window of the warp is covered completely
         const uint32_t phi = s.x + s.y * (uint32_t)mt + k1;
         const float2 u = cscale_pk(cis_u32(phi), __uint_as_float(s.z));
         const float2 v = cmul_pk(recv[q], vk2);
@@ -74,7 +83,7 @@ __device__ __forceinline__ void accumulate_kept(float2 (&acc)[SPT], const uint4*
         const float c2 = 2.0f * v.x;
         float2 f0 = u, f1 = cmul_pk(u, v);
         float2 b0 = cmul_conj_pk(u, v), b1 = cfms_pk(c2, b0, u);
-        if (t_lo >= lo && t_hi <= hi) {
+        if (whole) {
 #pragma unroll
             for (int i = 0; i < HALF; i += 2) {
                 acc[HALF + i] = cadd_pk(acc[HALF + i], f0);
@@ -89,17 +98,15 @@ __device__ __forceinline__ void accumulate_kept(float2 (&acc)[SPT], const uint4*
                 }
             }
         } else {
-            const int a = lo - t_lo, b = hi - t_lo;   // live samples: a <= j < b
+            // bit j of `live` <-> sample t_lo + j lies in [lo, hi); lanes the chirp does not reach carry 0
+            const int ea = max(lo - t_lo, 0), eb = min(hi - t_lo, SPT);
+            const uint32_t live = ea < eb ? ((0xffffffffu >> (32 - eb)) & (0xffffffffu << ea)) : 0u;
 #pragma unroll
             for (int i = 0; i < HALF; i += 2) {
-                int j = HALF + i;
-                if (j >= a && j < b) acc[j] = cadd(acc[j], f0);
-                j = HALF + i + 1;
-                if (j >= a && j < b) acc[j] = cadd(acc[j], f1);
-                j = HALF - 1 - i;
-                if (j >= a && j < b) acc[j] = cadd(acc[j], b0);
-                j = HALF - 2 - i;
-                if (j >= a && j < b) acc[j] = cadd(acc[j], b1);
+                if (live & (1u << (HALF + i))) acc[HALF + i] = cadd_pk(acc[HALF + i], f0);
+                if (live & (1u << (HALF + i + 1))) acc[HALF + i + 1] = cadd_pk(acc[HALF + i + 1], f1);
+                if (live & (1u << (HALF - 1 - i))) acc[HALF - 1 - i] = cadd_pk(acc[HALF - 1 - i], b0);
+                if (live & (1u << (HALF - 2 - i))) acc[HALF - 2 - i] = cadd_pk(acc[HALF - 2 - i], b1);
                 if (i + 2 < HALF) {
                     f0 = cfms_pk(c2, f1, f0);
                     f1 = cfms_pk(c2, f0, f1);
@@ -240,6 +247,140 @@ __global__ void __launch_bounds__(256, 4) k_echo_sparse(EchoConst k, EchoTail<SP
 #pragma unroll
             for (int j = 0; j < SPT; ++j) {
                 if (n0 + t_lo + j < k.S) {
+                    float2 x = cmul(acc[j], tail.e[j]);
+                    if (k.accumulate == 2) {
+                        atomicAdd_system(&out[j].x, x.x);
+                        atomicAdd_system(&out[j].y, x.y);
+                    } else {
+                        if (k.accumulate) { const float2 o = out[j]; x.x += o.x; x.y += o.y; }
+                        out[j] = x;
+                    }
+                }
+            }
+        }
+    }
+}
+
+// Sparse scenes, second form (late round 2): the windows of a pulse are handed to the warps DYNAMICALLY.
+// In k_echo_sparse a warp owns one fixed window (32 x SPT samples) of every chunk and the CTA meets at a barrier per chunk:
+// with 81 chirps that cover a fifth of the sample window most (scatterer, window) pairs miss, the warps whose windows no
+// chirp reaches idle at the barrier, and the ones that work spend a fifth of their instructions skipping records (ncu:
+// issue slots 56 % busy, 24-32 resident warps of which about half own work).  Here a CTA is four independent warps; the
+// geometry of all scatterers is evaluated once per pulse, with the phase polynomial expanded about the PULSE centre in
+// 64-bit fixed point (exact over +-4096 samples, so it need not be re-expanded per chunk); then every warp repeatedly
+// takes the next window of the pulse from a shared counter, builds the list of the chirps that reach this window by
+// ballot (3 warp-wide tests for 81 scatterers) and runs the recurrence loop over that list only.  No barrier after the
+// prologue, no skipped records except at the two ends of a chirp.
+template <int SPT>
+__global__ void __launch_bounds__(128, 7) k_echo_sparse_dyn(EchoConst k, EchoTail<SPT> tail, const double* __restrict__ pos0,
+                                                            const double* __restrict__ vel, const double* __restrict__ amp,
+                                                            const double* __restrict__ pos_tx, const double* __restrict__ pos_rx,
+                                                            const double* __restrict__ t_slow, const double* __restrict__ t_fast,
+                                                            float2* __restrict__ raw, int n_windows) {
+    constexpr int NTH = 128, NW = NTH / 32, HALF = SPT / 2, WIN = 32 * SPT;
+    __shared__ uint64_t s_cq[256], s_bq[256];   // phase at the pulse centre and per sample, 2^-64 turns
+    __shared__ int2 s_sup[256];                 // absolute support [lo, hi)
+    __shared__ float s_amp[256];
+    __shared__ uint4 w_rec[NW][256];            // per warp: the records of the window in hand (format of accumulate_kept)
+    __shared__ float2 w_recv[NW][256];
+    __shared__ int s_next;
+
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int pulse = k.P0 + blockIdx.x;
+    const int nc = k.S / 2;
+    const double half = k.t_p / 2, off = half;
+    // this thread's samples relative to the centre of whatever window its warp holds: constants of the kernel
+    const int t_lo = lane * SPT, t_hi = t_lo + SPT;
+    const int mt = t_lo + HALF - WIN / 2;
+    const uint32_t k1 = frac32(k.a_turns * (double)mt * (double)mt);
+    const float2 vk2 = cis_u32(frac32(2.0 * k.a_turns * (double)mt));
+
+    // ---- once per pulse: geometry and phase polynomial of every scatterer
+    {
+        const double ti = t_slow[pulse];
+        const double tx0 = pos_tx[3 * pulse], tx1 = pos_tx[3 * pulse + 1], tx2 = pos_tx[3 * pulse + 2];
+        const double t_center = k.t_start + (double)nc * k.dt_fast;
+        for (int b = tid; b < k.T; b += NTH) {
+            const double* vb = k.per_target_velocity ? vel + 3 * b : vel;
+            const double px = __dadd_rn(pos0[3 * b], __dmul_rn(vb[0], ti)),
+                         py = __dadd_rn(pos0[3 * b + 1], __dmul_rn(vb[1], ti)),
+                         pz = __dadd_rn(pos0[3 * b + 2], __dmul_rn(vb[2], ti));
+            double dx = px - tx0, dy = py - tx1, dz = pz - tx2;
+            const double d_tx = sqrt(__dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz)));
+            double tau;
+            if (k.bistatic) {
+                dx = px - pos_rx[3 * pulse]; dy = py - pos_rx[3 * pulse + 1]; dz = pz - pos_rx[3 * pulse + 2];
+                const double d_rx = sqrt(__dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz)));
+                tau = __ddiv_rn(__dadd_rn(d_tx, d_rx), k.c);
+            } else {
+                tau = __ddiv_rn(__dmul_rn(2.0, d_tx), k.c);
+            }
+            int lo, hi;
+            chirp_support(k, t_fast, tau, off, half, lo, hi);
+            const double uu = t_center - tau - off;
+            s_cq[b] = turns_to_u64(fma(0.5 * k.k_rate * uu, uu, -k.fc * tau));
+            s_bq[b] = turns_to_u64(k.k_rate * uu * k.dt_fast);
+            s_sup[b] = make_int2(lo, hi);
+            s_amp[b] = (float)amp[b];
+        }
+        if (tid == 0) s_next = 0;
+    }
+    __syncthreads();
+
+    uint4* const rec = w_rec[wid];
+    float2* const recv = w_recv[wid];
+    for (;;) {
+        int w = 0;
+        if (lane == 0) w = atomicAdd(&s_next, 1);
+        w = __shfl_sync(0xffffffffu, w, 0);
+        if (w >= n_windows) break;
+        const int w_lo = w * WIN, w_hi = min(w_lo + WIN, k.S);
+        // ---- the chirps that reach this window, in scatterer order (deterministic summation order): each lane tests
+        // one scatterer and re-expands its phase polynomial about the WINDOW centre (64-bit integer arithmetic, exact)
+        const uint64_t wc = (uint64_t)(int64_t)(w_lo + WIN / 2 - nc);
+        int cnt = 0;
+        for (int b0 = 0; b0 < k.T; b0 += 32) {
+            const int b = b0 + lane;
+            bool ov = false;
+            int2 sup = make_int2(0, 0);
+            if (b < k.T) {
+                sup = s_sup[b];
+                ov = sup.x < w_hi && sup.y > w_lo;
+            }
+            const unsigned ball = __ballot_sync(0xffffffffu, ov);
+            if (ov) {
+                const uint64_t bq = s_bq[b];
+                const uint64_t c64 = s_cq[b] + bq * wc + k.a64 * (wc * wc);
+                const uint64_t b64 = bq + 2ull * k.a64 * wc;
+                const int slot = cnt + __popc(ball & ((1u << lane) - 1u));
+                uint4 r;
+                r.x = (uint32_t)(c64 >> 32);
+                r.y = (uint32_t)(b64 >> 32);
+                r.z = __float_as_uint(s_amp[b]);
+                r.w = (uint32_t)max(sup.x - w_lo, 0) | ((uint32_t)min(sup.y - w_lo, WIN) << 16);
+                rec[slot] = r;
+                recv[slot] = cis_u32(r.y);
+            }
+            cnt += __popc(ball);
+        }
+        __syncwarp();
+        float2 acc[SPT];
+#pragma unroll
+        for (int j = 0; j < SPT; ++j) acc[j] = make_float2(0.f, 0.f);
+        accumulate_kept<SPT>(acc, rec, recv, cnt, t_lo, t_hi, mt, k1, vk2);
+        __syncwarp();   // the list is rebuilt for the next window
+        if (w_lo + t_lo >= k.S) continue;
+        float2* out = raw + (int64_t)pulse * k.S + w_lo + t_lo;
+        if (k.accumulate == 0 && w_lo + t_hi <= k.S) {   // whole thread inside the sample window: 16-byte stores
+#pragma unroll
+            for (int j = 0; j < SPT; j += 2) {
+                const float2 x0 = cmul(acc[j], tail.e[j]), x1 = cmul(acc[j + 1], tail.e[j + 1]);
+                *reinterpret_cast<float4*>(out + j) = make_float4(x0.x, x0.y, x1.x, x1.y);
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < SPT; ++j) {
+                if (w_lo + t_lo + j < k.S) {
                     float2 x = cmul(acc[j], tail.e[j]);
                     if (k.accumulate == 2) {
                         atomicAdd_system(&out[j].x, x.x);
@@ -431,6 +572,13 @@ int launch_echo(nis_ctx* ctx, const EchoConst& k, const double* pos0, const doub
     const bool sparse_ok = !(sparse_env && sparse_env[0] == '0');
     if (sparse_ok && !k.spotlight && k.T > 0 && k.T <= 256 && n_pulses >= 2 * ctx->num_sms && (k.S % 2) == 0 &&
         (((uintptr_t)raw) & 15) == 0) {
+        // NIS_ECHO_SPARSE=chunk: the first form (fixed windows, one barrier per chunk); default: windows handed out dynamically
+        if (!(sparse_env && sparse_env[0] == 'c')) {
+            const int n_windows = (k.S + 32 * SPT - 1) / (32 * SPT);
+            k_echo_sparse_dyn<SPT><<<n_pulses, 128, 0, st>>>(k, tail, pos0, vel, amp, pos_tx, pos_rx, t_slow, t_fast, raw, n_windows);
+            NIS_LAUNCH_CHECK(ctx);
+            return NIS_OK;
+        }
         const int n_chunks = (k.S + 256 * SPT - 1) / (256 * SPT);
         k_echo_sparse<SPT><<<n_pulses, 256, 0, st>>>(k, tail, pos0, vel, amp, pos_tx, pos_rx, t_slow, t_fast, raw, n_chunks);
         NIS_LAUNCH_CHECK(ctx);
@@ -460,6 +608,7 @@ static int echo_common(nis_ctx* ctx, const nis_echo_params* prm, const double* t
     k.c = prm->c; k.fc = prm->fc; k.k_rate = prm->k_rate; k.t_p = prm->t_p;
     k.t_start = prm->t_start; k.dt_fast = prm->dt_fast;
     k.a_turns = 0.5 * prm->k_rate * prm->dt_fast * prm->dt_fast;
+    k.a64 = turns_to_u64(k.a_turns);
     k.T = T; k.P0 = P0; k.S = S; k.per_target_velocity = prm->per_target_velocity;
     k.accumulate = accumulate; k.bistatic = (pos_rx != nullptr) && !spotlight;
     k.spotlight = spotlight; k.ant = ant;
