@@ -473,12 +473,13 @@ def bench_config5_hrws(device, rank, world, n=4096):
         torch.cuda.synchronize(device)
         if world > 1:
             dist.barrier()
-        e0.record(cur)
-        for _ in range(reps):
+        evs = [_ev_pair() for _ in range(reps)]
+        for a_ev, b_ev in evs:       # per-repetition events, median: one slow NCCL send / recv (lazy connection set-up on a
+            a_ev.record(cur)         # ring neighbour) otherwise decides the mean of five
             out = fn()
-        e1.record(cur)
+            b_ev.record(cur)
         torch.cuda.synchronize(device)
-        return _max_ms(e0.elapsed_time(e1) / reps, device, world), out
+        return _max_ms(float(np.median([a_ev.elapsed_time(b_ev) for a_ev, b_ev in evs])), device, world), out
     if world == 1:
         other = channel(1)
         ms, out = timed(lambda: prod(mine, other))
