@@ -2,6 +2,8 @@
 #include <stdarg.h>
 #include <string.h>
 
+#include <exception>
+
 #include "common.cuh"
 
 namespace nis {
@@ -162,16 +164,26 @@ extern "C" int nis_d2h_widen(nis_ctx* ctx, const nis_c32* dev_src, double* host_
     NIS_REQUIRE(ctx && dev_src && host_dst, "nis_d2h_widen: null argument");
     NIS_REQUIRE(threads >= 1 && threads <= 32, "nis_d2h_widen: threads = %d outside 1..32", threads);
     DeviceGuard guard(ctx->device);
-    return hostcopy_d2h_widen(ctx->device, reinterpret_cast<const float*>(dev_src), host_dst, (size_t)n * 2, threads,
-                              (cudaStream_t)stream);
+    try {   // (std::thread / std::vector may throw; nothing crosses the C ABI)
+        return hostcopy_d2h_widen(ctx->device, reinterpret_cast<const float*>(dev_src), host_dst, (size_t)n * 2, threads,
+                                  (cudaStream_t)stream);
+    } catch (const std::exception& e) {
+        set_error("nis_d2h_widen: %s", e.what());
+        return NIS_ERR_NOMEM;
+    }
 }
 extern "C" int nis_h2d_narrow(nis_ctx* ctx, const double* host_src, nis_c32* dev_dst, uint64_t n, int32_t threads,
                               nis_stream stream) {
     NIS_REQUIRE(ctx && host_src && dev_dst, "nis_h2d_narrow: null argument");
     NIS_REQUIRE(threads >= 1 && threads <= 32, "nis_h2d_narrow: threads = %d outside 1..32", threads);
     DeviceGuard guard(ctx->device);
-    return hostcopy_h2d_narrow(ctx->device, host_src, reinterpret_cast<float*>(dev_dst), (size_t)n * 2, threads,
-                               (cudaStream_t)stream);
+    try {
+        return hostcopy_h2d_narrow(ctx->device, host_src, reinterpret_cast<float*>(dev_dst), (size_t)n * 2, threads,
+                                   (cudaStream_t)stream);
+    } catch (const std::exception& e) {
+        set_error("nis_h2d_narrow: %s", e.what());
+        return NIS_ERR_NOMEM;
+    }
 }
 
 namespace nis {
