@@ -156,7 +156,13 @@ int hostcopy_d2h_widen(int device, const float* dev_src, double* dst, size_t n_f
     };
     std::vector<std::thread> pool;
     pool.reserve(threads);
-    for (int k = 0; k < threads; ++k) pool.emplace_back(worker, k);
+    try {
+        for (int k = 0; k < threads; ++k) pool.emplace_back(worker, k);
+    } catch (...) {   // thread creation failed: release the workers that did start, then report
+        abort_flag.store(1);
+        for (auto& t : pool) t.join();
+        throw;
+    }
 
     size_t next = 0;                          // next chunk to enqueue
     auto enqueue_ready = [&]() -> cudaError_t {
@@ -230,7 +236,13 @@ int hostcopy_h2d_narrow(int device, const double* src, float* dev_dst, size_t n_
     };
     std::vector<std::thread> pool;
     pool.reserve(threads);
-    for (int k = 0; k < threads; ++k) pool.emplace_back(worker, k);
+    try {
+        for (int k = 0; k < threads; ++k) pool.emplace_back(worker, k);
+    } catch (...) {   // thread creation failed: release the workers that did start, then report
+        abort_flag.store(1);
+        for (auto& t : pool) t.join();
+        throw;
+    }
 
     size_t sent = 0;
     long fr = 0;
