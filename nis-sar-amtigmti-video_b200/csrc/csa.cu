@@ -463,7 +463,8 @@ __global__ void __launch_bounds__(P::NT* RPB, MINB) k_range(float2* __restrict__
 }
 
 // The same row pipeline with ONE copy of the transform in the instruction stream: the inverse transform is run as
-// conj(FFT(conj(.))) (bit-identical to the conjugated-twiddle form: every operation is mirrored exactly), so the loop
+// conj(FFT(conj(.))) (equal to the conjugated-twiddle form up to rounding -- the fused multiply-adds of the inter-pass
+// twiddles round the other product first: 1e-7 relative, csrc/hosttest/test_fft_host.cu), so the loop
 // body executes twice per row and the conjugations ride on the phase multiplies.  The straight-line form above is
 // 4096 SASS instructions (64 KB) at 8192 samples -- twice the 32 KB instruction cache, ncu: 5 % of the stalls
 // `no_instruction`; this one is a little more than half of that.  One row per CTA, next row prefetched by TMA.

@@ -11,14 +11,12 @@
 using namespace nis::fft;
 namespace nis { void set_error(const char*, ...) {} }
 
+// the transform of one row, threads emulated one after another; result in natural order
 template <class P, bool INV, int SMS, int PADSHIFT>
-double run_plan() {
+std::vector<float2> transform_host(const std::vector<float2>& x) {
     constexpr int N = P::N, E = P::E, NT = P::NT;
     std::vector<float2> tw(P::tw_len + 1);
     build_twiddles<P>(tw.data());
-    std::vector<float2> x(N);
-    srand(N * 7 + INV);
-    for (auto& e : x) e = make_float2(rand() / (float)RAND_MAX - 0.5f, rand() / (float)RAND_MAX - 0.5f);
     std::vector<std::vector<float2>> v(NT, std::vector<float2>(E));
     std::vector<float2> sm((size_t)(N + (PADSHIFT ? (N >> PADSHIFT) : 0) + 8) * SMS);
     for (int t = 0; t < NT; ++t)
@@ -49,6 +47,18 @@ double run_plan() {
             }
         }
     }
+    std::vector<float2> out(N);
+    for (int k = 0; k < N; ++k) out[k] = v[k % NT][k / NT];
+    return out;
+}
+
+template <class P, bool INV, int SMS, int PADSHIFT>
+double run_plan() {
+    constexpr int N = P::N;
+    std::vector<float2> x(N);
+    srand(N * 7 + INV);
+    for (auto& e : x) e = make_float2(rand() / (float)RAND_MAX - 0.5f, rand() / (float)RAND_MAX - 0.5f);
+    const std::vector<float2> v = transform_host<P, INV, SMS, PADSHIFT>(x);
     // reference DFT in double
     double err = 0, nrm = 0;
     const double two_pi = 6.283185307179586476925286766559;
@@ -58,12 +68,43 @@ double run_plan() {
             double a = (INV ? 1.0 : -1.0) * two_pi * (double)(((long long)k * n) % N) / N;
             acc += std::complex<double>(x[n].x, x[n].y) * std::complex<double>(cos(a), sin(a));
         }
-        float2 got = v[k % NT][k / NT];
+        float2 got = v[k];
         err += std::norm(acc - std::complex<double>(got.x, got.y));
         nrm += std::norm(acc);
     }
     return sqrt(err / nrm);
 }
+
+// The rolled kernels (k_range_rolled, the 16384-point range compressions, ...) run the inverse transform as
+// conj(FFT(conj(x))) through the FORWARD code path.  The butterflies of the conjugated-twiddle inverse are mirrored
+// exactly (sign flips only); the inter-pass twiddle multiplies are not -- fmaf(a.x, b.y, -(a.y b.x)) rounds the other
+// product first than fmaf(a.y, b.x, -(a.x b.y)) -- so the two agree to rounding, not bit for bit.  This pins how closely.
+template <class P, int SMS, int PADSHIFT>
+double conj_identity_error() {
+    constexpr int N = P::N;
+    std::vector<float2> x(N), xc(N);
+    srand(N * 13 + 5);
+    for (int i = 0; i < N; ++i) {
+        x[i] = make_float2(rand() / (float)RAND_MAX - 0.5f, rand() / (float)RAND_MAX - 0.5f);
+        xc[i] = make_float2(x[i].x, -x[i].y);
+    }
+    const std::vector<float2> inv = transform_host<P, true, SMS, PADSHIFT>(x);
+    const std::vector<float2> fwd = transform_host<P, false, SMS, PADSHIFT>(xc);
+    double err = 0, nrm = 0;
+    for (int i = 0; i < N; ++i) {
+        const double dr = (double)inv[i].x - fwd[i].x, di = (double)inv[i].y + fwd[i].y;
+        err += dr * dr + di * di;
+        nrm += (double)inv[i].x * inv[i].x + (double)inv[i].y * inv[i].y;
+    }
+    return sqrt(err / nrm);
+}
+
+#define CHECK_CONJ(P, SMS, PAD)                                                                  \
+    do {                                                                                         \
+        const double e = conj_identity_error<P, SMS, PAD>();                                      \
+        printf("%-28s sms=%d pad=%d |inverse - conj(forward(conj))| / |inverse| = %.2e\n", #P, SMS, PAD, e); \
+        if (!(e < 3e-7)) fails++;                                                                \
+    } while (0)
 
 #define CHECK(P, SMS, PAD)                                                                       \
     do {                                                                                         \
@@ -102,6 +143,13 @@ int main() {
     using Q512 = Plan<512, 8, 8, 8, 8>;
     using Q4096 = Plan<4096, 8, 8, 8, 8, 8>;
     CHECK(Q8192, 1, 4); CHECK(Q16384, 1, 4); CHECK(Q512, 1, 3); CHECK(Q4096, 1, 3);
+    // round 2: two-pass plans of the azimuth tiles, the 32-sample 16384-point plan, and the conjugation identity
+    using P512E32 = Plan<512, 32, 32, 16, 1>;
+    using P1024E32 = Plan<1024, 32, 32, 32, 1>;
+    using P16384E32 = Plan<16384, 32, 32, 32, 16>;
+    CHECK(P512E32, 1, 0); CHECK(P512E32, 16, 0); CHECK(P1024E32, 8, 0); CHECK(P16384E32, 1, 5);
+    CHECK_CONJ(P8192, 1, 5); CHECK_CONJ(P16384E32, 1, 5); CHECK_CONJ(Q8192, 1, 4); CHECK_CONJ(P512E32, 16, 0);
+    CHECK_CONJ(P4096, 1, 4);
     printf(fails ? "FAILED %d\n" : "all ok\n", fails);
     return fails != 0;
 }

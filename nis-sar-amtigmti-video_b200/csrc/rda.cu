@@ -60,8 +60,8 @@ __global__ void __launch_bounds__(P::NT, (P::E == 32 && P::N == 8192) ? 2 : 1) k
             const int idx = t + NT * s;
             v[s] = idx < N ? p[idx] : make_float2(0.f, 0.f);
         }
-        // forward and inverse transform share ONE copy of the code: the inverse runs as conj(FFT(conj(.))), bit-identical to
-        // the conjugated-twiddle form, the conjugations folded into the filter multiply and the store (two inlined bodies of
+        // forward and inverse transform share ONE copy of the code: the inverse runs as conj(FFT(conj(.))), equal to
+        // the conjugated-twiddle form up to rounding (1e-7, csrc/hosttest), the conjugations folded into the filter multiply and the store (two inlined bodies of
         // the 32-element 16384-point plan spilled 680 bytes per thread at its 128-register cap)
 #pragma unroll 1
         for (int step = 0; step < 2; ++step) {
@@ -163,7 +163,7 @@ __global__ void __launch_bounds__(P::NT, (P::E == 32 && P::N == 8192) ? 2 : 1) k
         const float2* p = in + (int64_t)row * in_pitch;
         float2 v[E];
         // even bins, then odd bins, forward and inverse: ONE copy of the transform in the instruction stream.  The inverse is
-        // run as conj(FFT(conj(.))) -- bit-identical to the conjugated-twiddle form -- with the conjugations folded into the
+        // run as conj(FFT(conj(.))) -- the conjugated-twiddle form up to rounding -- with the conjugations folded into the
         // filter multiply and into the uses of the result.  Round 2: with four inlined transform bodies (two per branch) the
         // 32-element plan needed ~700 bytes of local memory per thread at its 128-register cap (ncu: 4.8 GB of DRAM writes
         // for a 0.76 GB pass); one body fits the registers.

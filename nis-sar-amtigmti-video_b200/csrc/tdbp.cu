@@ -49,8 +49,8 @@ __global__ void __launch_bounds__(P::NT) k_tdbp_range(const float2* __restrict__
             if (idx >= N) idx %= N;
             v[s] = p[idx];
         }
-        // forward and inverse transform share ONE copy of the code (inverse = conj FFT conj, bit-identical to the
-        // conjugated-twiddle form): two inlined bodies of the 32-element plan spilled 340 bytes per thread at 128 registers
+        // forward and inverse transform share ONE copy of the code (inverse = conj FFT conj, equal to the
+        // conjugated-twiddle form up to rounding: 1e-7, csrc/hosttest): two inlined bodies of the 32-element plan spilled 340 bytes per thread at 128 registers
 #pragma unroll 1
         for (int step = 0; step < 2; ++step) {
             transform<P, false, 1, PAD>(v, t, sm, tw);
