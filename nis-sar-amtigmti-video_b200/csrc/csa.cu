@@ -679,6 +679,7 @@ using P16384 = Plan<16384, 16, 16, 16, 8, 8>;
 // may use the whole register file (one CTA per SM either way) -- the default at 8192 samples
 using P8192E32 = Plan<8192, 32, 32, 16, 16>;
 using P512E32 = Plan<512, 32, 32, 16, 1>;
+using P4096E32 = Plan<4096, 32, 32, 16, 8>;
 using P16384E32 = Plan<16384, 32, 32, 32, 16>;
 using P1024E32 = Plan<1024, 32, 32, 32, 1>;
 
@@ -1102,9 +1103,18 @@ extern "C" int nis_csa_plan_create(nis_ctx* ctx, int32_t n_az, int32_t n_rg, con
         case 2048: pl->range = launch_range<P2048, 4, 1, 4>; FAIL_IF(upload_twiddles<P2048>(&pl->tw_rg)); break;
         // one row per CTA, several CTAs per SM: independent CTAs drift out of phase, so one CTA's shared-memory exchange
         // overlaps another's butterflies (measured: 0.096 vs 0.104 ms at 4096^2 against two row groups inside one CTA)
-        // (the rolled two-CTA form of the 8192-sample kernel below gains nothing here: 0.098 vs 0.097 ms, and three CTAs per SM
-        // at 80 registers spill: 0.119 ms)
-        case 4096: pl->range = launch_range<P4096, 4, 1, 2>; FAIL_IF(upload_twiddles<P4096>(&pl->tw_rg)); break;
+        case 4096:
+            // the rolled form with 32 samples per thread (32 x 16 x 8, 128 threads at 128 registers, FOUR CTAs per SM, next row
+            // prefetched into the exchange buffer): 0.0955 -> 0.0884 ms at 4096^2.  (The rolled form on the 16-sample plan had
+            // gained nothing: 0.098 ms.)  NIS_RANGE_PLAN=e16 keeps the straight-line 16-sample kernel reachable.
+            if (const char* v = getenv("NIS_RANGE_PLAN"); !(v && v[0] == 'e') && !pl->phase_in_az) {
+                pl->range = launch_range_rolled<P4096E32, 5, 2, 4>;
+                FAIL_IF(upload_twiddles<P4096E32>(&pl->tw_rg));
+            } else {
+                pl->range = launch_range<P4096, 4, 1, 2>;
+                FAIL_IF(upload_twiddles<P4096>(&pl->tw_rg));
+            }
+            break;
         case 8192: {
             // 32 samples per thread, three passes 32 x 16 x 16.  Default (round 2): k_range_rolled -- ONE copy of the transform
             // in the instruction stream (inverse = conj FFT conj), which ptxas fits into 128 registers without spills, so TWO
