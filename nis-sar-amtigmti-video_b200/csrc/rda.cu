@@ -44,7 +44,7 @@ static_assert(sizeof(RdaRow) == 40, "RdaRow layout");
 // (8192 points on the 32-samples-per-thread three-pass plan: 256 threads at <= 128 registers, two CTAs per SM -- the
 // arrangement of k_range_rolled in csa.cu)
 template <class P, int PAD>
-__global__ void __launch_bounds__(P::NT, (P::E == 32 && P::N == 8192) ? 2 : 1) k_rda_range(const float2* __restrict__ in, int64_t in_pitch,
+__global__ void __launch_bounds__(P::NT, (P::E == 32 && P::N == 8192) ? 2 : ((P::E == 32 && P::N == 4096) ? 4 : 1)) k_rda_range(const float2* __restrict__ in, int64_t in_pitch,
                                                      float2* __restrict__ work, int64_t work_pitch,
                                                      float2* __restrict__ rc_out, int n_rows, int N, int s0,
                                                      const float2* __restrict__ Hf, const float* __restrict__ win,
@@ -325,6 +325,7 @@ using P4096 = Plan<4096, 16, 16, 16, 16>;
 using P8192 = Plan<8192, 16, 16, 8, 8, 8>;
 using P16384 = Plan<16384, 32, 32, 32, 16>;
 using P8192E32 = Plan<8192, 32, 32, 16, 16>;
+using P4096E32 = Plan<4096, 32, 32, 16, 8>;
 
 void host_fft_pow2(std::vector<std::complex<double>>& a) {   // in-place radix-2, forward
     const size_t n = a.size();
@@ -627,7 +628,10 @@ extern "C" int nis_rda_plan_create(nis_ctx* ctx, int32_t P, int32_t S, const nis
         case 256: pl->range_fn = launch_rda_range<P256, 4>; FAIL_IF(upload_tw<P256>(&pl->tw)); break;
         case 1024: pl->range_fn = launch_rda_range<P1024, 4>; FAIL_IF(upload_tw<P1024>(&pl->tw)); break;
         case 2048: pl->range_fn = launch_rda_range<P2048, 4>; FAIL_IF(upload_tw<P2048>(&pl->tw)); break;
-        case 4096: pl->range_fn = launch_rda_range<P4096, 4>; FAIL_IF(upload_tw<P4096>(&pl->tw)); break;
+        case 4096:   // 32 samples per thread (32 x 16 x 8), 128 threads, four CTAs per SM -- as k_range_rolled at 4096 samples
+            if (getenv("NIS_RDA_E16")) { pl->range_fn = launch_rda_range<P4096, 4>; FAIL_IF(upload_tw<P4096>(&pl->tw)); }
+            else { pl->range_fn = launch_rda_range<P4096E32, 5>; FAIL_IF(upload_tw<P4096E32>(&pl->tw)); }
+            break;
         case 8192:
             if (getenv("NIS_RDA_E16")) { pl->range_fn = launch_rda_range<P8192, 4>; FAIL_IF(upload_tw<P8192>(&pl->tw)); }
             else { pl->range_fn = launch_rda_range<P8192E32, 5>; FAIL_IF(upload_tw<P8192E32>(&pl->tw)); }
